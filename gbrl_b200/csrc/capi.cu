@@ -1,0 +1,560 @@
+// capi.cu -- C-ABI (include/gbrl_b200.h): model lifetime, step / fit / predict orchestration, getters.
+//
+// Mirrors the dispatcher of the reference, class GBRL (gbrl/src/cpp/gbrl.cpp): same validation order and
+// error conditions for the calls on the hot path; the device work is delegated to the kernels in this
+// directory.  There is no CPU path: every entry point requires a CUDA device.
+#include "engine.cuh"
+#include <string.h>
+#include <algorithm>
+#include <numeric>
+#include <random>
+
+namespace gb {
+
+std::atomic<long long> g_kernel_launches{0};
+static thread_local std::string g_last_error;
+
+void dist_unique_id(uint8_t id[128]);
+void dist_init(Model &m, const uint8_t id[128], int rank, int world);
+void dist_shutdown(Model &m);
+double microbench(int which, int iters);
+
+// ---------------------------------------------------------------- DevBuf
+void DevBuf::ensure(size_t n, bool keep, cudaStream_t s) {
+    if (n <= bytes && p) return;
+    size_t nb = n;
+    if (nb < 256) nb = 256;
+    void *np = nullptr;
+    GB_CUDA(cudaMalloc(&np, nb));
+    if (keep && p && bytes) {
+        GB_CUDA(cudaMemcpyAsync(np, p, bytes, cudaMemcpyDeviceToDevice, s));
+        GB_CUDA(cudaMemsetAsync((char *)np + bytes, 0, nb - bytes, s));
+        GB_CUDA(cudaStreamSynchronize(s));
+    } else if (keep) {
+        GB_CUDA(cudaMemsetAsync(np, 0, nb, s));
+    }
+    if (p) cudaFree(p);
+    p = np; bytes = nb;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+}
+
+// ---------------------------------------------------------------- workspace
+static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const int D = m.cfg.output_dim, md = m.cfg.max_depth, B = m.cfg.n_bins;
+    ws.N = N; ws.F = F; ws.D = D; ws.depth = md; ws.B = B;
+    ws.nT = ceil_div(F, FT);
+    ws.MAXN = (2 << md) - 1;
+    // feature tiles owned by this rank (contiguous block)
+    ws.tile_lo = (int)((long long)ws.nT * m.rank / m.world);
+    ws.tile_hi = (int)((long long)ws.nT * (m.rank + 1) / m.world);
+    const size_t n1 = (size_t)(N > 0 ? N : 1);
+    ws.order[0].ensure(n1 * sizeof(int)); ws.order[1].ensure(n1 * sizeof(int));
+    ws.nid.ensure(n1 * sizeof(int)); ws.rflag.ensure(n1); ws.rscan.ensure(n1 * sizeof(int));
+    ws.chunk_sums.ensure((size_t)(ceil_div((int)n1, 2048) + 1) * sizeof(int));
+    const int lv = md > 0 ? md - 1 : 0;
+    const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + D) * sizeof(long long);
+    ws.hist[0].ensure(slot_bytes << lv); ws.hist[1].ensure(slot_bytes << lv);
+    const size_t C = (size_t)F * B;
+    ws.scores.ensure((C << lv) * sizeof(float));
+    ws.cand_flags.ensure(C << lv);
+    ws.obl_tot.ensure(C * sizeof(float));
+    size_t tb = (size_t)ws.nT << lv;
+    if (tb < C / 256 + 1) tb = C / 256 + 1;
+    ws.tile_best.ensure(tb * sizeof(float2));
+    ws.items_cap = (N / ITEM_ROWS + (1 << md) + 1) * (ws.tile_hi - ws.tile_lo > 0 ? ws.tile_hi - ws.tile_lo : 1);
+    ws.items.ensure((size_t)ws.items_cap * sizeof(Item));
+    ws.replay_cap = 1 << 18;
+    if ((size_t)ws.replay_cap < 4 * ((size_t)1 << md)) ws.replay_cap = 4 << md;
+    ws.replay.ensure((size_t)ws.replay_cap * (sizeof(ReplayItem) + sizeof(int)));
+    ws.replay_scores.ensure((size_t)ws.replay_cap * sizeof(float));
+    // node arrays carved from one allocation
+    const size_t MN = ws.MAXN;
+    const size_t bytes = MN * D * sizeof(long long) + MN * 10 * sizeof(int) + MN * 4 * sizeof(float);
+    ws.nodes.ensure(bytes);
+    char *p = ws.nodes.as<char>();
+    ws.na.tot_sum = (long long *)p; p += MN * D * sizeof(long long);
+    int **ip[] = {&ws.na.seg_start, &ws.na.seg_len, &ws.na.state, &ws.na.split_f, &ws.na.split_j,
+                  &ws.na.direct, &ws.na.rep_begin, &ws.na.rep_count, &ws.na.best_idx, &ws.na.leaf_index};
+    for (auto q : ip) { *q = (int *)p; p += MN * sizeof(int); }
+    float **fp[] = {&ws.na.split_thr, &ws.na.best_gain, &ws.na.parent_score, &ws.na.band};
+    for (auto q : fp) { *q = (float *)p; p += MN * sizeof(float); }
+    (void)s;
+}
+
+static const float *stage_in(DevBuf &buf, const float *ptr, int is_dev, size_t count, cudaStream_t s) {
+    if (is_dev) return ptr;
+    buf.ensure((count > 0 ? count : 1) * sizeof(float));
+    if (count) GB_CUDA(cudaMemcpyAsync(buf.p, ptr, count * sizeof(float), cudaMemcpyHostToDevice, s));
+    return buf.as<float>();
+}
+
+static void sync_ctl(Model &m, cudaStream_t s) {
+    Ctl h;
+    GB_CUDA(cudaMemcpyAsync(&h, m.ws.ctl.p, sizeof(Ctl), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    m.ens.n_leaves = h.n_leaves;
+    m.ens.n_leaves_ub = h.n_leaves;
+    GB_CHECK(h.n_trees == m.ens.n_trees, "internal error: device/host tree count mismatch");
+    m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
+    m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
+}
+
+static void check_features(Model &m, int n_features) {
+    // gbrl.cpp:946-957: the feature split is latched at iteration 0
+    if (m.iteration == 0) { m.n_num_features = n_features; m.n_cat_features = 0; }
+    GB_CHECK(n_features == m.n_num_features && m.n_cat_features == 0,
+             "Incompatible dataset: feature count differs from the one the ensemble was started with");
+    GB_CHECK(n_features == m.cfg.input_dim, "Incompatible dataset: n_num_features + n_cat_features != input_dim");
+}
+
+static void do_step(Model &m, const float *obs, int obs_dev, const float *grads, int grads_dev, int N, int F, cudaStream_t s) {
+    GB_CHECK(N > 0, "step: n_samples must be positive");
+    check_features(m, F);
+    GB_CUDA(cudaSetDevice(m.device));
+    Workspace &ws = m.ws;
+    const int D = m.cfg.output_dim;
+    const float *X = stage_in(ws.xstage, obs, obs_dev, (size_t)N * F, s);
+    const float *G = stage_in(ws.gstage, grads, grads_dev, (size_t)N * D, s);
+    prepare_workspace(m, N, F, s);
+    compute_thresholds(m, X, N, F, s);          // fitter.cpp:72-90: candidates from the current observations
+    ws.codes_rows = N; ws.row_offset = 0;
+    bin_features(m, X, N, F, s);
+    build_grads(m, G, N, s);                    // fitter.cpp:57-64
+    grow_tree(m, X, G, N, F, s);                // fitter.cpp:98-102
+    sync_ctl(m, s);
+    m.iteration++;                              // fitter.cpp:114
+}
+
+__global__ void fill_rows_kernel(float *dst, const float *bias, long long n, int D) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n * D; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = bias[i % D];
+}
+__global__ void gather_rows_kernel(const float *src, const int *perm, float *dst, int N, int W) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)N * W; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[(size_t)perm[i / W] * W + i % W];
+}
+
+static float do_fit(Model &m, const float *obs, int obs_dev, const float *targets, int targets_dev, int iterations, int N, int F,
+                    int shuffle, cudaStream_t s) {
+    GB_CHECK(N > 0, "fit: n_samples must be positive");
+    GB_CHECK(iterations >= 0, "fit: iterations must be >= 0");
+    check_features(m, F);
+    GB_CHECK(!m.opts.empty(), "fit: no optimizers set");
+    GB_CUDA(cudaSetDevice(m.device));
+    Workspace &ws = m.ws;
+    const int D = m.cfg.output_dim, bs = m.cfg.batch_size;
+    GB_CHECK(bs > 0, "fit: batch_size must be positive");
+    const float *X = stage_in(ws.xstage, obs, obs_dev, (size_t)N * F, s);
+    const float *Tg = stage_in(ws.tstage, targets, targets_dev, (size_t)N * D, s);
+    DevBuf xs, ts, permbuf;
+    if (shuffle) {
+        // gbrl.cpp:1017-1026: the reference shuffles with std::random_device (not reproducible); we do the same
+        std::vector<int> perm(N);
+        std::iota(perm.begin(), perm.end(), 0);
+        std::random_device rd; std::mt19937 g(rd());
+        std::shuffle(perm.begin(), perm.end(), g);
+        permbuf.ensure((size_t)N * sizeof(int)); xs.ensure((size_t)N * F * sizeof(float)); ts.ensure((size_t)N * D * sizeof(float));
+        GB_CUDA(cudaMemcpyAsync(permbuf.p, perm.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, s));
+        GB_LAUNCH(gather_rows_kernel, 1184, 256, 0, s, X, permbuf.as<int>(), xs.as<float>(), N, F);
+        GB_LAUNCH(gather_rows_kernel, 1184, 256, 0, s, Tg, permbuf.as<int>(), ts.as<float>(), N, D);
+        GB_CUDA(cudaStreamSynchronize(s));
+        X = xs.as<float>(); Tg = ts.as<float>();
+    }
+    prepare_workspace(m, N, F, s);
+    // gbrl.cpp:1076-1078: bias := column mean of the targets (reference thread partition emulated)
+    column_mean_ref(m, Tg, N, D, m.bias.as<float>(), s);
+    m.h_bias.resize(D);
+    GB_CUDA(cudaMemcpyAsync(m.h_bias.data(), m.bias.p, D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // fitter.cpp:134-151: candidates ONCE on the full data
+    compute_thresholds(m, X, N, F, s);
+    ws.codes_rows = N; ws.row_offset = 0;
+    bin_features(m, X, N, F, s);
+    const int n_trees0 = m.ens.n_trees;
+    const bool incremental = (n_trees0 == 0);
+    ws.preds_full.ensure((size_t)N * D * sizeof(float));
+    // two gradient buffers like the reference (regular / last batch), zero-initialised once (fitter.cpp:125-130)
+    const size_t gsz = (size_t)(bs < N ? bs : N) * D;
+    ws.grads_fit.ensure((gsz + (size_t)(N % bs) * D + 2) * sizeof(float));
+    GB_CUDA(cudaMemsetAsync(ws.grads_fit.p, 0, ws.grads_fit.bytes, s));
+    float *g_regular = ws.grads_fit.as<float>(), *g_last = g_regular + gsz;
+    if (incremental) GB_LAUNCH(fill_rows_kernel, 1184, 256, 0, s, ws.preds_full.as<float>(), m.bias.as<float>(), (long long)N, D);
+    int batch_start = 0;
+    int batch_n = batch_start + bs < N ? bs : N - batch_start;
+    DevBuf batch_preds;
+    for (int it = 0; it < iterations; ++it) {
+        const float *bX = X + (size_t)batch_start * F;
+        const float *bT = Tg + (size_t)batch_start * D;
+        const bool is_last = batch_start + bs > N;
+        float *grads = is_last ? g_last : g_regular;
+        const float *preds;
+        if (incremental) {
+            preds = ws.preds_full.as<float>() + (size_t)batch_start * D;
+        } else {
+            // fitter.cpp:191: predict_cpu(batch, 0, i): stop index 0 means "all trees"
+            batch_preds.ensure((size_t)batch_n * D * sizeof(float));
+            const int stop = (it == 0) ? m.ens.n_trees : std::min(it, m.ens.n_trees);
+            launch_predict(m, bX, batch_n, F, 0, stop, batch_preds.as<float>(), true, s);
+            preds = batch_preds.as<float>();
+        }
+        multirmse_grads(m, preds, bT, grads, batch_n, s);      // fitter.cpp:193-195
+        // the tree is grown on the batch rows: order/nid are batch-relative, codes are addressed with row_offset
+        ws.N = batch_n; ws.row_offset = batch_start;
+        build_grads(m, grads, batch_n, s);                     // fitter.cpp:203-214
+        grow_tree(m, bX, grads, batch_n, F, s);                // fitter.cpp:220-225
+        if (incremental) launch_update_preds_last_tree(m, X, N, F, ws.preds_full.as<float>(), s);
+        batch_start += batch_n;                                // fitter.cpp:227-230
+        if (batch_start >= N) batch_start = 0;
+        batch_n = batch_start + bs < N ? bs : N - batch_start;
+        m.iteration++;
+    }
+    ws.N = N; ws.row_offset = 0;
+    // fitter.cpp:244-250: full-data loss over trees [0, iterations)
+    float loss = INFINITY;
+    const float *fp;
+    if (incremental) fp = ws.preds_full.as<float>();
+    else {
+        batch_preds.ensure((size_t)N * D * sizeof(float));
+        const int stop = (iterations == 0) ? m.ens.n_trees : std::min(iterations, m.ens.n_trees);
+        launch_predict(m, X, N, F, 0, stop, batch_preds.as<float>(), true, s);
+        fp = batch_preds.as<float>();
+    }
+    multirmse_loss(m, fp, Tg, N, &loss, s);
+    sync_ctl(m, s);
+    return loss;
+}
+
+static void do_predict(Model &m, const float *obs, int obs_dev, int N, int F, int start_tree, int stop_tree, float *preds,
+                       int preds_dev, cudaStream_t s) {
+    // gbrl.cpp:369-422 + binding.cpp:800-811
+    GB_CHECK(N > 0, "predict: n_samples must be positive");
+    if (m.iteration == 0) { m.n_num_features = F; m.n_cat_features = 0; }
+    GB_CHECK(F == m.cfg.input_dim, "Incompatible dataset: n_num_features + n_cat_features != input_dim");
+    GB_CHECK(F == m.n_num_features, "Incompatible dataset: feature layout differs from the ensemble's");
+    GB_CHECK(start_tree >= 0 && stop_tree >= 0, "predict: tree indices must be non-negative");
+    GB_CUDA(cudaSetDevice(m.device));
+    const int D = m.cfg.output_dim;
+    const int n_trees = m.ens.n_trees;
+    GB_CHECK(stop_tree <= n_trees, "predict: stop_tree_idx greater than number of trees in model");
+    GB_CHECK(start_tree <= n_trees, "predict: start_tree_idx greater than number of trees in model");
+    if (stop_tree == 0) stop_tree = n_trees;
+    Workspace &ws = m.ws;
+    const float *X = stage_in(ws.xstage, obs, obs_dev, (size_t)N * F, s);
+    float *out = preds;
+    if (!preds_dev) { ws.pstage.ensure((size_t)N * D * sizeof(float)); out = ws.pstage.as<float>(); }
+    const bool have_opts = !m.opts.empty();
+    // predictor.cpp:122-140: bias is always added; trees only if there are trees and optimizers
+    launch_predict(m, X, N, F, start_tree, (n_trees > 0 && have_opts) ? stop_tree : start_tree, out, true, s);
+    if (!preds_dev) GB_CUDA(cudaMemcpyAsync(preds, out, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace gb
+
+// ====================================================================================================
+using namespace gb;
+struct gbrl_b200_model { Model m; };
+
+#define API_BEGIN try {
+#define API_END                                   \
+    return 0;                                     \
+    } catch (const std::exception &e) {           \
+        gb::g_last_error = e.what();              \
+        return 1;                                 \
+    } catch (...) {                               \
+        gb::g_last_error = "unknown error";       \
+        return 1;                                 \
+    }
+
+extern "C" {
+
+const char *gbrl_b200_last_error(void) { return gb::g_last_error.c_str(); }
+
+int gbrl_b200_cuda_available(void) {
+    int n = 0;
+    return (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) ? 1 : 0;
+}
+
+int gbrl_b200_create(const gbrl_b200_config *cfg, gbrl_b200_model **out) {
+    API_BEGIN
+    GB_CHECK(cfg && out, "null argument");
+    GB_CHECK(gbrl_b200_cuda_available(), "no CUDA device: this engine has no CPU fallback");
+    GB_CHECK(cfg->input_dim > 0 && cfg->output_dim > 0, "input_dim and output_dim must be positive");
+    GB_CHECK(cfg->output_dim <= 64, "output_dim > 64 is not supported by this engine yet");
+    GB_CHECK(cfg->max_depth >= 0 && cfg->max_depth <= MAX_DEPTH_SUPPORTED, "max_depth must be in [0, 12]");
+    GB_CHECK(cfg->n_bins >= 1 && cfg->n_bins <= NB, "n_bins must be in [1, 256]");
+    GB_CHECK(cfg->split_score_func == 0 || cfg->split_score_func == 1, "invalid split_score_func");
+    GB_CHECK(cfg->generator_type == 0 || cfg->generator_type == 1, "invalid generator_type");
+    GB_CHECK(cfg->grow_policy == 0 || cfg->grow_policy == 1, "invalid grow_policy");
+    int ndev = 0;
+    GB_CUDA(cudaGetDeviceCount(&ndev));
+    GB_CHECK(cfg->device_ordinal >= 0 && cfg->device_ordinal < ndev, "invalid device ordinal");
+    GB_CUDA(cudaSetDevice(cfg->device_ordinal));
+    auto *h = new gbrl_b200_model();
+    Model &m = h->m;
+    m.cfg = *cfg;
+    if (m.cfg.ref_threads < 1) m.cfg.ref_threads = 1;
+    if (m.cfg.par_th < 1) m.cfg.par_th = 1;
+    m.device = cfg->device_ordinal;
+    const int I = cfg->input_dim, D = cfg->output_dim;
+    m.bias.ensure(D * sizeof(float), true); m.feature_weights.ensure(I * sizeof(float), true);
+    m.rev_num_map.ensure(I * sizeof(int), true);      // zero until set_feature_mapping (types.cpp:232-234)
+    m.h_bias.assign(D, 0.0f); m.h_fw.assign(I, 0.0f);
+    m.h_mapping.assign(I, 0); m.h_rev_num.assign(I, 0); m.h_rev_cat.assign(I, 0); m.h_numerics.assign(I, 0);
+    m.ws.ctl.ensure(sizeof(Ctl), true);
+    GB_CUDA(cudaDeviceSynchronize());
+    *out = h;
+    API_END
+}
+
+void gbrl_b200_destroy(gbrl_b200_model *h) {
+    if (!h) return;
+    try { gb::dist_shutdown(h->m); } catch (...) {}
+    delete h;
+}
+
+int gbrl_b200_set_bias(gbrl_b200_model *h, const float *bias, int n, int dev) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CHECK(n == m.cfg.output_dim, "Incompatible dimensions: bias");
+    GB_CUDA(cudaSetDevice(m.device));
+    GB_CUDA(cudaMemcpy(m.bias.p, bias, n * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    GB_CUDA(cudaMemcpy(m.h_bias.data(), m.bias.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    API_END
+}
+
+int gbrl_b200_set_feature_weights(gbrl_b200_model *h, const float *w, int n, int dev) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CHECK(n == m.cfg.input_dim, "Incompatible dimensions: feature_weights");
+    GB_CUDA(cudaSetDevice(m.device));
+    GB_CUDA(cudaMemcpy(m.feature_weights.p, w, n * sizeof(float), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    GB_CUDA(cudaMemcpy(m.h_fw.data(), m.feature_weights.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+    API_END
+}
+
+int gbrl_b200_set_feature_mapping(gbrl_b200_model *h, const int *mapping, const uint8_t *numerics, int n) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CHECK(n == m.cfg.input_dim, "Incompatible dimensions: feature_mapping");
+    // gbrl.cpp:280-293
+    int j = 0, k = 0;
+    for (int i = 0; i < n; ++i) { m.h_rev_num[i] = -1; m.h_rev_cat[i] = -1; }
+    for (int i = 0; i < n; ++i) {
+        m.h_mapping[i] = mapping[i]; m.h_numerics[i] = numerics[i] ? 1 : 0;
+        if (numerics[i]) m.h_rev_num[j++] = i; else m.h_rev_cat[k++] = i;
+    }
+    GB_CUDA(cudaSetDevice(m.device));
+    GB_CUDA(cudaMemcpy(m.rev_num_map.p, m.h_rev_num.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    API_END
+}
+
+int gbrl_b200_get_bias(gbrl_b200_model *h, float *out) {
+    API_BEGIN
+    memcpy(out, h->m.h_bias.data(), h->m.cfg.output_dim * sizeof(float));
+    API_END
+}
+int gbrl_b200_get_feature_weights(gbrl_b200_model *h, float *out) {
+    API_BEGIN
+    memcpy(out, h->m.h_fw.data(), h->m.cfg.input_dim * sizeof(float));
+    API_END
+}
+int gbrl_b200_get_feature_mapping(gbrl_b200_model *h, int *mapping, uint8_t *numerics, int *rev_num, int *rev_cat) {
+    API_BEGIN
+    Model &m = h->m;
+    const int n = m.cfg.input_dim;
+    if (mapping) memcpy(mapping, m.h_mapping.data(), n * sizeof(int));
+    if (numerics) memcpy(numerics, m.h_numerics.data(), n);
+    if (rev_num) memcpy(rev_num, m.h_rev_num.data(), n * sizeof(int));
+    if (rev_cat) memcpy(rev_cat, m.h_rev_cat.data(), n * sizeof(int));
+    API_END
+}
+
+int gbrl_b200_set_optimizer(gbrl_b200_model *h, int scheduler, float init_lr, int start_idx, int stop_idx, float stop_lr, int T) {
+    API_BEGIN
+    Model &m = h->m;
+    // gbrl.cpp:457-471
+    GB_CHECK((int)m.opts.size() < m.cfg.output_dim && (int)m.opts.size() < MAX_OPTS, "Optimizer Limit Reached");
+    GB_CHECK(start_idx < stop_idx, "invalid index ranges");
+    GB_CHECK(!(start_idx < 0 || stop_idx <= 0 || start_idx >= m.cfg.output_dim || stop_idx > m.cfg.output_dim), "invalid index ranges");
+    GB_CHECK(scheduler == GBRL_B200_SCHED_CONST || scheduler == GBRL_B200_SCHED_LINEAR, "Unrecognized scheduler func");
+    Optimizer o; o.sched = scheduler; o.init_lr = init_lr; o.start_idx = start_idx; o.stop_idx = stop_idx; o.stop_lr = stop_lr; o.T = T;
+    m.opts.push_back(o);
+    GB_CUDA(cudaSetDevice(m.device));
+    upload_optimizers(m, 0);
+    API_END
+}
+int gbrl_b200_n_optimizers(gbrl_b200_model *h) { return (int)h->m.opts.size(); }
+int gbrl_b200_get_optimizer(gbrl_b200_model *h, int i, int *scheduler, float *init_lr, int *start_idx, int *stop_idx, float *stop_lr, int *T) {
+    API_BEGIN
+    GB_CHECK(i >= 0 && i < (int)h->m.opts.size(), "optimizer index out of range");
+    const Optimizer &o = h->m.opts[i];
+    *scheduler = o.sched; *init_lr = o.init_lr; *start_idx = o.start_idx; *stop_idx = o.stop_idx; *stop_lr = o.stop_lr; *T = o.T;
+    API_END
+}
+int gbrl_b200_get_scheduler_lrs(gbrl_b200_model *h, float *out) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CHECK(!m.opts.empty(), "No optimizers found");
+    const int t = m.ens.n_trees;
+    for (size_t i = 0; i < m.opts.size(); ++i) {
+        const Optimizer &o = m.opts[i];
+        float lr = o.init_lr;
+        if (o.sched == GBRL_B200_SCHED_LINEAR) {
+            float T_ = (float)o.T, t_ = (float)t + 1;
+            float pr = (T_ - t_) / T_;
+            lr = o.init_lr + (1.0f - pr) * (o.stop_lr - o.init_lr);
+            if (lr < o.stop_lr) lr = o.stop_lr;
+        }
+        out[i] = lr;
+    }
+    API_END
+}
+
+int gbrl_b200_step(gbrl_b200_model *h, const float *obs, int obs_dev, const float *grads, int grads_dev, int n_samples,
+                   int n_features, void *stream) {
+    API_BEGIN
+    GB_CHECK(h && obs && grads, "null argument");
+    gb::do_step(h->m, obs, obs_dev, grads, grads_dev, n_samples, n_features, (cudaStream_t)stream);
+    API_END
+}
+
+int gbrl_b200_fit(gbrl_b200_model *h, const float *obs, int obs_dev, const float *targets, int targets_dev, int iterations,
+                  int n_samples, int n_features, int shuffle, float *loss_out, void *stream) {
+    API_BEGIN
+    GB_CHECK(h && obs && targets, "null argument");
+    const float l = gb::do_fit(h->m, obs, obs_dev, targets, targets_dev, iterations, n_samples, n_features, shuffle, (cudaStream_t)stream);
+    if (loss_out) *loss_out = l;
+    API_END
+}
+
+int gbrl_b200_predict(gbrl_b200_model *h, const float *obs, int obs_dev, int n_samples, int n_features, int start_tree_idx,
+                      int stop_tree_idx, float *preds, int preds_dev, void *stream) {
+    API_BEGIN
+    GB_CHECK(h && obs && preds, "null argument");
+    gb::do_predict(h->m, obs, obs_dev, n_samples, n_features, start_tree_idx, stop_tree_idx, preds, preds_dev, (cudaStream_t)stream);
+    API_END
+}
+
+int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
+    API_BEGIN
+    Model &m = h->m;
+    memset(o, 0, sizeof(*o));
+    o->input_dim = m.cfg.input_dim; o->output_dim = m.cfg.output_dim; o->policy_dim = m.cfg.policy_dim;
+    o->max_depth = m.cfg.max_depth; o->min_data_in_leaf = m.cfg.min_data_in_leaf; o->n_bins = m.cfg.n_bins;
+    o->par_th = m.cfg.par_th; o->batch_size = m.cfg.batch_size; o->split_score_func = m.cfg.split_score_func;
+    o->generator_type = m.cfg.generator_type; o->grow_policy = m.cfg.grow_policy; o->verbose = m.cfg.verbose;
+    o->n_num_features = m.n_num_features; o->n_cat_features = m.n_cat_features; o->n_trees = m.ens.n_trees;
+    o->n_leaves = m.ens.n_leaves; o->iteration = m.iteration;
+    o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
+    o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated;
+    API_END
+}
+
+int gbrl_b200_get_ensemble(gbrl_b200_model *h, int *tree_indices, int *depths, float *values, int *feature_indices,
+                           float *feature_values, float *edge_weights, uint8_t *inequality_directions) {
+    API_BEGIN
+    Model &m = h->m;
+    Ensemble &e = m.ens;
+    GB_CUDA(cudaSetDevice(m.device));
+    const int md = m.cfg.max_depth, D = m.cfg.output_dim;
+    const size_t S = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? e.n_trees : e.n_leaves;
+    if (e.n_trees == 0) return 0;
+    GB_CUDA(cudaMemcpy(tree_indices, e.tree_indices.p, e.n_trees * sizeof(int), cudaMemcpyDeviceToHost));
+    GB_CUDA(cudaMemcpy(depths, e.depths.p, S * sizeof(int), cudaMemcpyDeviceToHost));
+    GB_CUDA(cudaMemcpy(values, e.values.p, (size_t)e.n_leaves * D * sizeof(float), cudaMemcpyDeviceToHost));
+    if (md > 0) {
+        GB_CUDA(cudaMemcpy(feature_indices, e.feature_indices.p, S * md * sizeof(int), cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(feature_values, e.feature_values.p, S * md * sizeof(float), cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(edge_weights, e.edge_weights.p, (size_t)e.n_leaves * md * sizeof(float), cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(inequality_directions, e.ineq.p, (size_t)e.n_leaves * md, cudaMemcpyDeviceToHost));
+    }
+    API_END
+}
+
+__global__ void set_ctl_counts_kernel(Ctl *ctl, int n_trees, int n_leaves) { ctl->n_trees = n_trees; ctl->n_leaves = n_leaves; }
+
+int gbrl_b200_set_ensemble(gbrl_b200_model *h, int n_trees, int n_leaves, const int *tree_indices, const int *depths,
+                           const float *values, const int *feature_indices, const float *feature_values,
+                           const float *edge_weights, const uint8_t *inequality_directions, int n_num_features) {
+    API_BEGIN
+    Model &m = h->m;
+    Ensemble &e = m.ens;
+    GB_CUDA(cudaSetDevice(m.device));
+    GB_CHECK(n_trees >= 0 && n_leaves >= 0, "negative sizes");
+    const int md = m.cfg.max_depth, D = m.cfg.output_dim;
+    e.n_trees = 0; e.n_leaves = 0;
+    // make room (capacity is computed from tree counts; leaves may exceed trees * 2^md only if inconsistent)
+    GB_CHECK((long long)n_leaves <= (long long)n_trees * (1 << md), "inconsistent ensemble: too many leaves");
+    ensure_ensemble_capacity(m, n_trees > 0 ? n_trees : 1, 0);
+    const size_t S = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? n_trees : n_leaves;
+    if (n_trees > 0) {
+        GB_CUDA(cudaMemcpy(e.tree_indices.p, tree_indices, n_trees * sizeof(int), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemcpy(e.depths.p, depths, S * sizeof(int), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemcpy(e.values.p, values, (size_t)n_leaves * D * sizeof(float), cudaMemcpyHostToDevice));
+        if (md > 0) {
+            GB_CUDA(cudaMemcpy(e.feature_indices.p, feature_indices, S * md * sizeof(int), cudaMemcpyHostToDevice));
+            GB_CUDA(cudaMemcpy(e.feature_values.p, feature_values, S * md * sizeof(float), cudaMemcpyHostToDevice));
+            GB_CUDA(cudaMemcpy(e.edge_weights.p, edge_weights, (size_t)n_leaves * md * sizeof(float), cudaMemcpyHostToDevice));
+            GB_CUDA(cudaMemcpy(e.ineq.p, inequality_directions, (size_t)n_leaves * md, cudaMemcpyHostToDevice));
+        }
+    }
+    e.n_trees = n_trees; e.n_leaves = n_leaves; e.n_leaves_ub = n_leaves;
+    GB_LAUNCH(set_ctl_counts_kernel, 1, 1, 0, 0, m.ws.ctl.as<Ctl>(), n_trees, n_leaves);
+    rebuild_heap_topology(m, 0);
+    GB_CUDA(cudaDeviceSynchronize());
+    m.n_num_features = n_num_features; m.n_cat_features = 0;
+    if (n_trees > 0 && m.iteration == 0) m.iteration = n_trees;
+    API_END
+}
+
+int gbrl_b200_get_candidates(gbrl_b200_model *h, float *thresholds, int *n_candidates) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CHECK(m.have_candidates, "no candidates computed yet");
+    GB_CUDA(cudaSetDevice(m.device));
+    const int C = m.ws.F * m.ws.B;
+    if (thresholds) GB_CUDA(cudaMemcpy(thresholds, m.ws.thr.p, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost));
+    if (n_candidates) *n_candidates = C;
+    API_END
+}
+
+int gbrl_b200_get_root_scores(gbrl_b200_model *h, float *scores, int *n_candidates) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CHECK(m.have_candidates, "no tree grown yet");
+    GB_CUDA(cudaSetDevice(m.device));
+    const int C = m.ws.F * m.ws.B;
+    if (scores) GB_CUDA(cudaMemcpy(scores, m.ws.scores.p, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost));
+    if (n_candidates) *n_candidates = C;
+    API_END
+}
+
+int gbrl_b200_dist_unique_id(uint8_t id[128]) {
+    API_BEGIN
+    gb::dist_unique_id(id);
+    API_END
+}
+int gbrl_b200_dist_init(gbrl_b200_model *h, const uint8_t id[128], int rank, int world_size) {
+    API_BEGIN
+    GB_CHECK(world_size >= 1 && rank >= 0 && rank < world_size, "invalid rank / world size");
+    GB_CUDA(cudaSetDevice(h->m.device));
+    gb::dist_init(h->m, id, rank, world_size);
+    API_END
+}
+int gbrl_b200_dist_shutdown(gbrl_b200_model *h) {
+    API_BEGIN
+    gb::dist_shutdown(h->m);
+    API_END
+}
+
+int gbrl_b200_microbench(int which, int iters, double *result) {
+    API_BEGIN
+    *result = gb::microbench(which, iters);
+    API_END
+}
+
+}  // extern "C"

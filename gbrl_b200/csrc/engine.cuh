@@ -1,0 +1,152 @@
+// engine.cuh -- internal data structures of the B200 fit/predict engine.
+//
+// HBM layout (all device-resident for the lifetime of a step()/fit() call):
+//   X        [N x F]  fp32 row-major      caller's matrix (borrowed or staged copy)      node.cpp:339
+//   codes    [nT][N][32] u16              per-feature-tile candidate-bin codes of X:
+//                                         code(x) = #{j : thr[f][j] < x} in [0, n_bins]
+//                                         (x > thr[f][j]  <=>  code > j); 64 B per row and tile
+//   bg       [N x D]  fp32                build_grads (fitter.cpp:57-64)
+//   order    [N] int32 (ping-pong)        rows grouped by tree node, ascending inside a node
+//                                         (== the reference's per-node sample_indices, node.cpp:86-96)
+//   nid      [N] int32                    heap id of the node each row currently sits in
+//   hist     [slot][nT][256][32][1+D] i64 per-node (count, sum of fixed-point build_grads) per
+//                                         (feature, code-1); two level buffers (parent / current)
+//   scores   [slot][F*n_bins] fp32        per-(node,candidate) score (exact-arithmetic path)
+#pragma once
+#include "common.cuh"
+#include "../../include/gbrl_b200.h"
+#include <vector>
+
+namespace gb {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t n, bool keep = false, cudaStream_t s = 0);
+    void release();
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+enum NodeState : int { NODE_NONE = 0, NODE_OPEN = 1, NODE_LEAF = 2, NODE_SPLIT = 3 };
+
+struct Item {          // one histogram work item: rows [k0,k1) of `order` (all in one node) x one tile
+    int slot, tile, k0, k1;
+};
+struct ReplayItem {    // re-score (node, candidate) in the reference's sequential order; cand -1 = parent
+    int node, cand;
+};
+
+// device-side control block (one per model workspace); everything the level pipeline needs to decide
+// without a host round trip
+struct Ctl {
+    int n_items;             // histogram items of the current level
+    int n_replay;            // replay items of the current level
+    int replay_overflow;
+    int qexp;                // fixed-point exponent of build_grads: q = rint(g * 2^qexp)
+    int qexp_raw;            // same for the raw gradients (leaf values)
+    unsigned int max_abs_bg; // float bits of max |bg|
+    unsigned int max_abs_raw;
+    int n_leaves;            // running leaf count of the ensemble (device copy)
+    int n_trees;
+    int tree_leaves;         // leaves of the tree being finalised
+    int obl_best_idx;        // oblivious: chosen candidate of the level (-1: stop)
+    float obl_best;
+    int obl_depth;           // oblivious: depth reached
+    int obl_has_replay;
+    float obl_band;
+    long long stat_replay_items, stat_replay_nodes, stat_nodes_evaluated, stat_replay_overflow;
+};
+
+// per-node arrays, heap indexed, MAXN = 2^(max_depth+1)-1 entries each
+struct NodeArrays {
+    int *seg_start, *seg_len, *state, *split_f, *split_j, *direct, *rep_begin, *rep_count, *best_idx;
+    float *split_thr, *best_gain, *parent_score, *band;
+    long long *tot_sum;      // [MAXN x D] fixed-point sum of build_grads of the node
+    int *leaf_index;         // leaf number inside the tree (DFS-left-first), -1 for internal nodes
+};
+
+struct Optimizer {
+    int sched, start_idx, stop_idx, T;
+    float init_lr, stop_lr;
+};
+
+struct Ensemble {            // reference layout, types.h:279-304 (numerical features only)
+    DevBuf tree_indices, depths, values, feature_indices, feature_values, edge_weights, ineq;
+    // auxiliary per-tree heap topology for the O(depth) walk used by the greedy predict kernel
+    DevBuf heap_feat, heap_thr, heap_leaf;
+    int cap_trees = 0, cap_leaves = 0;
+    int n_trees = 0, n_leaves = 0;
+    long long n_leaves_ub = 0;   // host-side upper bound of n_leaves while trees are grown without a host sync
+};
+
+struct Workspace {           // sized for (N, F, D, depth); reused across calls with the same shape
+    int N = 0, F = 0, nT = 0, D = 0, depth = 0, MAXN = 0, B = 0;
+    int tile_lo = 0, tile_hi = 0;   // feature tiles owned by this rank [tile_lo, tile_hi)
+    int codes_rows = 0;             // rows of the code matrix (tile stride); >= N when a tree is grown on a mini-batch
+    int row_offset = 0;             // first row of the current mini-batch inside the code matrix
+    DevBuf codes, thr, thrT, bg, order[2], nid, rflag, rscan, chunk_sums, hist[2], scores, cand_flags;
+    DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
+    DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage;
+    NodeArrays na{};
+    size_t sort_tmp_bytes = 0;
+    int replay_cap = 0, items_cap = 0;
+};
+
+struct Model {
+    gbrl_b200_config cfg{};
+    int device = 0;
+    int n_num_features = 0, n_cat_features = 0, iteration = 0;
+    Ensemble ens;
+    std::vector<Optimizer> opts;
+    DevBuf bias, feature_weights, rev_num_map, d_opts;
+    std::vector<float> h_bias, h_fw;
+    std::vector<int> h_mapping, h_rev_num, h_rev_cat;
+    std::vector<uint8_t> h_numerics;
+    Workspace ws;
+    // multi-GPU
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    // statistics
+    long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0;
+    bool have_candidates = false;
+};
+
+// ---------------------------------------------------------------- kernel launchers (one per .cu)
+// candidates.cu
+void compute_thresholds(Model &m, const float *X, int N, int F, cudaStream_t s);
+void bin_features(Model &m, const float *X, int N, int F, cudaStream_t s);
+// preprocess.cu
+void build_grads(Model &m, const float *grads, int N, cudaStream_t s);          // -> ws.bg, ctl.qexp
+void column_mean_ref(Model &m, const float *mat, int N, int D, float *out_dev, cudaStream_t s);
+void multirmse_grads(Model &m, const float *preds, const float *targets, float *grads, int n, cudaStream_t s);
+void multirmse_loss(Model &m, const float *preds, const float *targets, int n, float *loss_host, cudaStream_t s);
+void raw_grad_scale(Model &m, const float *grads, int N, cudaStream_t s);       // -> ctl.qexp_raw
+// tree growth
+void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, cudaStream_t s);
+// histogram.cu
+void launch_plan_level(Model &m, int level, cudaStream_t s);
+void launch_histogram(Model &m, int level, cudaStream_t s);
+// split.cu
+void launch_scan(Model &m, int level, cudaStream_t s);
+void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s);
+void launch_decide(Model &m, int level, cudaStream_t s);
+// partition.cu
+void launch_partition(Model &m, const float *X, int level, int cur, cudaStream_t s);
+// tree.cu
+void launch_init_tree(Model &m, int N, cudaStream_t s);
+void launch_finalize_tree(Model &m, const float *raw_grads, int N, int cur, cudaStream_t s);
+void ensure_ensemble_capacity(Model &m, int extra_trees, cudaStream_t s);
+// predict.cu
+void launch_predict(Model &m, const float *X, int N, int F, int start_tree, int stop_tree, float *preds, bool add_bias,
+                    cudaStream_t s);
+void launch_update_preds_last_tree(Model &m, const float *X, int N, int F, float *preds, cudaStream_t s);
+void upload_optimizers(Model &m, cudaStream_t s);
+void rebuild_heap_topology(Model &m, cudaStream_t s);
+// dist.cu
+void dist_allreduce_hist(Model &m, long long *buf, size_t count, cudaStream_t s);
+
+}  // namespace gb

@@ -1,0 +1,158 @@
+// predict.cu -- batched ensemble predict.
+//
+// Reference semantics restated:
+//   predictor.cpp:122-185  preds = bias, then for every tree (ascending) the matching leaf's value is handed to each
+//                          optimizer: theta[i] -= lr(t) * value[i] for i in [start_idx, stop_idx)  (optimizer.cpp:110-118)
+//   predictor.cpp:231-265  oblivious: leaf_idx |= (x[f_k] > thr_k) << (depth-1-k)
+//   predictor.cpp:188-229  greedy: first leaf of the tree whose path conditions all hold.  A tree is a binary
+//                          partition, so this equals walking the tree from the root; we walk the per-tree heap
+//                          topology stored next to the reference-layout arrays (O(depth) instead of O(leaves*depth)).
+//                          A depth-0 tree never matches in the reference (passed=false) -> contributes nothing.
+//   scheduler.h:124-135,182-185  Linear / Const learning rate
+// Per sample the trees are applied sequentially in ascending order with mul-then-sub (no FMA), i.e. the
+// float result equals the reference's sample-parallel / serial mode bit for bit.
+#include "engine.cuh"
+
+namespace gb {
+
+struct DevOpt { int sched, start_idx, stop_idx, T; float init_lr, stop_lr; };
+
+__device__ __forceinline__ float sched_lr(const DevOpt &o, int t) {
+    if (o.sched == GBRL_B200_SCHED_CONST) return o.init_lr;
+    const float T_ = (float)o.T;
+    const float t_ = (float)t + 1;
+    const float progress_remaining = (T_ - t_) / T_;
+    const float lr = o.init_lr + (1.0f - progress_remaining) * (o.stop_lr - o.init_lr);
+    return lr < o.stop_lr ? o.stop_lr : lr;
+}
+
+struct PredictParams {
+    const float *X; float *preds; const float *bias;
+    const int *tree_indices, *depths, *feature_indices, *heap_feat, *heap_leaf;
+    const float *values, *feature_values, *heap_thr;
+    const DevOpt *opts;
+    int n_opts, N, F, D, md, start_tree, stop_tree, add_bias, oblivious;
+};
+
+template <int DM>
+__global__ void __launch_bounds__(128) predict_kernel(PredictParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const float *x = P.X + (size_t)i * P.F;
+    float theta[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) theta[d] = (d < P.D) ? (P.add_bias ? P.bias[d] : P.preds[(size_t)i * P.D + d]) : 0.0f;
+    const int md = P.md;
+    for (int t = P.start_tree; t < P.stop_tree; ++t) {
+        int leaf = -1;
+        if (P.oblivious) {
+            const int dep = P.depths[t];
+            int li = 0;
+            for (int k = 0; k < dep; ++k) {
+                const int f = P.feature_indices[(size_t)t * md + k];
+                const float thr = P.feature_values[(size_t)t * md + k];
+                li |= (x[f] > thr ? 1 : 0) << (dep - 1 - k);
+            }
+            leaf = P.tree_indices[t] + li;
+        } else {
+            const int *hf = P.heap_feat + (size_t)t * (1 << md);
+            const float *ht = P.heap_thr + (size_t)t * (1 << md);
+            int h = 0, f = hf[0];
+            if (f < 0) continue;                 // depth-0 tree: never matches in the reference
+            while (f >= 0) {
+                h = 2 * h + 1 + (x[f] > ht[h] ? 1 : 0);
+                f = (h < (1 << md) - 1) ? hf[h] : -1;
+            }
+            leaf = P.tree_indices[t] + P.heap_leaf[(size_t)t * (2 << md) + h];
+        }
+        const float *v = P.values + (size_t)leaf * P.D;
+        for (int o = 0; o < P.n_opts; ++o) {
+            const DevOpt op = P.opts[o];
+            const float lr = sched_lr(op, t);
+#pragma unroll
+            for (int d = 0; d < DM; ++d)
+                if (d >= op.start_idx && d < op.stop_idx) theta[d] = theta[d] - lr * v[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+        if (d < P.D) P.preds[(size_t)i * P.D + d] = theta[d];
+}
+
+void upload_optimizers(Model &m, cudaStream_t s) {
+    std::vector<DevOpt> h(m.opts.size());
+    for (size_t i = 0; i < m.opts.size(); ++i) {
+        h[i].sched = m.opts[i].sched; h[i].start_idx = m.opts[i].start_idx; h[i].stop_idx = m.opts[i].stop_idx;
+        h[i].T = m.opts[i].T; h[i].init_lr = m.opts[i].init_lr; h[i].stop_lr = m.opts[i].stop_lr;
+    }
+    m.d_opts.ensure((h.size() > 0 ? h.size() : 1) * sizeof(DevOpt));
+    if (!h.empty()) {
+        GB_CUDA(cudaMemcpyAsync(m.d_opts.p, h.data(), h.size() * sizeof(DevOpt), cudaMemcpyHostToDevice, s));
+        GB_CUDA(cudaStreamSynchronize(s));
+    }
+}
+
+template <int DM>
+static void launch_predict_dm(const PredictParams &P, cudaStream_t s) {
+    GB_LAUNCH(predict_kernel<DM>, ceil_div(P.N, 128), 128, 0, s, P);
+}
+
+void launch_predict(Model &m, const float *X, int N, int F, int start_tree, int stop_tree, float *preds, bool add_bias,
+                    cudaStream_t s) {
+    if (N <= 0) return;
+    Ensemble &e = m.ens;
+    PredictParams P;
+    P.X = X; P.preds = preds; P.bias = m.bias.as<float>();
+    P.tree_indices = e.tree_indices.as<int>(); P.depths = e.depths.as<int>(); P.feature_indices = e.feature_indices.as<int>();
+    P.heap_feat = e.heap_feat.as<int>(); P.heap_leaf = e.heap_leaf.as<int>(); P.values = e.values.as<float>();
+    P.feature_values = e.feature_values.as<float>(); P.heap_thr = e.heap_thr.as<float>();
+    P.opts = m.d_opts.as<DevOpt>(); P.n_opts = (int)m.opts.size();
+    P.N = N; P.F = F; P.D = m.cfg.output_dim; P.md = m.cfg.max_depth; P.start_tree = start_tree; P.stop_tree = stop_tree;
+    P.add_bias = add_bias ? 1 : 0; P.oblivious = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
+    const int D = P.D;
+    if (D <= 1) launch_predict_dm<1>(P, s);
+    else if (D <= 2) launch_predict_dm<2>(P, s);
+    else if (D <= 4) launch_predict_dm<4>(P, s);
+    else if (D <= 8) launch_predict_dm<8>(P, s);
+    else if (D <= 16) launch_predict_dm<16>(P, s);
+    else if (D <= 32) launch_predict_dm<32>(P, s);
+    else launch_predict_dm<64>(P, s);
+}
+
+// the newest tree only, applied on top of existing predictions (fit loop)
+void launch_update_preds_last_tree(Model &m, const float *X, int N, int F, float *preds, cudaStream_t s) {
+    launch_predict(m, X, N, F, m.ens.n_trees - 1, m.ens.n_trees, preds, false, s);
+}
+
+// ---------------------------------------------------------------- rebuild heap topology from leaf paths
+// (ensembles loaded in the reference layout: gbrl_b200_set_ensemble)
+__global__ void rebuild_heap_kernel(const int *tree_indices, const int *depths, const int *feature_indices,
+                                    const float *feature_values, const uint8_t *ineq, int *heap_feat, float *heap_thr,
+                                    int *heap_leaf, int n_trees, int n_leaves, int md) {
+    const int t = blockIdx.x;
+    if (t >= n_trees) return;
+    const int l0 = tree_indices[t], l1 = (t + 1 < n_trees) ? tree_indices[t + 1] : n_leaves;
+    for (int h = threadIdx.x; h < (1 << md); h += blockDim.x) { heap_feat[(size_t)t * (1 << md) + h] = -1; heap_thr[(size_t)t * (1 << md) + h] = 0.0f; }
+    for (int h = threadIdx.x; h < (2 << md); h += blockDim.x) heap_leaf[(size_t)t * (2 << md) + h] = -1;
+    __syncthreads();
+    for (int leaf = l0 + threadIdx.x; leaf < l1; leaf += blockDim.x) {
+        const int dep = depths[leaf];
+        int h = 0;
+        for (int k = 0; k < dep; ++k) {
+            heap_feat[(size_t)t * (1 << md) + h] = feature_indices[(size_t)leaf * md + k];
+            heap_thr[(size_t)t * (1 << md) + h] = feature_values[(size_t)leaf * md + k];
+            h = 2 * h + 1 + (ineq[(size_t)leaf * md + k] ? 1 : 0);
+        }
+        heap_leaf[(size_t)t * (2 << md) + h] = leaf - l0;
+    }
+}
+
+void rebuild_heap_topology(Model &m, cudaStream_t s) {
+    Ensemble &e = m.ens;
+    if (m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS || e.n_trees == 0) return;
+    GB_LAUNCH(rebuild_heap_kernel, e.n_trees, 64, 0, s, e.tree_indices.as<int>(), e.depths.as<int>(), e.feature_indices.as<int>(),
+              e.feature_values.as<float>(), e.ineq.as<uint8_t>(), e.heap_feat.as<int>(), e.heap_thr.as<float>(),
+              e.heap_leaf.as<int>(), e.n_trees, e.n_leaves, m.cfg.max_depth);
+}
+
+}  // namespace gb

@@ -1,0 +1,212 @@
+// preprocess.cu -- gradient preprocessing, fixed-point scale selection, MultiRMSE.
+//
+// Reference semantics restated:
+//   fitter.cpp:57-64 / :204-214   L2: build_grads = (g - mean) / (std + 1e-8), std with 1/(n-1); Cosine: raw g
+//   math_ops.cpp:255-300          calculate_mean: T thread-partial sums over contiguous ELEMENT ranges of the
+//                                 row-major matrix, merged in thread order, then * (1/n)
+//   math_ops.cpp:407-513          calculate_var/std_and_center: same partition for sum (x-mean)^2, centers in place
+//   math_ops.cpp:79-105           divide_mat_by_vec_inplace
+//   utils.h:64-81                 T = calculate_num_threads(n_elements, par_th)  (emulated max = cfg.ref_threads)
+//   loss.cpp:34-62                MultiRMSE gradients; each thread covers exactly n_elements/T elements, so the
+//                                 trailing n_elements % T gradients are never written
+//
+// The reference's float sums are sequential chains; to reproduce their bits each (thread-partition, column)
+// chain is evaluated by one CUDA thread in the same order (no FMA: the engine is compiled with -fmad=false).
+#include "engine.cuh"
+
+namespace gb {
+
+__host__ __device__ inline int calc_threads(long long total, int min_per_thread, int max_threads) {
+    long long n = total / (min_per_thread > 0 ? min_per_thread : 1);
+    if (n > total) n = total;
+    if (n <= 1) return 1;
+    if (n > max_threads) return max_threads;
+    return (int)n;
+}
+
+// chains (t, col): partial[t*D + col] = sequential sum over i in [t*ept, (t+1)*ept or end), i % D == col
+// mode 0: sum x          mode 1: sum (x-mean)^2 and center x in place
+__global__ void __launch_bounds__(256)
+ref_chain_kernel(float *mat, const float *mean, float *partial, long long n_elements, int D, int T, int mode) {
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= T * D) return;
+    const int t = chain / D, col = chain % D;
+    const long long ept = n_elements / T;
+    const long long s = (long long)t * ept, e = (t == T - 1) ? n_elements : s + ept;
+    long long i = s + ((col - (s % D)) % D + D) % D;
+    float acc = 0.0f;
+    if (mode == 0) {
+        for (; i + 7 * (long long)D < e; i += 8 * (long long)D) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = mat[i + (long long)j * D];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = acc + v[j];
+        }
+        for (; i < e; i += D) acc = acc + mat[i];
+    } else {
+        const float mu = mean[col];
+        for (; i + 7 * (long long)D < e; i += 8 * (long long)D) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = mat[i + (long long)j * D];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float c = v[j] - mu;
+                acc = acc + c * c;
+                mat[i + (long long)j * D] = c;
+            }
+        }
+        for (; i < e; i += D) {
+            const float c = mat[i] - mu;
+            acc = acc + c * c;
+            mat[i] = c;
+        }
+    }
+    partial[chain] = acc;
+}
+
+// merge partials in thread order (d = 0..T*D-1, column d % D), then finish
+// mode 0: mean = sum * (1/n)     mode 1: std = sqrtf(sum * 1/(n-1))
+__global__ void ref_merge_kernel(const float *partial, float *out, int D, int T, int n_samples, int mode) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= D) return;
+    float acc = 0.0f;
+    if (T > 1) { for (int t = 0; t < T; ++t) acc = acc + partial[t * D + col]; }
+    else acc = partial[col];
+    if (mode == 0) out[col] = acc * (1.0f / (float)n_samples);
+    else out[col] = sqrtf(acc * (1.0f / ((float)n_samples - 1.0f)));
+}
+
+__global__ void __launch_bounds__(256)
+divide_and_max_kernel(float *bg, const float *stdv, Ctl *ctl, long long n_elements, int D, int do_divide, int which) {
+    float mx = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elements; i += (long long)gridDim.x * blockDim.x) {
+        float v = bg[i];
+        if (do_divide) { v = v / (stdv[i % D] + 1e-8f); bg[i] = v; }
+        const float a = fabsf(v);
+        if (a > mx && a < INFINITY) mx = a;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, __float_as_uint(mx));
+}
+
+__global__ void max_only_kernel(const float *g, Ctl *ctl, long long n_elements, int which) {
+    float mx = 0.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elements; i += (long long)gridDim.x * blockDim.x) {
+        const float a = fabsf(g[i]);
+        if (a > mx && a < INFINITY) mx = a;
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, __float_as_uint(mx));
+}
+
+// q = rint(g * 2^qexp) must satisfy |q| < 2^(Q_BITS-1)
+__global__ void qexp_kernel(Ctl *ctl, int which) {
+    const float mx = __uint_as_float(which == 0 ? ctl->max_abs_bg : ctl->max_abs_raw);
+    int e = 0;
+    if (mx > 0.0f) {
+        int k;
+        frexpf(mx, &k);            // mx = m * 2^k, m in [0.5, 1)  ->  mx < 2^k
+        e = (Q_BITS - 2) - k;
+        if (e > 120) e = 120;
+        if (e < -120) e = -120;
+    }
+    if (which == 0) ctl->qexp = e; else ctl->qexp_raw = e;
+}
+
+static void reset_max(Model &m, int which, cudaStream_t s) {
+    Ctl *ctl = m.ws.ctl.as<Ctl>();
+    GB_CUDA(cudaMemsetAsync(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, 0, sizeof(unsigned int), s));
+}
+
+void column_mean_ref(Model &m, const float *mat, int N, int D, float *out_dev, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const long long ne = (long long)N * D;
+    const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
+    ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
+    float *partial = ws.lrs.as<float>();
+    GB_LAUNCH(ref_chain_kernel, ceil_div(T * D, 256), 256, 0, s, const_cast<float *>(mat), nullptr, partial, ne, D, T, 0);
+    GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, out_dev, D, T, N, 0);
+}
+
+void build_grads(Model &m, const float *grads, int N, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const int D = ws.D;
+    const long long ne = (long long)N * D;
+    ws.bg.ensure((size_t)(ne > 0 ? ne : 1) * sizeof(float));
+    Ctl *ctl = ws.ctl.as<Ctl>();
+    reset_max(m, 0, s);
+    if (ne > 0) GB_CUDA(cudaMemcpyAsync(ws.bg.p, grads, (size_t)ne * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int grid = (int)((ne + 2047) / 2048);
+    if (grid > 1184) grid = 1184;
+    if (grid < 1) grid = 1;
+    if (m.cfg.split_score_func == GBRL_B200_SCORE_L2 && ne > 0) {
+        const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
+        ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
+        float *partial = ws.lrs.as<float>(), *mean = partial + (size_t)T * D, *stdv = mean + D;
+        GB_LAUNCH(ref_chain_kernel, ceil_div(T * D, 256), 256, 0, s, ws.bg.as<float>(), nullptr, partial, ne, D, T, 0);
+        GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, mean, D, T, N, 0);
+        GB_LAUNCH(ref_chain_kernel, ceil_div(T * D, 256), 256, 0, s, ws.bg.as<float>(), mean, partial, ne, D, T, 1);
+        GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, stdv, D, T, N, 1);
+        GB_LAUNCH(divide_and_max_kernel, grid, 256, 0, s, ws.bg.as<float>(), stdv, ctl, ne, D, 1, 0);
+    } else if (ne > 0) {
+        GB_LAUNCH(max_only_kernel, grid, 256, 0, s, ws.bg.as<float>(), ctl, ne, 0);
+    }
+    GB_LAUNCH(qexp_kernel, 1, 1, 0, s, ctl, 0);
+}
+
+void raw_grad_scale(Model &m, const float *grads, int N, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const long long ne = (long long)N * ws.D;
+    Ctl *ctl = ws.ctl.as<Ctl>();
+    reset_max(m, 1, s);
+    int grid = (int)((ne + 2047) / 2048);
+    if (grid > 1184) grid = 1184;
+    if (ne > 0) GB_LAUNCH(max_only_kernel, grid, 256, 0, s, grads, ctl, ne, 1);
+    GB_LAUNCH(qexp_kernel, 1, 1, 0, s, ctl, 1);
+}
+
+// loss.cpp:34-62; only the first T*(n_elements/T) gradients are written
+__global__ void multirmse_grads_kernel(const float *preds, const float *targets, float *grads, long long covered) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < covered; i += (long long)gridDim.x * blockDim.x)
+        grads[i] = preds[i] - targets[i];
+}
+
+void multirmse_grads(Model &m, const float *preds, const float *targets, float *grads, int n, cudaStream_t s) {
+    const long long ne = (long long)n * m.cfg.output_dim;
+    const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
+    const long long covered = (ne / T) * T;
+    if (covered <= 0) return;
+    int grid = (int)((covered + 1023) / 1024);
+    if (grid > 1184) grid = 1184;
+    GB_LAUNCH(multirmse_grads_kernel, grid, 256, 0, s, preds, targets, grads, covered);
+}
+
+__global__ void __launch_bounds__(256) sq_err_kernel(const float *preds, const float *targets, double *out, long long ne) {
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
+        const float gdiff = preds[i] - targets[i];
+        acc += (double)(gdiff * gdiff);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// MultiRMSE::get_loss (loss.cpp:64-90): sqrt(0.5 * sum / n).  The sum is accumulated in fp64 (the
+// reference's value is an fp32 thread-partitioned sum; agreement is to ~1e-6 relative, not bit level).
+void multirmse_loss(Model &m, const float *preds, const float *targets, int n, float *loss_host, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const long long ne = (long long)n * m.cfg.output_dim;
+    ws.pstage.ensure(sizeof(double));
+    GB_CUDA(cudaMemsetAsync(ws.pstage.p, 0, sizeof(double), s));
+    int grid = (int)((ne + 1023) / 1024);
+    if (grid > 1184) grid = 1184;
+    if (ne > 0) GB_LAUNCH(sq_err_kernel, grid, 256, 0, s, preds, targets, ws.pstage.as<double>(), ne);
+    double h = 0.0;
+    GB_CUDA(cudaMemcpyAsync(&h, ws.pstage.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    *loss_host = sqrtf(0.5f * (float)h * (1.0f / (float)n));
+}
+
+}  // namespace gb

@@ -1,0 +1,729 @@
+// split.cu -- split-score scan, arg-max, near-tie replay and split decision.
+//
+// Reference semantics restated (file:line are gbrl/src/cpp/):
+//   L2 score        node.cpp:354-375     n_L*|S_L/n_L|^2 + n_R*|S_R/n_R|^2, -inf if a side < min_data_in_leaf
+//   Cosine score    node.cpp:225-250 + math_ops.h:538-575  (S_R.mu_R + S_L.mu_L) / sqrt(|mu_R|^2 n_R + |mu_L|^2 n_L)
+//   path guard      node.cpp:151-166     a (feature, value) already on the node's path scores -inf
+//   greedy          fitter.cpp:292-371   gain = score*w[f] - parent, strict '>' (lowest index wins ties), split iff >= 0
+//   parent score    split_candidate_generator.cpp:262-320, root forced to 0 (fitter.cpp:315)
+//   oblivious       fitter.cpp:411-477   score_c = (sum over nodes in node order) * w[rev_map[f]], stop iff best == -inf
+//
+// Two-tier evaluation:
+//   1. exact tier  -- per-side sums come from the integer histograms (suffix scan over codes), are rounded
+//      once to fp32 and pushed through the reference's formula in the reference's operation order.
+//      Identical partitions therefore get bit-identical scores and the lowest-index rule reproduces the
+//      reference on every exact tie (duplicate thresholds, small nodes).
+//   2. replay tier -- the reference's own sums are sequential fp32 accumulations in ascending sample
+//      order, i.e. they carry O(u*sqrt(n)) rounding noise.  Whenever another (non-identical) candidate is
+//      within that noise band of the exact best, both are re-scored by replay_kernel with exactly the
+//      reference's chain of float operations, so the chosen split is the reference's, bit for bit.
+#include "engine.cuh"
+#include <cfloat>
+#include <climits>
+
+namespace gb {
+
+constexpr float U24 = 5.9604644775390625e-08f;   // 2^-24
+
+struct ScanParams {
+    int level, nT, F, B, D, C;                // C = F*B candidates
+    int score_func, oblivious, min_data, max_depth, use_subtraction;
+    const long long *hist_par;                // parent level buffer
+    long long *hist_cur;                      // this level's buffer
+    const float *thr;                         // [F*B]
+    const float *fw;                          // feature weights [input_dim]
+    float *scores;                            // [slot][C]
+    uint8_t *cand_flags;                      // greedy: [slot][C] bit0 = dominated; oblivious: [C] bit1 = empty code below
+    float2 *tile_best;                        // [slot][nT] (gain, idx as float bits)
+    const Ctl *ctl;
+};
+
+// reference formula on per-side sums (already rounded to fp32), templated on the max dimension
+template <int DM>
+__device__ __forceinline__ float side_score(int func, int D, int nL, int nR, const float *SL, const float *SR, int min_data) {
+    if (nL < min_data || nR < min_data) return -INFINITY;
+    const float lcf = (float)nL, rcf = (float)nR;
+    const float lrec = nL > 0 ? 1.0f / lcf : 0.0f;
+    const float rrec = nR > 0 ? 1.0f / rcf : 0.0f;
+    float ln = 0.0f, rn = 0.0f, tnum = 0.0f, fnum = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+        if (d < D) {
+            const float lm = SL[d] * lrec, rm = SR[d] * rrec;
+            ln = ln + lm * lm;
+            rn = rn + rm * rm;
+            // sum_i g_i . mu  ==  S . mu  (the exact tier's algebraic form of mat_vec_dot_sum)
+            tnum = tnum + SR[d] * rm;
+            fnum = fnum + SL[d] * lm;
+        }
+    }
+    if (func == GBRL_B200_SCORE_L2) return lcf * ln + rcf * rn;
+    if (nR == 0) tnum = 0.0f;
+    if (nL == 0) fnum = 0.0f;
+    const float num = tnum + fnum;
+    const float den = rn * rcf + ln * lcf;
+    if (den == 0.0f) return 0.0f;
+    return num / sqrtf(den);
+}
+
+template <int DM>
+__device__ __forceinline__ float node_parent_score(int func, int D, int n, const long long *tot, double inv_scale) {
+    const float nf = (float)n;
+    const float rec = 1.0f / nf;
+    float norm = 0.0f, dot = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+        if (d < D) {
+            const float S = (float)((double)tot[d] * inv_scale);
+            const float mu = S * rec;
+            norm = norm + mu * mu;
+            dot = dot + S * mu;
+        }
+    }
+    if (func == GBRL_B200_SCORE_L2) return norm * nf;
+    if (n == 0) return 0.0f;
+    const float den = norm * nf;
+    if (den == 0.0f) return 0.0f;
+    return dot / sqrtf(den);
+}
+
+__device__ __forceinline__ bool better(float ga, int ia, float gb_, int ib) {
+    return (ga > gb_) || (ga == gb_ && ia < ib);
+}
+
+// one CTA per (node slot, feature tile); thread (c = tid>>5, fl = tid&31) owns codes [32c, 32c+32) of
+// feature tile*32+fl.  Histogram layout [bin][feature][1+D] makes every load of a warp one contiguous
+// 32*(1+D)*8-byte run.
+template <int DM>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(ScanParams P, NodeArrays na) {
+    extern __shared__ long long s_tot[];        // [8][32][1+D]
+    __shared__ float s_gain[SCAN_THREADS];
+    __shared__ int s_idx[SCAN_THREADS];
+    __shared__ int s_path_f[MAX_DEPTH_SUPPORTED];
+    __shared__ float s_path_v[MAX_DEPTH_SUPPORTED];
+    __shared__ float s_parent;
+    const int p = blockIdx.x / P.nT, tile = blockIdx.x % P.nT;
+    const int h = level_base(P.level) + p;
+    if (na.state[h] != NODE_OPEN) return;
+    const int D = P.D, HS = 1 + D;
+    const int n = na.seg_len[h];
+    const int c = threadIdx.x >> 5, fl = threadIdx.x & 31;
+    const int f = tile * FT + fl;
+    const bool derived = (P.level > 0) && P.use_subtraction && (na.direct[h] == 0);
+    const double inv_scale = exp2((double)(-P.ctl->qexp));
+    const size_t tile_words = (size_t)NB * FT * HS;
+    long long *Hc = P.hist_cur + ((size_t)p * P.nT + tile) * tile_words;
+    const long long *Hs = nullptr, *Hp = nullptr;
+    if (derived) {
+        const int sib = (h & 1) ? h + 1 : h - 1;
+        const int par = (h - 1) >> 1;
+        Hs = P.hist_cur + ((size_t)(sib - level_base(P.level)) * P.nT + tile) * tile_words;
+        Hp = P.hist_par + ((size_t)(par - level_base(P.level - 1)) * P.nT + tile) * tile_words;
+    }
+    // ancestors' conditions (path guard) and the parent score, once per CTA
+    if (threadIdx.x == 0) {
+        int a = h, k = 0;
+        while (a > 0) {
+            const int par = (a - 1) >> 1;
+            s_path_f[k] = na.split_f[par];
+            s_path_v[k] = na.split_thr[par];
+            ++k;
+            a = par;
+        }
+        for (; k < MAX_DEPTH_SUPPORTED; ++k) s_path_f[k] = -1;
+        float ps = 0.0f;
+        if (!P.oblivious && P.level > 0) ps = node_parent_score<DM>(P.score_func, D, n, na.tot_sum + (size_t)h * D, inv_scale);
+        s_parent = ps;
+        if (tile == 0) na.parent_score[h] = ps;
+    }
+    // phase 1: per-chunk totals
+    long long run[1 + DM];
+#pragma unroll
+    for (int d = 0; d <= DM; ++d) run[d] = 0;
+    for (int b = 32 * c; b < 32 * c + 32; ++b) {
+        const size_t o = ((size_t)b * FT + fl) * HS;
+#pragma unroll
+        for (int d = 0; d <= DM; ++d)
+            if (d <= D) run[d] += derived ? (Hp[o + d] - Hs[o + d]) : Hc[o + d];
+    }
+#pragma unroll
+    for (int d = 0; d <= DM; ++d)
+        if (d <= D) s_tot[((size_t)c * FT + fl) * HS + d] = run[d];
+    __syncthreads();
+    // offset = totals of the chunks above
+    long long off[1 + DM];
+#pragma unroll
+    for (int d = 0; d <= DM; ++d) off[d] = 0;
+    for (int c2 = c + 1; c2 < 8; ++c2)
+#pragma unroll
+        for (int d = 0; d <= DM; ++d)
+            if (d <= D) off[d] += s_tot[((size_t)c2 * FT + fl) * HS + d];
+    const float parent = s_parent;
+    const float w = (f < P.F) ? P.fw[f] : 0.0f;
+    const int depth = P.level;
+    long long tot[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) tot[d] = (d < D) ? na.tot_sum[(size_t)h * D + d] : 0;
+    float bestg = -INFINITY;
+    int besti = INT_MAX;
+#pragma unroll
+    for (int d = 0; d <= DM; ++d) run[d] = 0;
+    // phase 2: descending codes -> suffix sums -> scores
+    for (int b = 32 * c + 31; b >= 32 * c; --b) {
+        const size_t o = ((size_t)b * FT + fl) * HS;
+        long long v[1 + DM];
+#pragma unroll
+        for (int d = 0; d <= DM; ++d) {
+            v[d] = 0;
+            if (d <= D) {
+                v[d] = derived ? (Hp[o + d] - Hs[o + d]) : Hc[o + d];
+                run[d] += v[d];
+                if (derived) Hc[o + d] = v[d];
+            }
+        }
+        if (f >= P.F || b >= P.B) continue;
+        // candidate j = b of feature f: right = codes > b  == bins >= b
+        const int nR = (int)(off[0] + run[0]);
+        const int nL = n - nR;
+        float SL[DM], SR[DM];
+#pragma unroll
+        for (int d = 0; d < DM; ++d) {
+            if (d < D) {
+                const long long r = off[1 + d] + run[1 + d];
+                SR[d] = (float)((double)r * inv_scale);
+                SL[d] = (float)((double)(tot[d] - r) * inv_scale);
+            } else { SR[d] = 0.0f; SL[d] = 0.0f; }
+        }
+        const float tv = P.thr[(size_t)f * P.B + b];
+        bool reused = false;
+        for (int k = 0; k < depth; ++k) reused |= (s_path_f[k] == f && s_path_v[k] == tv);
+        float sc = reused ? -INFINITY : side_score<DM>(P.score_func, D, nL, nR, SL, SR, P.min_data);
+        const int idx = f * P.B + b;
+        float gain = sc;
+        if (!P.oblivious) gain = sc * w - parent;
+        P.scores[(size_t)p * P.C + idx] = gain;
+        // dominated: same partition as the previous threshold of this feature, which is itself valid
+        uint8_t fl8 = 0;
+        if (b > 0) {
+            const size_t o1 = ((size_t)(b - 1) * FT + fl) * HS;
+            const long long cprev = derived ? (Hp[o1] - Hs[o1]) : Hc[o1];
+            if (cprev == 0) {
+                const float tvp = P.thr[(size_t)f * P.B + b - 1];
+                bool rp = false;
+                for (int k = 0; k < depth; ++k) rp |= (s_path_f[k] == f && s_path_v[k] == tvp);
+                if (!rp) fl8 = 1;
+                if (P.oblivious && P.level == 0) fl8 |= 2;   // no sample of the whole set has code == b
+            }
+        }
+        if (!P.oblivious) P.cand_flags[(size_t)p * P.C + idx] = fl8;
+        else if (P.level == 0) P.cand_flags[idx] = fl8 & 2;
+        if (gain > -INFINITY && better(gain, idx, bestg, besti)) { bestg = gain; besti = idx; }
+    }
+    // block arg-max (lowest index on ties)
+    s_gain[threadIdx.x] = bestg;
+    s_idx[threadIdx.x] = besti;
+    __syncthreads();
+    for (int o = SCAN_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            if (better(s_gain[threadIdx.x + o], s_idx[threadIdx.x + o], s_gain[threadIdx.x], s_idx[threadIdx.x])) {
+                s_gain[threadIdx.x] = s_gain[threadIdx.x + o];
+                s_idx[threadIdx.x] = s_idx[threadIdx.x + o];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P.tile_best[(size_t)p * P.nT + tile] = make_float2(s_gain[0], __int_as_float(s_idx[0]));
+}
+
+// derived histograms read a neighbour's bins while another thread of the same CTA overwrites Hc only at
+// its own (b, fl) positions, and the dominated test reads bin b-1 of the SAME feature before this thread
+// (descending b) or the chunk-below thread overwrites it with the identical derived value -- for derived
+// nodes the test always reads Hp - Hs, never Hc, so there is no read-after-write hazard.
+
+// ---------------------------------------------------------------- greedy: per-node best + replay list
+struct SelectParams {
+    int level, nT, F, B, D, C, tie_replay, replay_cap;
+    float kappa;
+    const float *scores;
+    const uint8_t *cand_flags;
+    const float2 *tile_best;
+    ReplayItem *replay;
+    Ctl *ctl;
+};
+
+__global__ void __launch_bounds__(256) select_greedy_kernel(SelectParams P, NodeArrays na) {
+    __shared__ float s_best;
+    __shared__ int s_besti, s_count, s_begin, s_w;
+    const int p = blockIdx.x, h = level_base(P.level) + p;
+    if (na.state[h] != NODE_OPEN) return;
+    if (threadIdx.x == 0) {
+        float g = -INFINITY; int bi = INT_MAX;
+        for (int t = 0; t < P.nT; ++t) {
+            const float2 v = P.tile_best[(size_t)p * P.nT + t];
+            const int i = __float_as_int(v.y);
+            if (v.x > -INFINITY && better(v.x, i, g, bi)) { g = v.x; bi = i; }
+        }
+        s_best = g; s_besti = bi; s_count = 0; s_w = 0;
+        na.best_gain[h] = g;
+        na.best_idx[h] = (bi == INT_MAX) ? -1 : bi;
+        na.rep_begin[h] = 0; na.rep_count[h] = 0;
+        atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, 1ull);
+    }
+    __syncthreads();
+    const float g = s_best;
+    if (!P.tie_replay || !(g > -INFINITY)) return;
+    const int n = na.seg_len[h];
+    const float parent = na.parent_score[h];
+    const float band = P.kappa * U24 * sqrtf((float)n) * (fabsf(g + parent) + fabsf(parent)) + FLT_MIN;
+    const float lim = g - band;
+    const float *sc = P.scores + (size_t)p * P.C;
+    const uint8_t *fl = P.cand_flags + (size_t)p * P.C;
+    int mine = 0;
+    for (int i = threadIdx.x; i < P.C; i += blockDim.x) mine += (sc[i] >= lim && !(fl[i] & 1)) ? 1 : 0;
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    const bool need = (s_count > 1) || (fabsf(g) <= band && P.level > 0);
+    if (!need) return;
+    const int n_items = s_count + (P.level > 0 ? 1 : 0);
+    if (threadIdx.x == 0) {
+        const int beg = atomicAdd(&P.ctl->n_replay, n_items);
+        if (beg + n_items > P.replay_cap) {
+            atomicAdd(&P.ctl->replay_overflow, 1);
+            s_begin = -1;
+        } else {
+            s_begin = beg;
+            na.rep_begin[h] = beg; na.rep_count[h] = n_items; na.band[h] = band;
+            if (P.level > 0) { P.replay[beg].node = h; P.replay[beg].cand = -1; s_w = 1; }
+            atomicAdd((unsigned long long *)&P.ctl->stat_replay_nodes, 1ull);
+            atomicAdd((unsigned long long *)&P.ctl->stat_replay_items, (unsigned long long)n_items);
+        }
+    }
+    __syncthreads();
+    if (s_begin < 0) return;
+    for (int i = threadIdx.x; i < P.C; i += blockDim.x) {
+        if (sc[i] >= lim && !(fl[i] & 1)) {
+            const int w = atomicAdd(&s_w, 1);
+            P.replay[s_begin + w].node = h;
+            P.replay[s_begin + w].cand = i;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- oblivious: level-wide reduction
+struct OblParams {
+    int level, F, B, D, C, nn, tie_replay, replay_cap, nblocks;
+    float kappa;
+    int N;
+    const float *scores;       // [nn][C] raw node scores
+    const uint8_t *cand_flags; // [C] bit1
+    const float *fw;
+    const int *rev_map;
+    float *obl_tot;            // [C]
+    float2 *blk_best;          // [nblocks]
+    ReplayItem *replay;
+    int *obl_cands;            // candidate list of replay (stored after the items, see launcher)
+    Ctl *ctl;
+};
+
+__global__ void __launch_bounds__(256) obl_reduce_kernel(OblParams P) {
+    __shared__ float s_gain[256];
+    __shared__ int s_idx[256];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    float tot = -INFINITY;
+    int idx = INT_MAX;
+    if (c < P.C) {
+        float s = 0.0f;
+        for (int p = 0; p < P.nn; ++p) s += P.scores[(size_t)p * P.C + c];   // fitter.cpp:427-430, node order
+        const int f = c / P.B;
+        s = s * P.fw[P.rev_map[f]];                                          // fitter.cpp:432-435
+        P.obl_tot[c] = s;
+        if (s > -INFINITY) { tot = s; idx = c; }
+    }
+    s_gain[threadIdx.x] = tot; s_idx[threadIdx.x] = idx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o && better(s_gain[threadIdx.x + o], s_idx[threadIdx.x + o], s_gain[threadIdx.x], s_idx[threadIdx.x])) {
+            s_gain[threadIdx.x] = s_gain[threadIdx.x + o]; s_idx[threadIdx.x] = s_idx[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P.blk_best[blockIdx.x] = make_float2(s_gain[0], __int_as_float(s_idx[0]));
+}
+
+__global__ void __launch_bounds__(256) obl_select_kernel(OblParams P, NodeArrays na) {
+    __shared__ float s_best, s_band;
+    __shared__ int s_besti, s_count, s_w, s_ok;
+    const int base = level_base(P.level);
+    if (na.state[base] != NODE_OPEN) return;    // tree already stopped
+    if (threadIdx.x == 0) {
+        float g = -INFINITY; int bi = INT_MAX;
+        for (int b = 0; b < P.nblocks; ++b) {
+            const float2 v = P.blk_best[b];
+            const int i = __float_as_int(v.y);
+            if (v.x > -INFINITY && better(v.x, i, g, bi)) { g = v.x; bi = i; }
+        }
+        s_best = g; s_besti = (bi == INT_MAX) ? -1 : bi; s_count = 0; s_w = 0; s_ok = 0;
+        P.ctl->obl_best = g; P.ctl->obl_best_idx = s_besti; P.ctl->obl_has_replay = 0;
+        atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, (unsigned long long)P.nn);
+        s_band = P.kappa * U24 * sqrtf((float)P.N) * fabsf(g) + FLT_MIN;
+    }
+    __syncthreads();
+    const float g = s_best;
+    if (!P.tie_replay || s_besti < 0) return;
+    const float lim = g - s_band;
+    auto in_band = [&](int i) -> bool {
+        if (!(P.obl_tot[i] >= lim)) return false;
+        const int j = i % P.B;
+        if (j > 0 && (P.cand_flags[i] & 2) && P.obl_tot[i - 1] > -INFINITY) return false;   // dominated by j-1
+        return true;
+    };
+    int mine = 0;
+    for (int i = threadIdx.x; i < P.C; i += blockDim.x) mine += in_band(i) ? 1 : 0;
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    if (s_count <= 1) return;
+    if (threadIdx.x == 0) {
+        const long long n_items = (long long)s_count * P.nn;
+        if (n_items > P.replay_cap) { atomicAdd(&P.ctl->replay_overflow, 1); s_ok = 0; }
+        else {
+            s_ok = 1;
+            P.ctl->n_replay = (int)n_items;
+            P.ctl->obl_has_replay = s_count;
+            atomicAdd((unsigned long long *)&P.ctl->stat_replay_nodes, (unsigned long long)P.nn);
+            atomicAdd((unsigned long long *)&P.ctl->stat_replay_items, (unsigned long long)n_items);
+        }
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    for (int i = threadIdx.x; i < P.C; i += blockDim.x) {
+        if (in_band(i)) {
+            const int w = atomicAdd(&s_w, 1);
+            P.obl_cands[w] = i;
+            for (int p = 0; p < P.nn; ++p) {
+                P.replay[(size_t)w * P.nn + p].node = base + p;
+                P.replay[(size_t)w * P.nn + p].cand = i;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- replay: the reference's own arithmetic
+struct ReplayParams {
+    int F, B, D, score_func, min_data;
+    const float *X;            // raw features, row-major
+    const float *bg;           // build_grads
+    const int *order;
+    const float *thr;
+    const ReplayItem *items;
+    float *out;
+    const Ctl *ctl;
+};
+
+// One warp per item.  Rows of the node are visited in ascending sample order (== reference sample_indices);
+// lane d owns output dimension d (chains over samples are independent per dimension); the Cosine
+// numerators are a single chain over (row, col) and are run by every lane redundantly.
+__global__ void __launch_bounds__(128) replay_kernel(ReplayParams P, NodeArrays na) {
+    extern __shared__ float s_dyn[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int D = P.D;
+    float *sg = s_dyn + (size_t)wib * (32 * D + 2 * D);     // [32][D] gradient tile
+    float *smean = sg + 32 * D;                             // [2][D]  left / right means
+    const int n_items = P.ctl->n_replay;
+    for (int it = blockIdx.x * wpb + wib; it < n_items; it += gridDim.x * wpb) {
+        const ReplayItem item = P.items[it];
+        const int h = item.node, cand = item.cand;
+        const int s0 = na.seg_start[h], n = na.seg_len[h];
+        const int f = cand >= 0 ? cand / P.B : 0;
+        const float tv = cand >= 0 ? P.thr[cand] : INFINITY;
+        float result;
+        int nL = 0, nR = 0;
+        float accL[2] = {0.0f, 0.0f}, accR[2] = {0.0f, 0.0f};    // lane d and lane d+32 (D <= 64)
+        for (int kb = 0; kb < n; kb += 32) {
+            const int k = kb + lane;
+            bool right = false;
+            if (k < n) {
+                const int i = P.order[s0 + k];
+                right = cand >= 0 && (P.X[(size_t)i * P.F + f] > tv);          // node.cpp:339
+                for (int d = 0; d < D; ++d) sg[lane * D + d] = P.bg[(size_t)i * D + d];
+            }
+            __syncwarp();
+            const unsigned int mask = __ballot_sync(0xffffffffu, right);
+            const int cnt = min(32, n - kb);
+            nR += __popc(mask & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
+            for (int t = 0; t < cnt; ++t) {
+                const bool r = (mask >> t) & 1u;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int d = lane + 32 * q;
+                    if (d < D) {
+                        const float v = sg[t * D + d];
+                        if (r) accR[q] = accR[q] + v; else accL[q] = accL[q] + v;   // node.cpp:341-350
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        nL = n - nR;
+        if (cand >= 0 && (nL < P.min_data || nR < P.min_data)) {
+            result = -INFINITY;
+        } else {
+            const float lcf = (float)nL, rcf = (float)nR;
+            float lrec, rrec;
+            if (cand >= 0) { lrec = nL > 0 ? 1.0f / lcf : 0.0f; rrec = nR > 0 ? 1.0f / rcf : 0.0f; }
+            else { lrec = 1.0f / lcf; rrec = 0.0f; }   // parent: n_samples_recip = 1/n (split_candidate_generator.cpp:265,296)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int d = lane + 32 * q;
+                if (d < D) { smean[d] = accL[q] * lrec; smean[D + d] = accR[q] * rrec; }
+            }
+            __syncwarp();
+            float ln = 0.0f, rn = 0.0f;
+            for (int d = 0; d < D; ++d) { ln = ln + smean[d] * smean[d]; rn = rn + smean[D + d] * smean[D + d]; }  // squared_norm
+            if (P.score_func == GBRL_B200_SCORE_L2) {
+                result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
+            } else {
+                // second pass: mat_vec_dot_sum chains (math_ops.h:432-449), rows in order, columns inner
+                float tnum = 0.0f, fnum = 0.0f;
+                for (int kb = 0; kb < n; kb += 32) {
+                    const int k = kb + lane;
+                    bool right = false;
+                    if (k < n) {
+                        const int i = P.order[s0 + k];
+                        right = cand >= 0 && (P.X[(size_t)i * P.F + f] > tv);
+                        for (int d = 0; d < D; ++d) sg[lane * D + d] = P.bg[(size_t)i * D + d];
+                    }
+                    __syncwarp();
+                    const unsigned int mask = __ballot_sync(0xffffffffu, right);
+                    const int cnt = min(32, n - kb);
+                    for (int t = 0; t < cnt; ++t) {
+                        const bool r = (mask >> t) & 1u;
+                        if (r) { for (int d = 0; d < D; ++d) tnum = tnum + sg[t * D + d] * smean[D + d]; }
+                        else   { for (int d = 0; d < D; ++d) fnum = fnum + sg[t * D + d] * smean[d]; }
+                    }
+                    __syncwarp();
+                }
+                if (cand >= 0) {
+                    const float num = tnum + fnum;
+                    const float den = rn * rcf + ln * lcf;
+                    result = (den == 0.0f) ? 0.0f : num / sqrtf(den);
+                } else {
+                    const float den = ln * lcf;
+                    result = (n == 0 || den == 0.0f) ? 0.0f : fnum / sqrtf(den);
+                }
+            }
+        }
+        if (lane == 0) P.out[it] = result;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- decisions
+struct DecideParams {
+    int level, nT, F, B, D, C, max_depth, nn;
+    const long long *hist_cur;
+    const float *thr, *fw;
+    const int *rev_map;
+    const ReplayItem *replay;
+    const float *replay_scores;
+    const int *obl_cands;
+    Ctl *ctl;
+};
+
+// suffix sum over codes > j of feature f in the node's histogram (one warp)
+__device__ void warp_right_sums(const long long *Hn, int nT, int D, int f, int j, long long *out /*[1+D], lane 0*/) {
+    const int lane = threadIdx.x & 31;
+    const int tile = f / FT, fl = f % FT, HS = 1 + D;
+    const long long *Ht = Hn + (size_t)tile * NB * FT * HS;
+    for (int d = 0; d <= D; ++d) {
+        long long s = 0;
+        for (int b = lane; b < NB; b += 32)
+            if (b >= j) s += Ht[((size_t)b * FT + fl) * HS + d];
+        for (int o = 16; o > 0; o >>= 1) s += shfl_down_ll(s, o);
+        if (lane == 0) out[d] = s;
+    }
+}
+
+__device__ void apply_split(NodeArrays na, const DecideParams &P, int h, int cand, const long long *Hn) {
+    // called by one warp; writes the split and initialises both children
+    const int lane = threadIdx.x & 31;
+    const int f = cand / P.B, j = cand % P.B;
+    __shared__ long long s_r[8][65];
+    long long *r = s_r[(threadIdx.x >> 5) & 7];
+    warp_right_sums(Hn, P.nT, P.D, f, j, r);
+    __syncwarp();
+    if (lane == 0) {
+        const int n = na.seg_len[h], s0 = na.seg_start[h];
+        const int nR = (int)r[0], nL = n - nR;
+        na.state[h] = NODE_SPLIT;
+        na.split_f[h] = f; na.split_j[h] = j; na.split_thr[h] = P.thr[cand];
+        const int lc = 2 * h + 1, rc = 2 * h + 2;
+        na.seg_start[lc] = s0; na.seg_len[lc] = nL;
+        na.seg_start[rc] = s0 + nL; na.seg_len[rc] = nR;
+        for (int d = 0; d < P.D; ++d) {
+            na.tot_sum[(size_t)rc * P.D + d] = r[1 + d];
+            na.tot_sum[(size_t)lc * P.D + d] = na.tot_sum[(size_t)h * P.D + d] - r[1 + d];
+        }
+        const bool last = (P.level + 1 >= P.max_depth);
+        na.state[lc] = last ? NODE_LEAF : NODE_OPEN;
+        na.state[rc] = last ? NODE_LEAF : NODE_OPEN;
+    }
+    __syncwarp();
+}
+
+// greedy: one warp per node of the level
+__global__ void __launch_bounds__(32) decide_greedy_kernel(DecideParams P, NodeArrays na) {
+    const int p = blockIdx.x, h = level_base(P.level) + p, lane = threadIdx.x;
+    if (na.state[h] != NODE_OPEN) return;
+    float g = na.best_gain[h];
+    int c = na.best_idx[h];
+    const int rc = na.rep_count[h];
+    if (rc > 0) {
+        // final arg-max over the replayed candidates, in the reference's arithmetic
+        const int rb = na.rep_begin[h];
+        float parent = 0.0f;
+        float bg_ = -INFINITY; int bi = INT_MAX;
+        if (P.level > 0) parent = P.replay_scores[rb];   // first item is the parent
+        for (int i = rb + lane; i < rb + rc; i += 32) {
+            const int cand = P.replay[i].cand;
+            if (cand < 0) continue;
+            const float gain = P.replay_scores[i] * P.fw[cand / P.B] - parent;
+            if (gain > -INFINITY && better(gain, cand, bg_, bi)) { bg_ = gain; bi = cand; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float og = __shfl_down_sync(0xffffffffu, bg_, o);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (better(og, oi, bg_, bi)) { bg_ = og; bi = oi; }
+        }
+        bg_ = __shfl_sync(0xffffffffu, bg_, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
+        if (bi != INT_MAX) { g = bg_; c = bi; }
+    }
+    // fitter.cpp:357: split iff best_score >= 0 (and the node could be split at all)
+    const bool split = (c >= 0) && (g >= 0.0f);
+    if (!split) {
+        if (lane == 0) na.state[h] = NODE_LEAF;
+        return;
+    }
+    const long long *Hn = P.hist_cur + (size_t)p * P.nT * NB * FT * (1 + P.D);
+    apply_split(na, P, h, c, Hn);
+    // fitter.cpp:300: a child that is empty (or at max depth) is never evaluated -> leaf
+    if (lane == 0) {
+        const int lc = 2 * h + 1, rcn = 2 * h + 2;
+        if (na.seg_len[lc] == 0) na.state[lc] = NODE_LEAF;
+        if (na.seg_len[rcn] == 0) na.state[rcn] = NODE_LEAF;
+    }
+}
+
+// oblivious: one CTA, warp w handles nodes w, w+8, ...
+__global__ void __launch_bounds__(256) decide_oblivious_kernel(DecideParams P, NodeArrays na) {
+    __shared__ int s_cand;
+    const int base = level_base(P.level);
+    if (na.state[base] != NODE_OPEN) return;
+    if (threadIdx.x == 0) {
+        int c = P.ctl->obl_best_idx;
+        const int nrep = P.ctl->obl_has_replay;
+        if (c >= 0 && nrep > 1) {
+            float bg_ = -INFINITY; int bi = INT_MAX;
+            for (int w = 0; w < nrep; ++w) {
+                const int cand = P.obl_cands[w];
+                float s = 0.0f;
+                for (int p = 0; p < P.nn; ++p) s += P.replay_scores[(size_t)w * P.nn + p];
+                s = s * P.fw[P.rev_map[cand / P.B]];
+                if (s > -INFINITY && better(s, cand, bg_, bi)) { bg_ = s; bi = cand; }
+            }
+            if (bi != INT_MAX) c = bi;
+        }
+        s_cand = c;
+        P.ctl->obl_depth = (c >= 0) ? P.level + 1 : P.level;
+    }
+    __syncthreads();
+    const int c = s_cand;
+    const int warp = threadIdx.x >> 5;
+    for (int p = warp; p < P.nn; p += 8) {
+        const int h = base + p;
+        if (c < 0) {
+            if ((threadIdx.x & 31) == 0) na.state[h] = NODE_LEAF;   // fitter.cpp:458 break
+        } else {
+            const long long *Hn = P.hist_cur + (size_t)p * P.nT * NB * FT * (1 + P.D);
+            apply_split(na, P, h, c, Hn);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+template <int DM>
+static void launch_scan_dm(const ScanParams &P, const NodeArrays &na, int grid, cudaStream_t s) {
+    const size_t smem = (size_t)8 * FT * (1 + P.D) * sizeof(long long);
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(scan_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_LAUNCH(scan_kernel<DM>, grid, SCAN_THREADS, smem, s, P, na);
+}
+
+void launch_scan(Model &m, int level, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    ScanParams P;
+    P.level = level; P.nT = ws.nT; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = ws.F * ws.B;
+    P.score_func = m.cfg.split_score_func; P.oblivious = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
+    P.min_data = m.cfg.min_data_in_leaf; P.max_depth = m.cfg.max_depth; P.use_subtraction = m.cfg.use_subtraction;
+    P.hist_cur = ws.hist[level & 1].as<long long>();
+    P.hist_par = ws.hist[(level + 1) & 1].as<long long>();
+    P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
+    P.scores = ws.scores.as<float>(); P.cand_flags = ws.cand_flags.as<uint8_t>();
+    P.tile_best = ws.tile_best.as<float2>(); P.ctl = ws.ctl.as<Ctl>();
+    const int grid = (1 << level) * ws.nT;
+    const int D = ws.D;
+    if (D <= 1) launch_scan_dm<1>(P, ws.na, grid, s);
+    else if (D <= 2) launch_scan_dm<2>(P, ws.na, grid, s);
+    else if (D <= 4) launch_scan_dm<4>(P, ws.na, grid, s);
+    else if (D <= 8) launch_scan_dm<8>(P, ws.na, grid, s);
+    else if (D <= 16) launch_scan_dm<16>(P, ws.na, grid, s);
+    else launch_scan_dm<32>(P, ws.na, grid, s);
+}
+
+void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const bool obl = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
+    const int C = ws.F * ws.B, nn = 1 << level;
+    Ctl *ctl = ws.ctl.as<Ctl>();
+    GB_CUDA(cudaMemsetAsync(&ctl->n_replay, 0, sizeof(int), s));
+    const float kappa = m.cfg.band_kappa > 0 ? m.cfg.band_kappa : 8.0f;
+    int *obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap);
+    if (!obl) {
+        SelectParams P;
+        P.level = level; P.nT = ws.nT; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = C; P.tie_replay = m.cfg.tie_replay;
+        P.replay_cap = ws.replay_cap; P.kappa = kappa; P.scores = ws.scores.as<float>();
+        P.cand_flags = ws.cand_flags.as<uint8_t>(); P.tile_best = ws.tile_best.as<float2>();
+        P.replay = ws.replay.as<ReplayItem>(); P.ctl = ctl;
+        GB_LAUNCH(select_greedy_kernel, nn, 256, 0, s, P, ws.na);
+    } else {
+        OblParams P;
+        P.level = level; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = C; P.nn = nn; P.tie_replay = m.cfg.tie_replay;
+        P.replay_cap = ws.replay_cap; P.nblocks = ceil_div(C, 256); P.kappa = kappa; P.N = ws.N;
+        P.scores = ws.scores.as<float>(); P.cand_flags = ws.cand_flags.as<uint8_t>(); P.fw = m.feature_weights.as<float>();
+        P.rev_map = m.rev_num_map.as<int>(); P.obl_tot = ws.obl_tot.as<float>();
+        P.blk_best = ws.tile_best.as<float2>(); P.replay = ws.replay.as<ReplayItem>(); P.obl_cands = obl_cands; P.ctl = ctl;
+        GB_LAUNCH(obl_reduce_kernel, P.nblocks, 256, 0, s, P);
+        GB_LAUNCH(obl_select_kernel, 1, 256, 0, s, P, ws.na);
+    }
+    if (m.cfg.tie_replay) {
+        ReplayParams R;
+        R.F = ws.F; R.B = ws.B; R.D = ws.D; R.score_func = m.cfg.split_score_func; R.min_data = m.cfg.min_data_in_leaf;
+        R.X = X; R.bg = ws.bg.as<float>(); R.order = ws.order[0].as<int>(); R.thr = ws.thr.as<float>();
+        R.items = ws.replay.as<ReplayItem>(); R.out = ws.replay_scores.as<float>(); R.ctl = ctl;
+        const size_t smem = (size_t)4 * (32 * ws.D + 2 * ws.D) * sizeof(float);
+        GB_LAUNCH(replay_kernel, 148 * 4, 128, smem, s, R, ws.na);
+    }
+}
+
+void launch_decide(Model &m, int level, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    DecideParams P;
+    P.level = level; P.nT = ws.nT; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = ws.F * ws.B; P.max_depth = m.cfg.max_depth;
+    P.nn = 1 << level;
+    P.hist_cur = ws.hist[level & 1].as<long long>(); P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
+    P.rev_map = m.rev_num_map.as<int>(); P.replay = ws.replay.as<ReplayItem>(); P.replay_scores = ws.replay_scores.as<float>();
+    P.obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap); P.ctl = ws.ctl.as<Ctl>();
+    if (m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS) GB_LAUNCH(decide_oblivious_kernel, 1, 256, 0, s, P, ws.na);
+    else GB_LAUNCH(decide_greedy_kernel, P.nn, 32, 0, s, P, ws.na);
+}
+
+}  // namespace gb

