@@ -31,7 +31,8 @@ EXPORTS = [
     "gbrl_b200_set_bias", "gbrl_b200_set_feature_weights", "gbrl_b200_set_feature_mapping", "gbrl_b200_get_bias",
     "gbrl_b200_get_feature_weights", "gbrl_b200_get_feature_mapping", "gbrl_b200_set_optimizer",
     "gbrl_b200_n_optimizers", "gbrl_b200_get_optimizer", "gbrl_b200_get_scheduler_lrs", "gbrl_b200_step",
-    "gbrl_b200_fit", "gbrl_b200_predict", "gbrl_b200_get_metadata", "gbrl_b200_get_ensemble",
+    "gbrl_b200_fit", "gbrl_b200_fit_begin", "gbrl_b200_fit_iterate", "gbrl_b200_fit_end", "gbrl_b200_profile",
+    "gbrl_b200_get_profile", "gbrl_b200_predict", "gbrl_b200_get_metadata", "gbrl_b200_get_ensemble",
     "gbrl_b200_set_ensemble", "gbrl_b200_get_candidates", "gbrl_b200_get_root_scores", "gbrl_b200_dist_unique_id",
     "gbrl_b200_dist_init", "gbrl_b200_dist_shutdown", "gbrl_b200_microbench",
 ]
@@ -67,6 +68,11 @@ def lib():
     L.gbrl_b200_step.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
     L.gbrl_b200_fit.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, vp]
     L.gbrl_b200_predict.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.gbrl_b200_fit_begin.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.gbrl_b200_fit_iterate.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.gbrl_b200_fit_end.argtypes = [vp, fp, vp]
+    L.gbrl_b200_profile.argtypes = [vp, C.c_int]
+    L.gbrl_b200_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_longlong)]
     L.gbrl_b200_get_metadata.argtypes = [vp, C.POINTER(Metadata)]
     L.gbrl_b200_get_ensemble.argtypes = [vp, ip, ip, fp, ip, fp, fp, u8p]
     L.gbrl_b200_set_ensemble.argtypes = [vp, C.c_int, C.c_int, ip, ip, fp, ip, fp, fp, u8p, C.c_int]

@@ -101,6 +101,7 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     GB_CHECK(h.n_trees == m.ens.n_trees, "internal error: device/host tree count mismatch");
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
     m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
+    m.hist_rows = h.stat_hist_rows;
 }
 
 static void check_features(Model &m, int n_features) {
@@ -120,10 +121,10 @@ static void do_step(Model &m, const float *obs, int obs_dev, const float *grads,
     const float *X = stage_in(ws.xstage, obs, obs_dev, (size_t)N * F, s);
     const float *G = stage_in(ws.gstage, grads, grads_dev, (size_t)N * D, s);
     prepare_workspace(m, N, F, s);
-    compute_thresholds(m, X, N, F, s);          // fitter.cpp:72-90: candidates from the current observations
+    { ProfScope ps(m, P_CAND, s); compute_thresholds(m, X, N, F, s); }   // fitter.cpp:72-90: candidates from the current observations
     ws.codes_rows = N; ws.row_offset = 0;
-    bin_features(m, X, N, F, s);
-    build_grads(m, G, N, s);                    // fitter.cpp:57-64
+    { ProfScope ps(m, P_BIN, s); bin_features(m, X, N, F, s); }
+    { ProfScope ps(m, P_PRE, s); build_grads(m, G, N, s); }               // fitter.cpp:57-64
     grow_tree(m, X, G, N, F, s);                // fitter.cpp:98-102
     sync_ctl(m, s);
     m.iteration++;                              // fitter.cpp:114
@@ -138,93 +139,151 @@ __global__ void gather_rows_kernel(const float *src, const int *perm, float *dst
         dst[i] = src[(size_t)perm[i / W] * W + i % W];
 }
 
-static float do_fit(Model &m, const float *obs, int obs_dev, const float *targets, int targets_dev, int iterations, int N, int F,
-                    int shuffle, cudaStream_t s) {
+// ---------------------------------------------------------------- fit as a session
+// fit == fit_begin + fit_iterate(iterations) + fit_end.  bench.py uses the three pieces to time exactly K boosting
+// iterations with the inputs already resident in HBM; gbrl_b200_fit() is the reference-facing call.
+static void fit_begin(Model &m, const float *obs, int obs_dev, const float *targets, int targets_dev, int N, int F, int shuffle,
+                      cudaStream_t s) {
     GB_CHECK(N > 0, "fit: n_samples must be positive");
-    GB_CHECK(iterations >= 0, "fit: iterations must be >= 0");
     check_features(m, F);
     GB_CHECK(!m.opts.empty(), "fit: no optimizers set");
     GB_CUDA(cudaSetDevice(m.device));
     Workspace &ws = m.ws;
+    FitSession &fs = m.fs;
     const int D = m.cfg.output_dim, bs = m.cfg.batch_size;
     GB_CHECK(bs > 0, "fit: batch_size must be positive");
     const float *X = stage_in(ws.xstage, obs, obs_dev, (size_t)N * F, s);
     const float *Tg = stage_in(ws.tstage, targets, targets_dev, (size_t)N * D, s);
-    DevBuf xs, ts, permbuf;
     if (shuffle) {
         // gbrl.cpp:1017-1026: the reference shuffles with std::random_device (not reproducible); we do the same
         std::vector<int> perm(N);
         std::iota(perm.begin(), perm.end(), 0);
         std::random_device rd; std::mt19937 g(rd());
         std::shuffle(perm.begin(), perm.end(), g);
-        permbuf.ensure((size_t)N * sizeof(int)); xs.ensure((size_t)N * F * sizeof(float)); ts.ensure((size_t)N * D * sizeof(float));
+        DevBuf permbuf;
+        permbuf.ensure((size_t)N * sizeof(int)); m.fit_x.ensure((size_t)N * F * sizeof(float)); m.fit_t.ensure((size_t)N * D * sizeof(float));
         GB_CUDA(cudaMemcpyAsync(permbuf.p, perm.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, s));
-        GB_LAUNCH(gather_rows_kernel, 1184, 256, 0, s, X, permbuf.as<int>(), xs.as<float>(), N, F);
-        GB_LAUNCH(gather_rows_kernel, 1184, 256, 0, s, Tg, permbuf.as<int>(), ts.as<float>(), N, D);
+        GB_LAUNCH(gather_rows_kernel, 1184, 256, 0, s, X, permbuf.as<int>(), m.fit_x.as<float>(), N, F);
+        GB_LAUNCH(gather_rows_kernel, 1184, 256, 0, s, Tg, permbuf.as<int>(), m.fit_t.as<float>(), N, D);
         GB_CUDA(cudaStreamSynchronize(s));
-        X = xs.as<float>(); Tg = ts.as<float>();
+        X = m.fit_x.as<float>(); Tg = m.fit_t.as<float>();
     }
     prepare_workspace(m, N, F, s);
     // gbrl.cpp:1076-1078: bias := column mean of the targets (reference thread partition emulated)
-    column_mean_ref(m, Tg, N, D, m.bias.as<float>(), s);
+    { ProfScope ps(m, P_PRE, s); column_mean_ref(m, Tg, N, D, m.bias.as<float>(), s); }
     m.h_bias.resize(D);
     GB_CUDA(cudaMemcpyAsync(m.h_bias.data(), m.bias.p, D * sizeof(float), cudaMemcpyDeviceToHost, s));
     // fitter.cpp:134-151: candidates ONCE on the full data
-    compute_thresholds(m, X, N, F, s);
+    { ProfScope ps(m, P_CAND, s); compute_thresholds(m, X, N, F, s); }
     ws.codes_rows = N; ws.row_offset = 0;
-    bin_features(m, X, N, F, s);
-    const int n_trees0 = m.ens.n_trees;
-    const bool incremental = (n_trees0 == 0);
+    { ProfScope ps(m, P_BIN, s); bin_features(m, X, N, F, s); }
+    fs.n_trees0 = m.ens.n_trees;
+    fs.incremental = (fs.n_trees0 == 0);
     ws.preds_full.ensure((size_t)N * D * sizeof(float));
     // two gradient buffers like the reference (regular / last batch), zero-initialised once (fitter.cpp:125-130)
     const size_t gsz = (size_t)(bs < N ? bs : N) * D;
     ws.grads_fit.ensure((gsz + (size_t)(N % bs) * D + 2) * sizeof(float));
     GB_CUDA(cudaMemsetAsync(ws.grads_fit.p, 0, ws.grads_fit.bytes, s));
-    float *g_regular = ws.grads_fit.as<float>(), *g_last = g_regular + gsz;
-    if (incremental) GB_LAUNCH(fill_rows_kernel, 1184, 256, 0, s, ws.preds_full.as<float>(), m.bias.as<float>(), (long long)N, D);
-    int batch_start = 0;
-    int batch_n = batch_start + bs < N ? bs : N - batch_start;
-    DevBuf batch_preds;
-    for (int it = 0; it < iterations; ++it) {
-        const float *bX = X + (size_t)batch_start * F;
-        const float *bT = Tg + (size_t)batch_start * D;
-        const bool is_last = batch_start + bs > N;
-        float *grads = is_last ? g_last : g_regular;
+    fs.g_regular = ws.grads_fit.as<float>(); fs.g_last = fs.g_regular + gsz;
+    if (fs.incremental) GB_LAUNCH(fill_rows_kernel, 1184, 256, 0, s, ws.preds_full.as<float>(), m.bias.as<float>(), (long long)N, D);
+    fs.X = X; fs.T = Tg; fs.N = N; fs.F = F; fs.it = 0;
+    fs.batch_start = 0;
+    fs.batch_n = fs.batch_start + bs < N ? bs : N - fs.batch_start;
+    fs.active = true;
+}
+
+static void fit_iterate(Model &m, int iterations, cudaStream_t s) {
+    FitSession &fs = m.fs;
+    GB_CHECK(fs.active, "fit_iterate without fit_begin");
+    GB_CUDA(cudaSetDevice(m.device));
+    Workspace &ws = m.ws;
+    const int D = m.cfg.output_dim, bs = m.cfg.batch_size, N = fs.N, F = fs.F;
+    for (int k = 0; k < iterations; ++k, ++fs.it) {
+        const float *bX = fs.X + (size_t)fs.batch_start * F;
+        const float *bT = fs.T + (size_t)fs.batch_start * D;
+        const bool is_last = fs.batch_start + bs > N;
+        float *grads = is_last ? fs.g_last : fs.g_regular;
         const float *preds;
-        if (incremental) {
-            preds = ws.preds_full.as<float>() + (size_t)batch_start * D;
+        if (fs.incremental) {
+            preds = ws.preds_full.as<float>() + (size_t)fs.batch_start * D;
         } else {
             // fitter.cpp:191: predict_cpu(batch, 0, i): stop index 0 means "all trees"
-            batch_preds.ensure((size_t)batch_n * D * sizeof(float));
-            const int stop = (it == 0) ? m.ens.n_trees : std::min(it, m.ens.n_trees);
-            launch_predict(m, bX, batch_n, F, 0, stop, batch_preds.as<float>(), true, s);
-            preds = batch_preds.as<float>();
+            ProfScope ps(m, P_PRED, s);
+            m.fit_batch_preds.ensure((size_t)fs.batch_n * D * sizeof(float));
+            const int stop = (fs.it == 0) ? m.ens.n_trees : std::min(fs.it, m.ens.n_trees);
+            launch_predict(m, bX, fs.batch_n, F, 0, stop, m.fit_batch_preds.as<float>(), true, s);
+            preds = m.fit_batch_preds.as<float>();
         }
-        multirmse_grads(m, preds, bT, grads, batch_n, s);      // fitter.cpp:193-195
         // the tree is grown on the batch rows: order/nid are batch-relative, codes are addressed with row_offset
-        ws.N = batch_n; ws.row_offset = batch_start;
-        build_grads(m, grads, batch_n, s);                     // fitter.cpp:203-214
-        grow_tree(m, bX, grads, batch_n, F, s);                // fitter.cpp:220-225
-        if (incremental) launch_update_preds_last_tree(m, X, N, F, ws.preds_full.as<float>(), s);
-        batch_start += batch_n;                                // fitter.cpp:227-230
-        if (batch_start >= N) batch_start = 0;
-        batch_n = batch_start + bs < N ? bs : N - batch_start;
+        ws.N = fs.batch_n; ws.row_offset = fs.batch_start;
+        { ProfScope ps(m, P_PRE, s);
+          multirmse_grads(m, preds, bT, grads, fs.batch_n, s);      // fitter.cpp:193-195
+          build_grads(m, grads, fs.batch_n, s); }                   // fitter.cpp:203-214
+        grow_tree(m, bX, grads, fs.batch_n, F, s);                  // fitter.cpp:220-225
+        if (fs.incremental) { ProfScope ps(m, P_PRED, s); launch_update_preds_last_tree(m, fs.X, N, F, ws.preds_full.as<float>(), s); }
+        fs.batch_start += fs.batch_n;                               // fitter.cpp:227-230
+        if (fs.batch_start >= N) fs.batch_start = 0;
+        fs.batch_n = fs.batch_start + bs < N ? bs : N - fs.batch_start;
         m.iteration++;
     }
     ws.N = N; ws.row_offset = 0;
+}
+
+static float fit_end(Model &m, cudaStream_t s) {
+    FitSession &fs = m.fs;
+    GB_CHECK(fs.active, "fit_end without fit_begin");
+    Workspace &ws = m.ws;
+    const int D = m.cfg.output_dim, N = fs.N, F = fs.F;
     // fitter.cpp:244-250: full-data loss over trees [0, iterations)
     float loss = INFINITY;
     const float *fp;
-    if (incremental) fp = ws.preds_full.as<float>();
+    if (fs.incremental) fp = ws.preds_full.as<float>();
     else {
-        batch_preds.ensure((size_t)N * D * sizeof(float));
-        const int stop = (iterations == 0) ? m.ens.n_trees : std::min(iterations, m.ens.n_trees);
-        launch_predict(m, X, N, F, 0, stop, batch_preds.as<float>(), true, s);
-        fp = batch_preds.as<float>();
+        m.fit_batch_preds.ensure((size_t)N * D * sizeof(float));
+        const int stop = (fs.it == 0) ? m.ens.n_trees : std::min(fs.it, m.ens.n_trees);
+        launch_predict(m, fs.X, N, F, 0, stop, m.fit_batch_preds.as<float>(), true, s);
+        fp = m.fit_batch_preds.as<float>();
     }
-    multirmse_loss(m, fp, Tg, N, &loss, s);
+    multirmse_loss(m, fp, fs.T, N, &loss, s);
     sync_ctl(m, s);
+    fs.active = false;
     return loss;
+}
+
+static float do_fit(Model &m, const float *obs, int obs_dev, const float *targets, int targets_dev, int iterations, int N, int F,
+                    int shuffle, cudaStream_t s) {
+    GB_CHECK(iterations >= 0, "fit: iterations must be >= 0");
+    fit_begin(m, obs, obs_dev, targets, targets_dev, N, F, shuffle, s);
+    fit_iterate(m, iterations, s);
+    return fit_end(m, s);
+}
+
+// ---------------------------------------------------------------- profiling
+ProfScope::ProfScope(Model &m_, int cat_, cudaStream_t s_) : m(m_), cat(cat_), s(s_), on(m_.profile) {
+    if (!on) return;
+    if (m.prof_used + 2 > m.prof_events.size()) {
+        for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); m.prof_events.push_back(e); }
+    }
+    idx = m.prof_used; m.prof_used += 2;
+    m.prof_cats.push_back(cat);
+    l0 = g_kernel_launches.load();
+    cudaEventRecord(m.prof_events[idx], s);
+}
+ProfScope::~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(m.prof_events[idx + 1], s);
+    m.prof_launches.push_back(g_kernel_launches.load() - l0);
+}
+void prof_collect(Model &m, cudaStream_t s) {
+    cudaStreamSynchronize(s);
+    for (size_t i = 0; i < m.prof_cats.size(); ++i) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, m.prof_events[2 * i], m.prof_events[2 * i + 1]) == cudaSuccess) {
+            m.prof_ms[m.prof_cats[i]] += ms;
+            m.prof_n[m.prof_cats[i]] += m.prof_launches[i];
+        }
+    }
+    m.prof_cats.clear(); m.prof_launches.clear(); m.prof_used = 0;
 }
 
 static void do_predict(Model &m, const float *obs, int obs_dev, int N, int F, int start_tree, int stop_tree, float *preds,
@@ -247,7 +306,7 @@ static void do_predict(Model &m, const float *obs, int obs_dev, int N, int F, in
     if (!preds_dev) { ws.pstage.ensure((size_t)N * D * sizeof(float)); out = ws.pstage.as<float>(); }
     const bool have_opts = !m.opts.empty();
     // predictor.cpp:122-140: bias is always added; trees only if there are trees and optimizers
-    launch_predict(m, X, N, F, start_tree, (n_trees > 0 && have_opts) ? stop_tree : start_tree, out, true, s);
+    { ProfScope ps(m, P_PRED, s); launch_predict(m, X, N, F, start_tree, (n_trees > 0 && have_opts) ? stop_tree : start_tree, out, true, s); }
     if (!preds_dev) GB_CUDA(cudaMemcpyAsync(preds, out, (size_t)N * D * sizeof(float), cudaMemcpyDeviceToHost, s));
     GB_CUDA(cudaStreamSynchronize(s));
 }
@@ -428,6 +487,48 @@ int gbrl_b200_fit(gbrl_b200_model *h, const float *obs, int obs_dev, const float
     GB_CHECK(h && obs && targets, "null argument");
     const float l = gb::do_fit(h->m, obs, obs_dev, targets, targets_dev, iterations, n_samples, n_features, shuffle, (cudaStream_t)stream);
     if (loss_out) *loss_out = l;
+    API_END
+}
+
+int gbrl_b200_fit_begin(gbrl_b200_model *h, const float *obs, int obs_dev, const float *targets, int targets_dev, int n_samples,
+                        int n_features, int shuffle, void *stream) {
+    API_BEGIN
+    GB_CHECK(h && obs && targets, "null argument");
+    gb::fit_begin(h->m, obs, obs_dev, targets, targets_dev, n_samples, n_features, shuffle, (cudaStream_t)stream);
+    API_END
+}
+int gbrl_b200_fit_iterate(gbrl_b200_model *h, int iterations, int sync, void *stream) {
+    API_BEGIN
+    gb::fit_iterate(h->m, iterations, (cudaStream_t)stream);
+    if (sync) GB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    API_END
+}
+int gbrl_b200_fit_end(gbrl_b200_model *h, float *loss_out, void *stream) {
+    API_BEGIN
+    const float l = gb::fit_end(h->m, (cudaStream_t)stream);
+    if (loss_out) *loss_out = l;
+    API_END
+}
+
+int gbrl_b200_profile(gbrl_b200_model *h, int enable) {
+    API_BEGIN
+    Model &m = h->m;
+    if (!enable && m.profile) gb::prof_collect(m, 0);
+    m.profile = enable != 0;
+    if (enable) { for (int i = 0; i < gb::P_NCAT; ++i) { m.prof_ms[i] = 0; m.prof_n[i] = 0; } }
+    API_END
+}
+int gbrl_b200_get_profile(gbrl_b200_model *h, double *ms, long long *launches, int n, long long *hist_rows) {
+    API_BEGIN
+    Model &m = h->m;
+    GB_CUDA(cudaSetDevice(m.device));
+    gb::prof_collect(m, 0);
+    for (int i = 0; i < n && i < gb::P_NCAT; ++i) { if (ms) ms[i] = m.prof_ms[i]; if (launches) launches[i] = m.prof_n[i]; }
+    if (hist_rows) {
+        gb::Ctl c;
+        GB_CUDA(cudaMemcpy(&c, m.ws.ctl.p, sizeof(gb::Ctl), cudaMemcpyDeviceToHost));
+        *hist_rows = c.stat_hist_rows;
+    }
     API_END
 }
 

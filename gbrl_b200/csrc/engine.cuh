@@ -58,7 +58,8 @@ struct Ctl {
     int obl_depth;           // oblivious: depth reached
     int obl_has_replay;
     float obl_band;
-    long long stat_replay_items, stat_replay_nodes, stat_nodes_evaluated, stat_replay_overflow;
+    int bg_nonfinite;        // some build_grad is NaN/inf: the reference's scores are all NaN -> no split
+    long long stat_replay_items, stat_replay_nodes, stat_nodes_evaluated, stat_replay_overflow, stat_hist_rows;
 };
 
 // per-node arrays, heap indexed, MAXN = 2^(max_depth+1)-1 entries each
@@ -96,6 +97,16 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     int replay_cap = 0, items_cap = 0;
 };
 
+// per-kernel-class device timing (CUDA events on the launching stream), enabled by gbrl_b200_profile()
+enum ProfCat : int { P_CAND = 0, P_BIN, P_PRE, P_HIST, P_ALLREDUCE, P_SCAN, P_SELECT, P_DECIDE, P_PART, P_FIN, P_PRED, P_NCAT };
+
+struct FitSession {          // state of fit_begin / fit_iterate / fit_end (fitter.cpp:117-261)
+    bool active = false, incremental = true;
+    const float *X = nullptr, *T = nullptr;
+    int N = 0, F = 0, it = 0, batch_start = 0, batch_n = 0, n_trees0 = 0;
+    float *g_regular = nullptr, *g_last = nullptr;
+};
+
 struct Model {
     gbrl_b200_config cfg{};
     int device = 0;
@@ -113,7 +124,25 @@ struct Model {
     // statistics
     long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0;
     bool have_candidates = false;
+    long long hist_rows = 0;          // rows scanned by the histogram kernel (read back from Ctl)
+    FitSession fs;
+    DevBuf fit_x, fit_t, fit_batch_preds;
+    // profiling
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;      // pairs
+    std::vector<int> prof_cats;
+    std::vector<long long> prof_launches;
+    size_t prof_used = 0;
+    double prof_ms[P_NCAT] = {0};
+    long long prof_n[P_NCAT] = {0};
 };
+
+struct ProfScope {
+    Model &m; int cat; cudaStream_t s; size_t idx = 0; long long l0 = 0; bool on;
+    ProfScope(Model &m_, int cat_, cudaStream_t s_);
+    ~ProfScope();
+};
+void prof_collect(Model &m, cudaStream_t s);
 
 // ---------------------------------------------------------------- kernel launchers (one per .cu)
 // candidates.cu

@@ -31,8 +31,9 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
                                   int nT_local, int use_subtraction, int oblivious) {
     __shared__ int s_cnt[1024];
     __shared__ int s_total;
+    __shared__ unsigned long long s_rows;
     const int base = level_base(level), nn = 1 << level;
-    if (threadIdx.x == 0) s_total = 0;
+    if (threadIdx.x == 0) { s_total = 0; s_rows = 0; }
     __syncthreads();
     for (int n0 = 0; n0 < nn; n0 += blockDim.x) {
         const int p = n0 + threadIdx.x;
@@ -54,7 +55,7 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
                 }
                 if (!oblivious && len == 0) direct = 1;            // nothing to add, histogram stays zero
                 na.direct[h] = direct;
-                if (direct && len > 0) my = ceil_div(len, ITEM_ROWS) * nT_local;
+                if (direct && len > 0) { my = ceil_div(len, ITEM_ROWS) * nT_local; atomicAdd(&s_rows, (unsigned long long)len); }
             }
         }
         // block exclusive scan of `my`
@@ -87,7 +88,10 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
         if (threadIdx.x == blockDim.x - 1) s_total += incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) ctl->n_items = min(s_total, items_cap);
+    if (threadIdx.x == 0) {
+        ctl->n_items = min(s_total, items_cap);
+        ctl->stat_hist_rows += s_rows;
+    }
 }
 
 void launch_plan_level(Model &m, int level, cudaStream_t s) {

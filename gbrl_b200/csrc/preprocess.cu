@@ -86,6 +86,7 @@ divide_and_max_kernel(float *bg, const float *stdv, Ctl *ctl, long long n_elemen
         if (do_divide) { v = v / (stdv[i % D] + 1e-8f); bg[i] = v; }
         const float a = fabsf(v);
         if (a > mx && a < INFINITY) mx = a;
+        if (!(a < INFINITY) && which == 0) ctl->bg_nonfinite = 1;
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, __float_as_uint(mx));
@@ -96,6 +97,7 @@ __global__ void max_only_kernel(const float *g, Ctl *ctl, long long n_elements, 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_elements; i += (long long)gridDim.x * blockDim.x) {
         const float a = fabsf(g[i]);
         if (a > mx && a < INFINITY) mx = a;
+        if (!(a < INFINITY) && which == 0) ctl->bg_nonfinite = 1;
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, __float_as_uint(mx));
@@ -118,6 +120,7 @@ __global__ void qexp_kernel(Ctl *ctl, int which) {
 static void reset_max(Model &m, int which, cudaStream_t s) {
     Ctl *ctl = m.ws.ctl.as<Ctl>();
     GB_CUDA(cudaMemsetAsync(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, 0, sizeof(unsigned int), s));
+    if (which == 0) GB_CUDA(cudaMemsetAsync(&ctl->bg_nonfinite, 0, sizeof(int), s));
 }
 
 void column_mean_ref(Model &m, const float *mat, int N, int D, float *out_dev, cudaStream_t s) {

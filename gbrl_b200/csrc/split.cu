@@ -160,6 +160,7 @@ scan_kernel(ScanParams P, NodeArrays na) {
         for (int d = 0; d <= DM; ++d)
             if (d <= D) off[d] += s_tot[((size_t)c2 * FT + fl) * HS + d];
     const float parent = s_parent;
+    const bool poisoned = P.ctl->bg_nonfinite != 0;
     const float w = (f < P.F) ? P.fw[f] : 0.0f;
     const int depth = P.level;
     long long tot[DM];
@@ -199,6 +200,9 @@ scan_kernel(ScanParams P, NodeArrays na) {
         bool reused = false;
         for (int k = 0; k < depth; ++k) reused |= (s_path_f[k] == f && s_path_v[k] == tv);
         float sc = reused ? -INFINITY : side_score<DM>(P.score_func, D, nL, nR, SL, SR, P.min_data);
+        // a NaN build_grad poisons every candidate's sequential sum in the reference (e.g. n_samples == 1 with L2:
+        // std = sqrt(0 * 1/0)); NaN scores never win (fitter.cpp:338) -> the node stays a leaf
+        if (poisoned && !reused) sc = NAN;
         const int idx = f * P.B + b;
         float gain = sc;
         if (!P.oblivious) gain = sc * w - parent;

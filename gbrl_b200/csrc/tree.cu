@@ -277,20 +277,20 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
     Workspace &ws = m.ws;
     const int md = m.cfg.max_depth;
     ensure_ensemble_capacity(m, 1, s);
-    raw_grad_scale(m, raw_grads, N, s);
-    launch_init_tree(m, N, s);
+    { ProfScope ps(m, P_PRE, s); raw_grad_scale(m, raw_grads, N, s); launch_init_tree(m, N, s); }
     const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + ws.D) * sizeof(long long);
     for (int level = 0; level < md; ++level) {
-        launch_plan_level(m, level, s);
-        GB_CUDA(cudaMemsetAsync(ws.hist[level & 1].p, 0, slot_bytes << level, s));
-        launch_histogram(m, level, s);
-        if (m.world > 1) dist_allreduce_hist(m, ws.hist[level & 1].as<long long>(), (slot_bytes << level) / sizeof(long long), s);
-        launch_scan(m, level, s);
-        launch_select_and_replay(m, X, level, s);
-        launch_decide(m, level, s);
-        launch_partition(m, X, level, 0, s);
+        { ProfScope ps(m, P_DECIDE, s); launch_plan_level(m, level, s);
+          GB_CUDA(cudaMemsetAsync(ws.hist[level & 1].p, 0, slot_bytes << level, s)); }
+        { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
+        if (m.world > 1) { ProfScope ps(m, P_ALLREDUCE, s);
+            dist_allreduce_hist(m, ws.hist[level & 1].as<long long>(), (slot_bytes << level) / sizeof(long long), s); }
+        { ProfScope ps(m, P_SCAN, s); launch_scan(m, level, s); }
+        { ProfScope ps(m, P_SELECT, s); launch_select_and_replay(m, X, level, s); }
+        { ProfScope ps(m, P_DECIDE, s); launch_decide(m, level, s); }
+        { ProfScope ps(m, P_PART, s); launch_partition(m, X, level, 0, s); }
     }
-    launch_finalize_tree(m, raw_grads, N, 0, s);
+    { ProfScope ps(m, P_FIN, s); launch_finalize_tree(m, raw_grads, N, 0, s); }
     m.ens.n_trees += 1;   // host mirror; the exact n_leaves is read back by the caller (sync_ctl)
     m.ens.n_leaves_ub = (m.ens.n_leaves_ub > m.ens.n_leaves ? m.ens.n_leaves_ub : m.ens.n_leaves) + (1ll << md);
 }

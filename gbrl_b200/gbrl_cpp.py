@@ -211,6 +211,39 @@ class GBRL:
                                             1 if shuffle else 0, C.byref(loss), self._stream()))
         return float(loss.value)
 
+    # fit() in three pieces (engine extension used by bench.py; see include/gbrl_b200.h)
+    def fit_begin(self, obs, targets, shuffle=False):
+        t = _Arg(targets, "targets", "fit", False)
+        o = _Arg(obs, "obs", "fit", False)
+        self._fit_keep = (t, o)
+        n_samples = t.shape[0]
+        _capi.check(self._lib.gbrl_b200_fit_begin(self._h, o.ptr, o.dev, t.ptr, t.dev, n_samples, o.shape[1], 1 if shuffle else 0, self._stream()))
+
+    def fit_iterate(self, iterations, sync=True):
+        _capi.check(self._lib.gbrl_b200_fit_iterate(self._h, int(iterations), 1 if sync else 0, self._stream()))
+
+    def fit_end(self):
+        loss = C.c_float(0.0)
+        _capi.check(self._lib.gbrl_b200_fit_end(self._h, C.byref(loss), self._stream()))
+        self._fit_keep = None
+        return float(loss.value)
+
+    PROFILE_CLASSES = ("candidates", "binning", "preprocess", "histogram", "allreduce", "scan", "select_replay",
+                       "plan_decide", "partition", "finalize", "predict")
+
+    def profile(self, enable=True):
+        _capi.check(self._lib.gbrl_b200_profile(self._h, 1 if enable else 0))
+
+    def get_profile(self):
+        n = len(self.PROFILE_CLASSES)
+        ms = (C.c_double * n)()
+        ln = (C.c_longlong * n)()
+        rows = C.c_longlong(0)
+        _capi.check(self._lib.gbrl_b200_get_profile(self._h, ms, ln, n, C.byref(rows)))
+        out = {k: {"ms": ms[i], "launches": ln[i]} for i, k in enumerate(self.PROFILE_CLASSES)}
+        out["hist_rows"] = rows.value
+        return out
+
     def _predict_shape(self, o, categorical_obs):
         if categorical_obs is not None:
             raise NotImplementedError("categorical features are out of scope of the B200 engine (SURVEY 2.1 #19)")

@@ -97,6 +97,12 @@ int gbrl_b200_step(gbrl_b200_model *m, const float *obs, int obs_dev, const floa
 /* GBRL::fit gbrl.cpp:983-1104 -> supervised MultiRMSE loop; returns the final full-data loss */
 int gbrl_b200_fit(gbrl_b200_model *m, const float *obs, int obs_dev, const float *targets, int targets_dev,
                   int iterations, int n_samples, int n_features, int shuffle, float *loss_out, void *stream);
+/* fit() as three calls (fit == fit_begin + fit_iterate(iterations) + fit_end): lets a caller time exactly K
+ * boosting iterations of fitter.cpp:176-231 with the inputs already resident in HBM (bench.py). */
+int gbrl_b200_fit_begin(gbrl_b200_model *m, const float *obs, int obs_dev, const float *targets, int targets_dev,
+                        int n_samples, int n_features, int shuffle, void *stream);
+int gbrl_b200_fit_iterate(gbrl_b200_model *m, int iterations, int sync, void *stream);
+int gbrl_b200_fit_end(gbrl_b200_model *m, float *loss_out, void *stream);
 /* GBRL::predict gbrl.cpp:369-422; `preds` receives n_samples*output_dim floats */
 int gbrl_b200_predict(gbrl_b200_model *m, const float *obs, int obs_dev, int n_samples, int n_features,
                       int start_tree_idx, int stop_tree_idx, float *preds, int preds_dev, void *stream);
@@ -123,6 +129,13 @@ int gbrl_b200_get_root_scores(gbrl_b200_model *m, float *scores, int *n_candidat
 int gbrl_b200_dist_unique_id(uint8_t id[128]);
 int gbrl_b200_dist_init(gbrl_b200_model *m, const uint8_t id[128], int rank, int world_size);
 int gbrl_b200_dist_shutdown(gbrl_b200_model *m);
+
+/* per-kernel-class device timing with CUDA events on the launching stream (no reference equivalent).
+ * classes: 0 candidates, 1 binning, 2 gradient preprocessing, 3 histogram, 4 all-reduce, 5 split scan,
+ * 6 select+replay, 7 plan+decide, 8 partition, 9 leaf emission/values, 10 predict.  ms[i] / launches[i]
+ * accumulate since gbrl_b200_profile(m, 1); hist_rows = rows scanned by the histogram kernel since creation. */
+int gbrl_b200_profile(gbrl_b200_model *m, int enable);
+int gbrl_b200_get_profile(gbrl_b200_model *m, double *ms, long long *launches, int n, long long *hist_rows);
 
 /* microbenchmarks used by DESIGN.md's kernel budgets (not part of the reference surface) */
 int gbrl_b200_microbench(int which, int iters, double *result);
