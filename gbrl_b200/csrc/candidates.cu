@@ -161,8 +161,8 @@ bin_kernel(const float *__restrict__ X, const float *__restrict__ thrT, uint16_t
             if (mslot == 0) c[0] = pos; else if (mslot == 1) c[1] = pos; else if (mslot == 2) c[2] = pos; else c[3] = pos;
         }
         uint2 w;
-        w.x = c[0] | (c[1] << 16);
-        w.y = c[2] | (c[3] << 16);
+        w.x = (c[0] << CODE_SHIFT) | (c[1] << (16 + CODE_SHIFT));      // stored pre-scaled: see hist_kernel
+        w.y = (c[2] << CODE_SHIFT) | (c[3] << (16 + CODE_SHIFT));
         *reinterpret_cast<uint2 *>(out + (size_t)row * FT + g * 4) = w;
     }
 }

@@ -17,7 +17,8 @@ constexpr int LO_BITS = 18;       // fixed-point split: q = hi * 2^18 + lo, lo i
 constexpr int Q_BITS = 36;        // |q| < 2^35  (8192 rows * 2^18 < 2^31, 8192 * 2^17 = 2^30)
 constexpr int MAX_DEPTH_SUPPORTED = 12;
 constexpr int MAX_OPTS = 64;
-constexpr int HIST_THREADS = 256;
+constexpr int HIST_THREADS = 512;
+constexpr int CODE_SHIFT = 6;       // the code matrix stores code << 6 (byte offset of a histogram row / 2)
 constexpr int SCAN_THREADS = 256;
 
 // ---------------------------------------------------------------- errors

@@ -4,7 +4,8 @@
 //   X        [N x F]  fp32 row-major      caller's matrix (borrowed or staged copy)      node.cpp:339
 //   codes    [nT][N][32] u16              per-feature-tile candidate-bin codes of X:
 //                                         code(x) = #{j : thr[f][j] < x} in [0, n_bins]
-//                                         (x > thr[f][j]  <=>  code > j); 64 B per row and tile
+//                                         (x > thr[f][j]  <=>  code > j); stored as code << 6;
+//                                         64 B per row and tile
 //   bg       [N x D]  fp32                build_grads (fitter.cpp:57-64)
 //   order    [N] int32 (ping-pong)        rows grouped by tree node, ascending inside a node
 //                                         (== the reference's per-node sample_indices, node.cpp:86-96)

@@ -101,41 +101,70 @@ void launch_plan_level(Model &m, int level, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------- the histogram kernel
-// dynamic shared memory: (1 + 2*nd) planes of NB*FT int32
+// dynamic shared memory: (1 + 2*ND) planes of (NB+1)*FT int32; row 0 of every plane is a dump row for code 0
+// (x <= every threshold: right of no candidate), which keeps the inner loop branch-free.
+// The code matrix stores code*64 (u16), so byte offset of (code, feature fs) inside a plane = stored*2 + fs*4.
+constexpr int HPLANE = (NB + 1) * FT;          // ints per plane
+
+__device__ __forceinline__ void red_shared(unsigned int addr, int v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void red_shared_off(unsigned int addr, int v) {
+    asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(OFF) : "memory");
+}
+
 template <int ND>
-__global__ void __launch_bounds__(HIST_THREADS)
+__global__ void __launch_bounds__(HIST_THREADS, ND == 1 ? 2 : 1)
 hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, const int *__restrict__ order,
             const Item *__restrict__ items, const Ctl *__restrict__ ctl, long long *__restrict__ hist, int codes_rows,
             int row_offset, int D, int d0, int nT_local, int tile_lo, int nT_total, int write_count) {
     extern __shared__ int sh[];
-    constexpr int PLANE = NB * FT;
     constexpr int W = 1 + 2 * ND;
+    constexpr int PB = HPLANE * 4;               // plane size in bytes
     const int n_items = ctl->n_items;
     const float scale = exp2f((float)ctl->qexp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rl = (lane >> 3) & 3, g = lane & 7;
     const int HS = 1 + D;   // int64 words per (bin, feature)
 
-    for (int i = threadIdx.x; i < W * PLANE; i += HIST_THREADS) sh[i] = 0;
+    for (int i = threadIdx.x; i < W * HPLANE; i += HIST_THREADS) sh[i] = 0;
     __syncthreads();
+
+    // per-lane constants of the 4 rounds: which halfword of the 8-byte code quad, and its column offset.
+    // round k handles feature slot ms = (k + rl) & 3 of the lane's quad, so the 32 lanes of a warp always address
+    // 32 different features (= 32 different banks).
+    const unsigned int sbase = (unsigned int)__cvta_generic_to_shared(sh);
+    unsigned int lbase[4], psel[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ms = (k + rl) & 3;
+        lbase[k] = sbase + (unsigned int)(g * 4 + ms) * 4u;
+        const unsigned int lo = 2u * ms, hi = 2u * ms + 1u;
+        psel[k] = lo | (hi << 4) | ((hi | 8u) << 8) | ((hi | 8u) << 12);   // zero-extend the halfword (msb is 0)
+    }
 
     for (int itx = blockIdx.x; itx < n_items; itx += gridDim.x) {
         const Item it = items[itx];
         const uint16_t *ctile = codes + ((size_t)it.tile * codes_rows + row_offset) * FT;
-        for (int kb = it.k0 + warp * 32; kb < it.k1; kb += (HIST_THREADS / 32) * 32) {
-            const int k = kb + lane;
-            const int my_row = (k < it.k1) ? order[k] : -1;
+        constexpr int STEP = (HIST_THREADS / 32) * 32;
+        int kb = it.k0 + warp * 32;
+        int my_row = (kb + lane < it.k1) ? order[kb + lane] : -1;
+        for (; kb < it.k1; kb += STEP) {
+            const int cur_row = my_row;
+            const int kn = kb + STEP + lane;
+            my_row = (kn < it.k1) ? order[kn] : -1;            // prefetch the next block of row ids
             uint2 b[8];
             float gv[8][ND];
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                const int row = __shfl_sync(0xffffffffu, my_row, s * 4 + rl);
+                const int row = __shfl_sync(0xffffffffu, cur_row, s * 4 + rl);
                 if (row >= 0) {
                     b[s] = ld_nc_u2(reinterpret_cast<const uint2 *>(ctile + (size_t)row * FT + g * 4));
 #pragma unroll
                     for (int dd = 0; dd < ND; ++dd) gv[s][dd] = __ldg(bg + (size_t)row * D + d0 + dd);
                 } else {
-                    b[s] = make_uint2(0u, 0u);
+                    b[s] = make_uint2(0u, 0u);                  // code 0 -> dump row
 #pragma unroll
                     for (int dd = 0; dd < ND; ++dd) gv[s][dd] = 0.0f;
                 }
@@ -150,38 +179,34 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
                     hi[dd] = (int)(q >> LO_BITS);
                 }
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const int ms = (k4 + rl) & 3;
-                    const unsigned int word = (ms & 2) ? b[s].y : b[s].x;
-                    const int code = (ms & 1) ? (int)(word >> 16) : (int)(word & 0xffffu);
-                    if (code > 0) {
-                        const int idx = (code - 1) * FT + g * 4 + ms;
-                        atomicAdd(&sh[idx], 1);
-#pragma unroll
-                        for (int dd = 0; dd < ND; ++dd) {
-                            atomicAdd(&sh[(1 + 2 * dd) * PLANE + idx], lo[dd]);
-                            atomicAdd(&sh[(2 + 2 * dd) * PLANE + idx], hi[dd]);
-                        }
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned int cs = __byte_perm(b[s].x, b[s].y, psel[k]);   // code * 64
+                    const unsigned int addr = lbase[k] + cs * 2u;
+                    red_shared(addr, 1);
+                    red_shared_off<PB>(addr, lo[0]);
+                    red_shared_off<2 * PB>(addr, hi[0]);
+                    if (ND > 1) { red_shared_off<3 * PB>(addr, lo[ND > 1 ? 1 : 0]); red_shared_off<4 * PB>(addr, hi[ND > 1 ? 1 : 0]); }
+                    if (ND > 2) { red_shared_off<5 * PB>(addr, lo[ND > 2 ? 2 : 0]); red_shared_off<6 * PB>(addr, hi[ND > 2 ? 2 : 0]); }
                 }
             }
         }
         __syncthreads();
-        // flush: (bin, feature) e -> global [slot][tile][bin][feature][1+D]
-        long long *hb = hist + ((size_t)it.slot * nT_total + (tile_lo + it.tile)) * (size_t)PLANE * HS;
-        for (int e = threadIdx.x; e < PLANE; e += HIST_THREADS) {
-            const int cnt = sh[e];
+        // flush: (bin, feature) e -> global [slot][tile][bin][feature][1+D]; shared row = bin + 1
+        long long *hb = hist + ((size_t)it.slot * nT_total + (tile_lo + it.tile)) * (size_t)(NB * FT) * HS;
+        for (int e = threadIdx.x; e < NB * FT; e += HIST_THREADS) {
+            const int se = e + FT;
+            const int cnt = sh[se];
             if (cnt != 0) {
                 if (write_count) red_add64(hb + (size_t)e * HS, (long long)cnt);
-                sh[e] = 0;
+                sh[se] = 0;
 #pragma unroll
                 for (int dd = 0; dd < ND; ++dd) {
-                    const unsigned int l = (unsigned int)sh[(1 + 2 * dd) * PLANE + e];
-                    const int h = sh[(2 + 2 * dd) * PLANE + e];
+                    const unsigned int l = (unsigned int)sh[(1 + 2 * dd) * HPLANE + se];
+                    const int h = sh[(2 + 2 * dd) * HPLANE + se];
                     const long long tot = ((long long)h << LO_BITS) + (long long)l;
                     if (tot != 0) red_add64(hb + (size_t)e * HS + 1 + d0 + dd, tot);
-                    sh[(1 + 2 * dd) * PLANE + e] = 0;
-                    sh[(2 + 2 * dd) * PLANE + e] = 0;
+                    sh[(1 + 2 * dd) * HPLANE + se] = 0;
+                    sh[(2 + 2 * dd) * HPLANE + se] = 0;
                 }
             }
         }
@@ -192,7 +217,7 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
 template <int ND>
 static void launch_hist_nd(Model &m, int d0, int write_count, long long *hist, int n_sms, cudaStream_t s) {
     Workspace &ws = m.ws;
-    const size_t smem = (size_t)(1 + 2 * ND) * NB * FT * sizeof(int);
+    const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int);
     static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[ND]) {
         GB_CUDA(cudaFuncSetAttribute(hist_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,44 +26,43 @@ __host__ __device__ inline int calc_threads(long long total, int min_per_thread,
 
 // chains (t, col): partial[t*D + col] = sequential sum over i in [t*ept, (t+1)*ept or end), i % D == col
 // mode 0: sum x          mode 1: sum (x-mean)^2 and center x in place
-__global__ void __launch_bounds__(256)
+// One WARP per reference thread t: the 32 lanes load 32 consecutive elements (coalesced), then the elements are
+// consumed strictly in memory order -- value j is broadcast with a shuffle and added by the lane that owns its
+// column (lane = col % 32), so every per-column chain sees its elements in the reference's order while the loads
+// stay coalesced.
+__global__ void __launch_bounds__(128)
 ref_chain_kernel(float *mat, const float *mean, float *partial, long long n_elements, int D, int T, int mode) {
-    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chain >= T * D) return;
-    const int t = chain / D, col = chain % D;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int lane = threadIdx.x & 31;
     const long long ept = n_elements / T;
     const long long s = (long long)t * ept, e = (t == T - 1) ? n_elements : s + ept;
-    long long i = s + ((col - (s % D)) % D + D) % D;
-    float acc = 0.0f;
-    if (mode == 0) {
-        for (; i + 7 * (long long)D < e; i += 8 * (long long)D) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = mat[i + (long long)j * D];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc = acc + v[j];
-        }
-        for (; i < e; i += D) acc = acc + mat[i];
-    } else {
-        const float mu = mean[col];
-        for (; i + 7 * (long long)D < e; i += 8 * (long long)D) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = mat[i + (long long)j * D];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float c = v[j] - mu;
-                acc = acc + c * c;
-                mat[i + (long long)j * D] = c;
+    float acc0 = 0.0f, acc1 = 0.0f;              // columns lane and lane + 32
+    int c0 = (int)(s % D);                       // column of element i0
+    for (long long i0 = s; i0 < e; i0 += 32) {
+        const long long i = i0 + lane;
+        float v = 0.0f;
+        if (i < e) {
+            v = mat[i];
+            if (mode == 1) {
+                const int col = (int)((c0 + lane) % D);
+                const float c = v - mean[col];
+                mat[i] = c;
+                v = c * c;
             }
         }
-        for (; i < e; i += D) {
-            const float c = mat[i] - mu;
-            acc = acc + c * c;
-            mat[i] = c;
+        const int cnt = (e - i0) < 32 ? (int)(e - i0) : 32;
+        int col = c0;
+#pragma unroll 8
+        for (int j = 0; j < cnt; ++j) {
+            const float vj = __shfl_sync(0xffffffffu, v, j);
+            if ((col & 31) == lane) { if (col < 32) acc0 = acc0 + vj; else acc1 = acc1 + vj; }
+            ++col; if (col == D) col = 0;
         }
+        c0 = (int)((c0 + 32) % D);
     }
-    partial[chain] = acc;
+    if (lane < D) partial[(size_t)t * D + lane] = acc0;
+    if (lane + 32 < D) partial[(size_t)t * D + lane + 32] = acc1;
 }
 
 // merge partials in thread order (d = 0..T*D-1, column d % D), then finish
@@ -129,7 +128,7 @@ void column_mean_ref(Model &m, const float *mat, int N, int D, float *out_dev, c
     const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
     ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
     float *partial = ws.lrs.as<float>();
-    GB_LAUNCH(ref_chain_kernel, ceil_div(T * D, 256), 256, 0, s, const_cast<float *>(mat), nullptr, partial, ne, D, T, 0);
+    GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, const_cast<float *>(mat), nullptr, partial, ne, D, T, 0);
     GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, out_dev, D, T, N, 0);
 }
 
@@ -148,9 +147,9 @@ void build_grads(Model &m, const float *grads, int N, cudaStream_t s) {
         const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
         ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
         float *partial = ws.lrs.as<float>(), *mean = partial + (size_t)T * D, *stdv = mean + D;
-        GB_LAUNCH(ref_chain_kernel, ceil_div(T * D, 256), 256, 0, s, ws.bg.as<float>(), nullptr, partial, ne, D, T, 0);
+        GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, ws.bg.as<float>(), nullptr, partial, ne, D, T, 0);
         GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, mean, D, T, N, 0);
-        GB_LAUNCH(ref_chain_kernel, ceil_div(T * D, 256), 256, 0, s, ws.bg.as<float>(), mean, partial, ne, D, T, 1);
+        GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, ws.bg.as<float>(), mean, partial, ne, D, T, 1);
         GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, stdv, D, T, N, 1);
         GB_LAUNCH(divide_and_max_kernel, grid, 256, 0, s, ws.bg.as<float>(), stdv, ctl, ne, D, 1, 0);
     } else if (ne > 0) {

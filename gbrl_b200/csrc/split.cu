@@ -424,55 +424,112 @@ struct ReplayParams {
     const Ctl *ctl;
 };
 
-// One warp per item.  Rows of the node are visited in ascending sample order (== reference sample_indices);
-// lane d owns output dimension d (chains over samples are independent per dimension); the Cosine
-// numerators are a single chain over (row, col) and are run by every lane redundantly.
-__global__ void __launch_bounds__(128) replay_kernel(ReplayParams P, NodeArrays na) {
+// One 128-thread CTA per item.  Rows of the node are visited in ascending sample order (== reference
+// sample_indices).  The chain itself is inherently sequential (every float add depends on the previous one), so
+// the kernel is organised around keeping that one chain fed: all four warps gather the next stage of rows
+// (order -> feature value -> gradients; the loads are issued before the chain of the current stage starts and
+// land in registers while it runs), warp 0 runs the chain out of shared memory, lane d owning output dimension d.
+// The Cosine numerators are one chain over (row, col) (mat_vec_dot_sum) and are run by every lane redundantly.
+constexpr int RP_THREADS = 128;
+
+template <int R, int PASS>
+__device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, float *sg /*[2][STAGE*D]*/,
+                                            unsigned int *smask /*[2][STAGE/32]*/, const float *smean, float *accL, float *accR,
+                                            int &nR, float &tnum, float &fnum) {
+    constexpr int STAGE = RP_THREADS * R;
+    const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_stages = (n + STAGE - 1) / STAGE;
+    int rows[R];
+    float xv[R];
+    // prologue: stage 0 -> registers
+    auto issue = [&](int st) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = st * STAGE + r * RP_THREADS + tid;
+            rows[r] = (k < n) ? P.order[s0 + k] : -1;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) xv[r] = (rows[r] >= 0 && is_cand) ? P.X[(size_t)rows[r] * P.F + f] : -INFINITY;
+    };
+    auto commit = [&](int st, int buf) {
+        float *g = sg + (size_t)buf * STAGE * D;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int slot = r * RP_THREADS + tid;
+            const bool right = rows[r] >= 0 && (xv[r] > tv);                     // node.cpp:339
+            const unsigned int m = __ballot_sync(0xffffffffu, right);
+            if (lane == 0) smask[buf * (STAGE / 32) + slot / 32] = m;
+            if (rows[r] >= 0)
+                for (int d = 0; d < D; ++d) g[(size_t)slot * D + d] = P.bg[(size_t)rows[r] * D + d];
+        }
+        (void)st;
+    };
+    issue(0);
+    commit(0, 0);
+    __syncthreads();
+    for (int st = 0; st < n_stages; ++st) {
+        const int buf = st & 1;
+        if (st + 1 < n_stages) issue(st + 1);
+        if (warp == 0) {
+            const float *g = sg + (size_t)buf * STAGE * D;
+            const int cnt = min(STAGE, n - st * STAGE);
+            for (int w = 0; w * 32 < cnt; ++w) {
+                const unsigned int mask = smask[buf * (STAGE / 32) + w];
+                const int c32 = min(32, cnt - w * 32);
+                if (PASS == 0) {
+                    nR += __popc(mask & (c32 == 32 ? 0xffffffffu : ((1u << c32) - 1u)));
+#pragma unroll 8
+                    for (int t = 0; t < c32; ++t) {
+                        const bool r = (mask >> t) & 1u;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int d = lane + 32 * q;
+                            if (d < D) {
+                                const float v = g[(size_t)(w * 32 + t) * D + d];
+                                if (r) accR[q] = accR[q] + v; else accL[q] = accL[q] + v;   // node.cpp:341-350
+                            }
+                        }
+                    }
+                } else {
+                    // mat_vec_dot_sum chains (math_ops.h:432-449): rows in order, columns inner
+                    for (int t = 0; t < c32; ++t) {
+                        const bool r = (mask >> t) & 1u;
+                        const float *gr = g + (size_t)(w * 32 + t) * D;
+                        if (r) { for (int d = 0; d < D; ++d) tnum = tnum + gr[d] * smean[D + d]; }
+                        else   { for (int d = 0; d < D; ++d) fnum = fnum + gr[d] * smean[d]; }
+                    }
+                }
+            }
+        }
+        if (st + 1 < n_stages) commit(st + 1, buf ^ 1);
+        __syncthreads();
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, NodeArrays na) {
     extern __shared__ float s_dyn[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int D = P.D;
-    float *sg = s_dyn + (size_t)wib * (32 * D + 2 * D);     // [32][D] gradient tile
-    float *smean = sg + 32 * D;                             // [2][D]  left / right means
+    constexpr int STAGE = RP_THREADS * R;
+    const int D = P.D, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *sg = s_dyn;                                           // [2][STAGE][D]
+    float *smean = sg + (size_t)2 * STAGE * D;                   // [2][D] left / right means
+    unsigned int *smask = reinterpret_cast<unsigned int *>(smean + 2 * D);   // [2][STAGE/32]
     const int n_items = P.ctl->n_replay;
-    for (int it = blockIdx.x * wpb + wib; it < n_items; it += gridDim.x * wpb) {
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         const ReplayItem item = P.items[it];
         const int h = item.node, cand = item.cand;
         const int s0 = na.seg_start[h], n = na.seg_len[h];
         const int f = cand >= 0 ? cand / P.B : 0;
         const float tv = cand >= 0 ? P.thr[cand] : INFINITY;
-        float result;
-        int nL = 0, nR = 0;
         float accL[2] = {0.0f, 0.0f}, accR[2] = {0.0f, 0.0f};    // lane d and lane d+32 (D <= 64)
-        for (int kb = 0; kb < n; kb += 32) {
-            const int k = kb + lane;
-            bool right = false;
-            if (k < n) {
-                const int i = P.order[s0 + k];
-                right = cand >= 0 && (P.X[(size_t)i * P.F + f] > tv);          // node.cpp:339
-                for (int d = 0; d < D; ++d) sg[lane * D + d] = P.bg[(size_t)i * D + d];
-            }
-            __syncwarp();
-            const unsigned int mask = __ballot_sync(0xffffffffu, right);
-            const int cnt = min(32, n - kb);
-            nR += __popc(mask & (cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u)));
-            for (int t = 0; t < cnt; ++t) {
-                const bool r = (mask >> t) & 1u;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int d = lane + 32 * q;
-                    if (d < D) {
-                        const float v = sg[t * D + d];
-                        if (r) accR[q] = accR[q] + v; else accL[q] = accL[q] + v;   // node.cpp:341-350
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        nL = n - nR;
-        if (cand >= 0 && (nL < P.min_data || nR < P.min_data)) {
-            result = -INFINITY;
-        } else {
-            const float lcf = (float)nL, rcf = (float)nR;
+        int nR = 0;
+        float tnum = 0.0f, fnum = 0.0f;
+        replay_pass<R, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, nR, tnum, fnum);
+        const int nL = n - nR;     // valid in warp 0
+        const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
+        const float lcf = (float)nL, rcf = (float)nR;
+        float ln = 0.0f, rn = 0.0f;
+        if (warp == 0) {
             float lrec, rrec;
             if (cand >= 0) { lrec = nL > 0 ? 1.0f / lcf : 0.0f; rrec = nR > 0 ? 1.0f / rcf : 0.0f; }
             else { lrec = 1.0f / lcf; rrec = 0.0f; }   // parent: n_samples_recip = 1/n (split_candidate_generator.cpp:265,296)
@@ -482,43 +539,26 @@ __global__ void __launch_bounds__(128) replay_kernel(ReplayParams P, NodeArrays 
                 if (d < D) { smean[d] = accL[q] * lrec; smean[D + d] = accR[q] * rrec; }
             }
             __syncwarp();
-            float ln = 0.0f, rn = 0.0f;
             for (int d = 0; d < D; ++d) { ln = ln + smean[d] * smean[d]; rn = rn + smean[D + d] * smean[D + d]; }  // squared_norm
-            if (P.score_func == GBRL_B200_SCORE_L2) {
-                result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
+        }
+        __syncthreads();
+        float result = 0.0f;
+        if (P.score_func == GBRL_B200_SCORE_L2) {
+            result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
+        } else {
+            replay_pass<R, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, nR, tnum, fnum);
+            if (cand >= 0) {
+                const float num = tnum + fnum;
+                const float den = rn * rcf + ln * lcf;
+                result = (den == 0.0f) ? 0.0f : num / sqrtf(den);
             } else {
-                // second pass: mat_vec_dot_sum chains (math_ops.h:432-449), rows in order, columns inner
-                float tnum = 0.0f, fnum = 0.0f;
-                for (int kb = 0; kb < n; kb += 32) {
-                    const int k = kb + lane;
-                    bool right = false;
-                    if (k < n) {
-                        const int i = P.order[s0 + k];
-                        right = cand >= 0 && (P.X[(size_t)i * P.F + f] > tv);
-                        for (int d = 0; d < D; ++d) sg[lane * D + d] = P.bg[(size_t)i * D + d];
-                    }
-                    __syncwarp();
-                    const unsigned int mask = __ballot_sync(0xffffffffu, right);
-                    const int cnt = min(32, n - kb);
-                    for (int t = 0; t < cnt; ++t) {
-                        const bool r = (mask >> t) & 1u;
-                        if (r) { for (int d = 0; d < D; ++d) tnum = tnum + sg[t * D + d] * smean[D + d]; }
-                        else   { for (int d = 0; d < D; ++d) fnum = fnum + sg[t * D + d] * smean[d]; }
-                    }
-                    __syncwarp();
-                }
-                if (cand >= 0) {
-                    const float num = tnum + fnum;
-                    const float den = rn * rcf + ln * lcf;
-                    result = (den == 0.0f) ? 0.0f : num / sqrtf(den);
-                } else {
-                    const float den = ln * lcf;
-                    result = (n == 0 || den == 0.0f) ? 0.0f : fnum / sqrtf(den);
-                }
+                const float den = ln * lcf;
+                result = (n == 0 || den == 0.0f) ? 0.0f : fnum / sqrtf(den);
             }
         }
-        if (lane == 0) P.out[it] = result;
-        __syncwarp();
+        if (invalid) result = -INFINITY;
+        if (threadIdx.x == 0) P.out[it] = result;
+        __syncthreads();
     }
 }
 
@@ -713,8 +753,16 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         R.F = ws.F; R.B = ws.B; R.D = ws.D; R.score_func = m.cfg.split_score_func; R.min_data = m.cfg.min_data_in_leaf;
         R.X = X; R.bg = ws.bg.as<float>(); R.order = ws.order[0].as<int>(); R.thr = ws.thr.as<float>();
         R.items = ws.replay.as<ReplayItem>(); R.out = ws.replay_scores.as<float>(); R.ctl = ctl;
-        const size_t smem = (size_t)4 * (32 * ws.D + 2 * ws.D) * sizeof(float);
-        GB_LAUNCH(replay_kernel, 148 * 4, 128, smem, s, R, ws.na);
+        // rows per thread per stage: 8 (1024-row stages) for D == 1 down to 1 for wide outputs, so that a stage's
+        // gradients fit in registers while they are in flight and two stages fit in shared memory
+        const int D = ws.D;
+        const int rpt = D <= 1 ? 8 : D <= 2 ? 4 : D <= 4 ? 2 : 1;
+        const size_t smem = ((size_t)2 * RP_THREADS * rpt * D + 2 * D) * sizeof(float) + (size_t)2 * (RP_THREADS * rpt / 32) * sizeof(unsigned int);
+        if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rpt == 8) GB_LAUNCH(replay_kernel<8>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
+        else if (rpt == 4) GB_LAUNCH(replay_kernel<4>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
+        else if (rpt == 2) GB_LAUNCH(replay_kernel<2>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
+        else GB_LAUNCH(replay_kernel<1>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
     }
 }
 
