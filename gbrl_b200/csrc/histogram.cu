@@ -136,12 +136,14 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
     // 32 different features (= 32 different banks).
     const unsigned int sbase = (unsigned int)__cvta_generic_to_shared(sh);
     unsigned int lbase[4], psel[4];
+    bool upper[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int ms = (k + rl) & 3;
         lbase[k] = sbase + (unsigned int)(g * 4 + ms) * 4u;
-        const unsigned int lo = 2u * ms, hi = 2u * ms + 1u;
-        psel[k] = lo | (hi << 4) | ((hi | 8u) << 8) | ((hi | 8u) << 12);   // zero-extend the halfword (msb is 0)
+        upper[k] = (ms & 2) != 0;                              // halfword lives in .y
+        const unsigned int lo = 2u * (ms & 1), hi = lo + 1u;   // bytes of the halfword inside its 32-bit word
+        psel[k] = lo | (hi << 4) | (4u << 8) | (4u << 12);     // upper two bytes from the zero operand
     }
 
     for (int itx = blockIdx.x; itx < n_items; itx += gridDim.x) {
@@ -180,7 +182,7 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const unsigned int cs = __byte_perm(b[s].x, b[s].y, psel[k]);   // code * 64
+                    const unsigned int cs = __byte_perm(upper[k] ? b[s].y : b[s].x, 0u, psel[k]);   // code * 64, zero-extended
                     const unsigned int addr = lbase[k] + cs * 2u;
                     red_shared(addr, 1);
                     red_shared_off<PB>(addr, lo[0]);
