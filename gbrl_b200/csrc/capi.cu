@@ -62,7 +62,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     ws.scores.ensure((C << lv) * sizeof(float));
     ws.cand_flags.ensure(C << lv);
     ws.obl_tot.ensure(C * sizeof(float));
-    size_t tb = (size_t)ws.nT << lv;
+    size_t tb = (size_t)F << lv;
     if (tb < C / 256 + 1) tb = C / 256 + 1;
     ws.tile_best.ensure(tb * sizeof(float2));
     ws.items_cap = (N / ITEM_ROWS + (1 << md) + 1) * (ws.tile_hi - ws.tile_lo > 0 ? ws.tile_hi - ws.tile_lo : 1);

@@ -34,7 +34,7 @@ struct ScanParams {
     const float *fw;                          // feature weights [input_dim]
     float *scores;                            // [slot][C]
     uint8_t *cand_flags;                      // greedy: [slot][C] bit0 = dominated; oblivious: [C] bit1 = empty code below
-    float2 *tile_best;                        // [slot][nT] (gain, idx as float bits)
+    float2 *tile_best;                        // [slot][F] per-(node, feature) best (gain, idx as float bits)
     const Ctl *ctl;
 };
 
@@ -91,25 +91,34 @@ __device__ __forceinline__ bool better(float ga, int ia, float gb_, int ib) {
     return (ga > gb_) || (ga == gb_ && ia < ib);
 }
 
-// one CTA per (node slot, feature tile); thread (c = tid>>5, fl = tid&31) owns codes [32c, 32c+32) of
-// feature tile*32+fl.  Histogram layout [bin][feature][1+D] makes every load of a warp one contiguous
-// 32*(1+D)*8-byte run.
+// One CTA per (node slot, feature): thread t owns code-bin b = 255 - t, so an inclusive prefix scan over t is the
+// suffix sum over bins that turns the histogram into per-candidate right-side sums: candidate j = b of the feature
+// has right = sum of bins >= b.  All 256 candidates of a feature are scored in parallel; (1+D) int64 scans by
+// warp shuffles + one shared-memory hop.
+__device__ __forceinline__ long long shfl_up_ll(long long v, int d) {
+    int lo = __shfl_up_sync(0xffffffffu, (int)(v & 0xffffffffll), d);
+    int hi = __shfl_up_sync(0xffffffffu, (int)(v >> 32), d);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+
 template <int DM>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(ScanParams P, NodeArrays na) {
-    extern __shared__ long long s_tot[];        // [8][32][1+D]
-    __shared__ float s_gain[SCAN_THREADS];
-    __shared__ int s_idx[SCAN_THREADS];
+    __shared__ long long s_wtot[8][1 + DM];
+    __shared__ int s_cnt[NB];
+    __shared__ float s_gain[8];
+    __shared__ int s_idx[8];
     __shared__ int s_path_f[MAX_DEPTH_SUPPORTED];
     __shared__ float s_path_v[MAX_DEPTH_SUPPORTED];
     __shared__ float s_parent;
-    const int p = blockIdx.x / P.nT, tile = blockIdx.x % P.nT;
+    const int p = blockIdx.x / P.F, f = blockIdx.x % P.F;
     const int h = level_base(P.level) + p;
     if (na.state[h] != NODE_OPEN) return;
+    const int tile = f / FT, fl = f % FT;
     const int D = P.D, HS = 1 + D;
     const int n = na.seg_len[h];
-    const int c = threadIdx.x >> 5, fl = threadIdx.x & 31;
-    const int f = tile * FT + fl;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int b = NB - 1 - t;
     const bool derived = (P.level > 0) && P.use_subtraction && (na.direct[h] == 0);
     const double inv_scale = exp2((double)(-P.ctl->qexp));
     const size_t tile_words = (size_t)NB * FT * HS;
@@ -122,7 +131,7 @@ scan_kernel(ScanParams P, NodeArrays na) {
         Hp = P.hist_par + ((size_t)(par - level_base(P.level - 1)) * P.nT + tile) * tile_words;
     }
     // ancestors' conditions (path guard) and the parent score, once per CTA
-    if (threadIdx.x == 0) {
+    if (t == 0) {
         int a = h, k = 0;
         while (a > 0) {
             const int par = (a - 1) >> 1;
@@ -135,65 +144,59 @@ scan_kernel(ScanParams P, NodeArrays na) {
         float ps = 0.0f;
         if (!P.oblivious && P.level > 0) ps = node_parent_score<DM>(P.score_func, D, n, na.tot_sum + (size_t)h * D, inv_scale);
         s_parent = ps;
-        if (tile == 0) na.parent_score[h] = ps;
+        if (f == 0) na.parent_score[h] = ps;
     }
-    // phase 1: per-chunk totals
-    long long run[1 + DM];
+    // load this bin (derived nodes: parent - sibling, written back for the next level)
+    const size_t o = ((size_t)b * FT + fl) * HS;
+    long long v[1 + DM];
 #pragma unroll
-    for (int d = 0; d <= DM; ++d) run[d] = 0;
-    for (int b = 32 * c; b < 32 * c + 32; ++b) {
-        const size_t o = ((size_t)b * FT + fl) * HS;
-#pragma unroll
-        for (int d = 0; d <= DM; ++d)
-            if (d <= D) run[d] += derived ? (Hp[o + d] - Hs[o + d]) : Hc[o + d];
+    for (int d = 0; d <= DM; ++d) {
+        v[d] = 0;
+        if (d <= D) {
+            v[d] = derived ? (Hp[o + d] - Hs[o + d]) : Hc[o + d];
+            if (derived) Hc[o + d] = v[d];
+        }
     }
+    s_cnt[b] = (int)v[0];
+    // inclusive scan over t (== suffix sum over bins)
 #pragma unroll
-    for (int d = 0; d <= DM; ++d)
-        if (d <= D) s_tot[((size_t)c * FT + fl) * HS + d] = run[d];
+    for (int d = 0; d <= DM; ++d) {
+        if (d <= D) {
+            long long x = v[d];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const long long y = shfl_up_ll(x, off);
+                if (lane >= off) x += y;
+            }
+            v[d] = x;
+            if (lane == 31) s_wtot[warp][d] = x;
+        }
+    }
     __syncthreads();
-    // offset = totals of the chunks above
-    long long off[1 + DM];
 #pragma unroll
-    for (int d = 0; d <= DM; ++d) off[d] = 0;
-    for (int c2 = c + 1; c2 < 8; ++c2)
-#pragma unroll
-        for (int d = 0; d <= DM; ++d)
-            if (d <= D) off[d] += s_tot[((size_t)c2 * FT + fl) * HS + d];
+    for (int d = 0; d <= DM; ++d) {
+        if (d <= D) {
+            long long add = 0;
+            for (int w = 0; w < warp; ++w) add += s_wtot[w][d];
+            v[d] += add;
+        }
+    }
     const float parent = s_parent;
     const bool poisoned = P.ctl->bg_nonfinite != 0;
-    const float w = (f < P.F) ? P.fw[f] : 0.0f;
+    const float w = P.fw[f];
     const int depth = P.level;
-    long long tot[DM];
-#pragma unroll
-    for (int d = 0; d < DM; ++d) tot[d] = (d < D) ? na.tot_sum[(size_t)h * D + d] : 0;
-    float bestg = -INFINITY;
-    int besti = INT_MAX;
-#pragma unroll
-    for (int d = 0; d <= DM; ++d) run[d] = 0;
-    // phase 2: descending codes -> suffix sums -> scores
-    for (int b = 32 * c + 31; b >= 32 * c; --b) {
-        const size_t o = ((size_t)b * FT + fl) * HS;
-        long long v[1 + DM];
-#pragma unroll
-        for (int d = 0; d <= DM; ++d) {
-            v[d] = 0;
-            if (d <= D) {
-                v[d] = derived ? (Hp[o + d] - Hs[o + d]) : Hc[o + d];
-                run[d] += v[d];
-                if (derived) Hc[o + d] = v[d];
-            }
-        }
-        if (f >= P.F || b >= P.B) continue;
-        // candidate j = b of feature f: right = codes > b  == bins >= b
-        const int nR = (int)(off[0] + run[0]);
+    float gain = -INFINITY;
+    int idx = INT_MAX;
+    if (b < P.B) {
+        const int nR = (int)v[0];
         const int nL = n - nR;
         float SL[DM], SR[DM];
 #pragma unroll
         for (int d = 0; d < DM; ++d) {
             if (d < D) {
-                const long long r = off[1 + d] + run[1 + d];
+                const long long r = v[1 + d];
                 SR[d] = (float)((double)r * inv_scale);
-                SL[d] = (float)((double)(tot[d] - r) * inv_scale);
+                SL[d] = (float)((double)(na.tot_sum[(size_t)h * D + d] - r) * inv_scale);
             } else { SR[d] = 0.0f; SL[d] = 0.0f; }
         }
         const float tv = P.thr[(size_t)f * P.B + b];
@@ -203,47 +206,38 @@ scan_kernel(ScanParams P, NodeArrays na) {
         // a NaN build_grad poisons every candidate's sequential sum in the reference (e.g. n_samples == 1 with L2:
         // std = sqrt(0 * 1/0)); NaN scores never win (fitter.cpp:338) -> the node stays a leaf
         if (poisoned && !reused) sc = NAN;
-        const int idx = f * P.B + b;
-        float gain = sc;
-        if (!P.oblivious) gain = sc * w - parent;
+        idx = f * P.B + b;
+        gain = P.oblivious ? sc : sc * w - parent;
         P.scores[(size_t)p * P.C + idx] = gain;
-        // dominated: same partition as the previous threshold of this feature, which is itself valid
+        // dominated: same partition as the previous threshold of this feature (no sample has code == b), which is
+        // itself not excluded by the path guard -> equal score, higher index: can never win
         uint8_t fl8 = 0;
-        if (b > 0) {
-            const size_t o1 = ((size_t)(b - 1) * FT + fl) * HS;
-            const long long cprev = derived ? (Hp[o1] - Hs[o1]) : Hc[o1];
-            if (cprev == 0) {
-                const float tvp = P.thr[(size_t)f * P.B + b - 1];
-                bool rp = false;
-                for (int k = 0; k < depth; ++k) rp |= (s_path_f[k] == f && s_path_v[k] == tvp);
-                if (!rp) fl8 = 1;
-                if (P.oblivious && P.level == 0) fl8 |= 2;   // no sample of the whole set has code == b
-            }
+        if (b > 0 && s_cnt[b - 1] == 0) {
+            const float tvp = P.thr[(size_t)f * P.B + b - 1];
+            bool rp = false;
+            for (int k = 0; k < depth; ++k) rp |= (s_path_f[k] == f && s_path_v[k] == tvp);
+            if (!rp) fl8 = 1;
+            if (P.oblivious && P.level == 0) fl8 |= 2;   // no sample of the whole set has code == b
         }
         if (!P.oblivious) P.cand_flags[(size_t)p * P.C + idx] = fl8;
         else if (P.level == 0) P.cand_flags[idx] = fl8 & 2;
-        if (gain > -INFINITY && better(gain, idx, bestg, besti)) { bestg = gain; besti = idx; }
+        if (!(gain > -INFINITY)) { gain = -INFINITY; idx = INT_MAX; }
     }
     // block arg-max (lowest index on ties)
-    s_gain[threadIdx.x] = bestg;
-    s_idx[threadIdx.x] = besti;
-    __syncthreads();
-    for (int o = SCAN_THREADS / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) {
-            if (better(s_gain[threadIdx.x + o], s_idx[threadIdx.x + o], s_gain[threadIdx.x], s_idx[threadIdx.x])) {
-                s_gain[threadIdx.x] = s_gain[threadIdx.x + o];
-                s_idx[threadIdx.x] = s_idx[threadIdx.x + o];
-            }
-        }
-        __syncthreads();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float og = __shfl_down_sync(0xffffffffu, gain, off);
+        const int oi = __shfl_down_sync(0xffffffffu, idx, off);
+        if (better(og, oi, gain, idx)) { gain = og; idx = oi; }
     }
-    if (threadIdx.x == 0) P.tile_best[(size_t)p * P.nT + tile] = make_float2(s_gain[0], __int_as_float(s_idx[0]));
+    if (lane == 0) { s_gain[warp] = gain; s_idx[warp] = idx; }
+    __syncthreads();
+    if (t == 0) {
+        for (int w2 = 1; w2 < 8; ++w2)
+            if (better(s_gain[w2], s_idx[w2], gain, idx)) { gain = s_gain[w2]; idx = s_idx[w2]; }
+        P.tile_best[(size_t)p * P.F + f] = make_float2(gain, __int_as_float(idx));
+    }
 }
-
-// derived histograms read a neighbour's bins while another thread of the same CTA overwrites Hc only at
-// its own (b, fl) positions, and the dominated test reads bin b-1 of the SAME feature before this thread
-// (descending b) or the chunk-below thread overwrites it with the identical derived value -- for derived
-// nodes the test always reads Hp - Hs, never Hc, so there is no read-after-write hazard.
 
 // ---------------------------------------------------------------- greedy: per-node best + replay list
 struct SelectParams {
@@ -261,18 +255,32 @@ __global__ void __launch_bounds__(256) select_greedy_kernel(SelectParams P, Node
     __shared__ int s_besti, s_count, s_begin, s_w;
     const int p = blockIdx.x, h = level_base(P.level) + p;
     if (na.state[h] != NODE_OPEN) return;
-    if (threadIdx.x == 0) {
+    {
+        // arg-max over the per-feature bests (lowest candidate index on ties)
+        __shared__ float r_g[8];
+        __shared__ int r_i[8];
         float g = -INFINITY; int bi = INT_MAX;
-        for (int t = 0; t < P.nT; ++t) {
-            const float2 v = P.tile_best[(size_t)p * P.nT + t];
+        for (int t = threadIdx.x; t < P.F; t += blockDim.x) {
+            const float2 v = P.tile_best[(size_t)p * P.F + t];
             const int i = __float_as_int(v.y);
             if (v.x > -INFINITY && better(v.x, i, g, bi)) { g = v.x; bi = i; }
         }
-        s_best = g; s_besti = bi; s_count = 0; s_w = 0;
-        na.best_gain[h] = g;
-        na.best_idx[h] = (bi == INT_MAX) ? -1 : bi;
-        na.rep_begin[h] = 0; na.rep_count[h] = 0;
-        atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, 1ull);
+        for (int off = 16; off > 0; off >>= 1) {
+            const float og = __shfl_down_sync(0xffffffffu, g, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (better(og, oi, g, bi)) { g = og; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { r_g[threadIdx.x >> 5] = g; r_i[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w2 = 1; w2 < 8; ++w2)
+                if (better(r_g[w2], r_i[w2], g, bi)) { g = r_g[w2]; bi = r_i[w2]; }
+            s_best = g; s_besti = bi; s_count = 0; s_w = 0;
+            na.best_gain[h] = g;
+            na.best_idx[h] = (bi == INT_MAX) ? -1 : bi;
+            na.rep_begin[h] = 0; na.rep_count[h] = 0;
+            atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, 1ull);
+        }
     }
     __syncthreads();
     const float g = s_best;
@@ -478,15 +486,59 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
                 const int c32 = min(32, cnt - w * 32);
                 if (PASS == 0) {
                     nR += __popc(mask & (c32 == 32 ? 0xffffffffu : ((1u << c32) - 1u)));
-#pragma unroll 8
-                    for (int t = 0; t < c32; ++t) {
-                        const bool r = (mask >> t) & 1u;
+                    if (D <= 32) {
+                        // fast path: batch 8 shared loads, then 8 predicated adds (the only true dependency is the
+                        // 4-cycle FADD chain of the side a row falls on)            node.cpp:341-350
+                        const bool mine = lane < D;
+                        const float *gcol = g + (size_t)(w * 32) * D + (mine ? lane : 0);
+                        float aL = accL[0], aR = accR[0];
+                        int t = 0;
+                        if (c32 == 32) {
+                            // full word: software-pipelined (the next 8 values are in flight while 8 are added)
+                            float v[8], vn[8];
 #pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int d = lane + 32 * q;
-                            if (d < D) {
-                                const float v = g[(size_t)(w * 32 + t) * D + d];
-                                if (r) accR[q] = accR[q] + v; else accL[q] = accL[q] + v;   // node.cpp:341-350
+                            for (int j = 0; j < 8; ++j) v[j] = gcol[(size_t)j * D];
+#pragma unroll
+                            for (int b8 = 0; b8 < 4; ++b8) {
+                                if (b8 < 3) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) vn[j] = gcol[(size_t)(8 * (b8 + 1) + j) * D];
+                                }
+                                const unsigned int m8 = mask >> (8 * b8);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    if (m8 & (1u << j)) aR = aR + v[j]; else aL = aL + v[j];
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = vn[j];
+                            }
+                            t = 32;
+                        }
+                        for (; t + 8 <= c32; t += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = gcol[(size_t)(t + j) * D];
+                            const unsigned int m8 = mask >> t;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (m8 & (1u << j)) aR = aR + v[j]; else aL = aL + v[j];
+                            }
+                        }
+                        for (; t < c32; ++t) {
+                            const float v = gcol[(size_t)t * D];
+                            if ((mask >> t) & 1u) aR = aR + v; else aL = aL + v;
+                        }
+                        if (mine) { accL[0] = aL; accR[0] = aR; }
+                    } else {
+                        for (int t = 0; t < c32; ++t) {
+                            const bool r = (mask >> t) & 1u;
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int d = lane + 32 * q;
+                                if (d < D) {
+                                    const float v = g[(size_t)(w * 32 + t) * D + d];
+                                    if (r) accR[q] = accR[q] + v; else accL[q] = accL[q] + v;
+                                }
                             }
                         }
                     }
@@ -697,9 +749,7 @@ __global__ void __launch_bounds__(256) decide_oblivious_kernel(DecideParams P, N
 // ---------------------------------------------------------------- launchers
 template <int DM>
 static void launch_scan_dm(const ScanParams &P, const NodeArrays &na, int grid, cudaStream_t s) {
-    const size_t smem = (size_t)8 * FT * (1 + P.D) * sizeof(long long);
-    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(scan_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_LAUNCH(scan_kernel<DM>, grid, SCAN_THREADS, smem, s, P, na);
+    GB_LAUNCH(scan_kernel<DM>, grid, SCAN_THREADS, 0, s, P, na);
 }
 
 void launch_scan(Model &m, int level, cudaStream_t s) {
@@ -713,7 +763,7 @@ void launch_scan(Model &m, int level, cudaStream_t s) {
     P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
     P.scores = ws.scores.as<float>(); P.cand_flags = ws.cand_flags.as<uint8_t>();
     P.tile_best = ws.tile_best.as<float2>(); P.ctl = ws.ctl.as<Ctl>();
-    const int grid = (1 << level) * ws.nT;
+    const int grid = (1 << level) * ws.F;
     const int D = ws.D;
     if (D <= 1) launch_scan_dm<1>(P, ws.na, grid, s);
     else if (D <= 2) launch_scan_dm<2>(P, ws.na, grid, s);
