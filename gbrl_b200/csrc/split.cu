@@ -287,8 +287,12 @@ __global__ void __launch_bounds__(256) select_greedy_kernel(SelectParams P, Node
     if (!P.tie_replay || !(g > -INFINITY)) return;
     const int n = na.seg_len[h];
     const float parent = na.parent_score[h];
-    const float band = P.kappa * U24 * sqrtf((float)n) * (fabsf(g + parent) + fabsf(parent)) + FLT_MIN;
-    const float lim = g - band;
+    // candidates are compared on score*w (the parent score is common to all of them), so the comparison band
+    // only carries the rounding noise of the candidate sums; the parent's noise matters for the sign test gain >= 0
+    const float unit = P.kappa * U24 * sqrtf((float)n);
+    const float band_c = unit * fabsf(g + parent) + FLT_MIN;
+    const float band = unit * (fabsf(g + parent) + fabsf(parent)) + FLT_MIN;
+    const float lim = g - band_c;
     const float *sc = P.scores + (size_t)p * P.C;
     const uint8_t *fl = P.cand_flags + (size_t)p * P.C;
     int mine = 0;
@@ -447,9 +451,12 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
     constexpr int STAGE = RP_THREADS * R;
     const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_stages = (n + STAGE - 1) / STAGE;
+    constexpr int DG = R >= 8 ? 1 : R >= 4 ? 2 : R >= 2 ? 4 : 0;   // gradient values prefetched per row (== D on the fast paths)
     int rows[R];
     float xv[R];
-    // prologue: stage 0 -> registers
+    float gpre[R][DG > 0 ? DG : 1];
+    const bool pre = (DG > 0) && (D <= DG);
+    // stage st -> registers: row ids, then (dependent) the feature value and the gradients of every row
     auto issue = [&](int st) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -457,7 +464,14 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
             rows[r] = (k < n) ? P.order[s0 + k] : -1;
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) xv[r] = (rows[r] >= 0 && is_cand) ? P.X[(size_t)rows[r] * P.F + f] : -INFINITY;
+        for (int r = 0; r < R; ++r) {
+            xv[r] = (rows[r] >= 0 && is_cand) ? P.X[(size_t)rows[r] * P.F + f] : -INFINITY;
+            if (pre && rows[r] >= 0) {
+#pragma unroll
+                for (int d = 0; d < (DG > 0 ? DG : 1); ++d)
+                    if (d < D) gpre[r][d] = P.bg[(size_t)rows[r] * D + d];
+            }
+        }
     };
     auto commit = [&](int st, int buf) {
         float *g = sg + (size_t)buf * STAGE * D;
@@ -467,8 +481,15 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
             const bool right = rows[r] >= 0 && (xv[r] > tv);                     // node.cpp:339
             const unsigned int m = __ballot_sync(0xffffffffu, right);
             if (lane == 0) smask[buf * (STAGE / 32) + slot / 32] = m;
-            if (rows[r] >= 0)
-                for (int d = 0; d < D; ++d) g[(size_t)slot * D + d] = P.bg[(size_t)rows[r] * D + d];
+            if (rows[r] >= 0) {
+                if (pre) {
+#pragma unroll
+                    for (int d = 0; d < (DG > 0 ? DG : 1); ++d)
+                        if (d < D) g[(size_t)slot * D + d] = gpre[r][d];
+                } else {
+                    for (int d = 0; d < D; ++d) g[(size_t)slot * D + d] = P.bg[(size_t)rows[r] * D + d];
+                }
+            }
         }
         (void)st;
     };
