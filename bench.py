@@ -31,6 +31,8 @@ WORKLOADS = {
     "c3": dict(n=4_000_000, f=64, d=2, depth=8, grow="oblivious", score="cosine", lrs=[(0.1, 0, 1), (0.01, 1, 2)]),
     "c5": dict(n=8_000_000, f=256, d=1, depth=6, grow="greedy", score="L2", lrs=[(0.1, 0, 1)]),
 }
+# predict-only workload (BASELINE config 4): 100k oblivious trees d6, D=2, batch 8192 x 128 (PPO rollout shape)
+PREDICT = dict(n=8192, f=128, d=2, depth=6, n_trees=100_000, lrs=[(0.1, 0, 1), (0.01, 1, 2)])
 METRIC = "boosting-iters/sec (fit)"
 UNIT = "iters/s"
 
@@ -170,6 +172,59 @@ def run_cpu_sample(c, rows, warmup, steps):
     return kind, its, its * rows / c["n"], t
 
 
+# ------------------------------------------------------------------------------------------------ predict (config 4)
+def bench_predict(args):
+    """obs/s of the batched ensemble predict: 100k-tree oblivious ensemble, 8192 x 128 observations per call."""
+    import numpy as np
+    import torch
+    from gbrl_b200 import GBRL
+    p = PREDICT
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    rng = np.random.default_rng(0)
+    nt, dep, f, d = p["n_trees"], p["depth"], p["f"], p["d"]
+    nl = nt << dep
+    e = {"tree_indices": (np.arange(nt, dtype=np.int64) << dep).astype(np.int32), "depths": np.full(nt, dep, np.int32),
+         "values": (0.01 * rng.standard_normal((nl, d), dtype=np.float32)),
+         "feature_indices": rng.integers(0, f, (nt, dep)).astype(np.int32),
+         "feature_values": rng.standard_normal((nt, dep), dtype=np.float32),
+         "edge_weights": np.zeros((nl, dep), np.float32), "inequality_directions": np.zeros((nl, dep), bool)}
+    m = GBRL(input_dim=f, output_dim=d, policy_dim=d, max_depth=dep, n_bins=256, split_score_func="cosine",
+             generator_type="quantile", batch_size=p["n"], grow_policy="oblivious", device="cuda:0")
+    m.set_bias(np.zeros(d, np.float32)); m.set_feature_weights(np.ones(f, np.float32))
+    m.set_feature_mapping(np.arange(f, dtype=np.int32), np.ones(f, dtype=bool))
+    for (lr, a, b) in p["lrs"]:
+        m.set_optimizer("SGD", "const", lr, a, b)
+    m._set_ensemble(e, f)
+    X = torch.randn((p["n"], f), device="cuda", dtype=torch.float32)
+    for _ in range(W):
+        m.predict_tensor(X)
+    torch.cuda.synchronize()
+    l0 = m.get_stats()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        out = m.predict_tensor(X)
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / K
+    launches = m.get_stats()["kernel_launches"] - l0
+    Xh = torch.empty((p["n"], f), dtype=torch.float32, pin_memory=True); Xh.copy_(X)
+    oh = np.empty((p["n"], d), np.float32)
+    t = time.perf_counter()
+    for _ in range(K):
+        oh = m.predict_numpy(Xh.numpy())
+    te = (time.perf_counter() - t) / K
+    walks = p["n"] * nt
+    out = {"metric": "obs/sec (predict)", "value": p["n"] / (ms * 1e-3), "unit": "obs/s", "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "c4: predict-only, %d oblivious trees depth %d, D=%d, batch %d obs x %d features" % (nt, dep, d, p["n"], f),
+                      "l2": "ensemble arrays (%.0f MB) cycle through L2 every call" % ((nl * d * 4 + nt * dep * 8) / 1e6)},
+           "tree_walks_per_s": walks / (ms * 1e-3),
+           "e2e": {"value": p["n"] / te, "unit": "obs/s", "h2d_bytes_per_step": p["n"] * f * 4, "d2h_bytes_per_step": p["n"] * d * 4},
+           "gpu_launches": int(launches)}
+    print(json.dumps(out))
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -177,13 +232,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="exact-arithmetic arg-max only (see DESIGN.md, near-tie replay)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
     args = ap.parse_args()
+    if args.workload == "c4":
+        return bench_predict(args)
     c = WORKLOADS[args.workload]
     K, W = max(args.steps, 1), max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -264,7 +321,10 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     hist_ms = prof["histogram"]["ms"]; hist_launches = max(prof["histogram"]["launches"], 1)
     rows_scanned = prof["hist_rows"] - rows0
-    alg_bytes = rows_scanned * (4 * c["f"] + 4 * c["d"] + 4)
+    n_tiles = (c["f"] + 31) // 32
+    own_tiles = (n_tiles * (rank + 1)) // world - (n_tiles * rank) // world      # feature tiles this rank histograms
+    f_local = min(c["f"], own_tiles * 32)
+    alg_bytes = rows_scanned * (4 * f_local + 4 * c["d"] + 4)
     achieved = alg_bytes / (hist_ms * 1e-3) / 1e9 if hist_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "hist_kernel", "launches": hist_launches, "avg_launch_ms": hist_ms / hist_launches,

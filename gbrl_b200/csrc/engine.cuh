@@ -92,7 +92,7 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     int row_offset = 0;             // first row of the current mini-batch inside the code matrix
     DevBuf codes, thr, thrT, bg, order[2], nid, rflag, rscan, chunk_sums, hist[2], scores, cand_flags;
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
-    DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage;
+    DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage, pred_partials;
     NodeArrays na{};
     size_t sort_tmp_bytes = 0;
     int replay_cap = 0, items_cap = 0;

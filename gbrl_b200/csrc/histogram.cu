@@ -150,17 +150,15 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
         const Item it = items[itx];
         const uint16_t *ctile = codes + ((size_t)it.tile * codes_rows + row_offset) * FT;
         constexpr int STEP = (HIST_THREADS / 32) * 32;
-        int kb = it.k0 + warp * 32;
-        int my_row = (kb + lane < it.k1) ? order[kb + lane] : -1;
-        for (; kb < it.k1; kb += STEP) {
-            const int cur_row = my_row;
-            const int kn = kb + STEP + lane;
-            my_row = (kn < it.k1) ? order[kn] : -1;            // prefetch the next block of row ids
-            uint2 b[8];
-            float gv[8][ND];
+        // Software pipeline over half-blocks of 16 rows (4 per lane group): while the shared-memory atomics of one
+        // half are issued, the code quads / gradients of the next half are already in flight, and the row ids of
+        // the block after that are prefetched.  Register budget is the same as a non-pipelined 32-row block.
+        uint2 bA[4], bB[4];
+        float gA[4][ND], gB[4][ND];
+        auto load_half = [&](int rows32, int half, uint2 *b, float (*gv)[ND]) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const int row = __shfl_sync(0xffffffffu, cur_row, s * 4 + rl);
+            for (int s = 0; s < 4; ++s) {
+                const int row = __shfl_sync(0xffffffffu, rows32, (half * 4 + s) * 4 + rl);
                 if (row >= 0) {
                     b[s] = ld_nc_u2(reinterpret_cast<const uint2 *>(ctile + (size_t)row * FT + g * 4));
 #pragma unroll
@@ -171,8 +169,10 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
                     for (int dd = 0; dd < ND; ++dd) gv[s][dd] = 0.0f;
                 }
             }
+        };
+        auto add_half = [&](const uint2 *b, const float (*gv)[ND]) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < 4; ++s) {
                 int lo[ND], hi[ND];
 #pragma unroll
                 for (int dd = 0; dd < ND; ++dd) {
@@ -191,6 +191,18 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
                     if (ND > 2) { red_shared_off<5 * PB>(addr, lo[ND > 2 ? 2 : 0]); red_shared_off<6 * PB>(addr, hi[ND > 2 ? 2 : 0]); }
                 }
             }
+        };
+        int kb = it.k0 + warp * 32;
+        int cur_row = (kb + lane < it.k1) ? order[kb + lane] : -1;
+        load_half(cur_row, 0, bA, gA);
+        for (; kb < it.k1; kb += STEP) {
+            const int kn = kb + STEP + lane;
+            const int next_row = (kn < it.k1) ? order[kn] : -1;   // row ids of the next block
+            load_half(cur_row, 1, bB, gB);
+            add_half(bA, gA);
+            load_half(next_row, 0, bA, gA);
+            add_half(bB, gB);
+            cur_row = next_row;
         }
         __syncthreads();
         // flush: (bin, feature) e -> global [slot][tile][bin][feature][1+D]; shared row = bin + 1

@@ -79,6 +79,100 @@ __global__ void __launch_bounds__(128) predict_kernel(PredictParams P) {
         if (d < P.D) P.preds[(size_t)i * P.D + d] = theta[d];
 }
 
+// ---------------------------------------------------------------- tree-chunked predict (rollout shape)
+// BASELINE config 4 (100k trees x 8192 observations): 8192 samples cannot fill 148 SMs with one thread per sample, so
+// the tree range is cut into chunks: a CTA owns 32 samples (lane = sample) x one chunk of trees, its 4 warps split
+// the chunk.  The 32 observations are staged transposed in shared memory (xT[f][33]: lane == bank, conflict-free
+// for the uniform feature index of a tree level); tree parameters are warp-uniform loads.  Partial sums per chunk
+// are written out and combined in chunk order by a second kernel, so the result is deterministic (the reference's
+// own tree-parallel mode also sums per-thread partial buffers, predictor.cpp:147-165); agreement with the
+// sequential order is within float rounding (<= 1e-5 is tested).
+template <int DM>
+__global__ void __launch_bounds__(128) predict_chunk_kernel(PredictParams P, float *__restrict__ partials, int trees_per_chunk) {
+    extern __shared__ float xT[];                      // [F][33]
+    __shared__ float red[4][32][DM];
+    const int tile = blockIdx.x, chunk = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = tile * 32;
+    for (int idx = threadIdx.x; idx < P.F * 32; idx += 128) {
+        const int s = idx / P.F, f = idx % P.F;
+        xT[f * 33 + s] = (s0 + s < P.N) ? P.X[(size_t)(s0 + s) * P.F + f] : 0.0f;
+    }
+    __syncthreads();
+    const int c0 = P.start_tree + chunk * trees_per_chunk;
+    const int c1 = min(P.stop_tree, c0 + trees_per_chunk);
+    const int per_warp = (c1 - c0 + 3) / 4;
+    const int t0 = c0 + warp * per_warp, t1 = min(c1, t0 + per_warp);
+    float acc[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) acc[d] = 0.0f;
+    const int md = P.md;
+    for (int t = t0; t < t1; ++t) {
+        int leaf;
+        if (P.oblivious) {
+            const int dep = P.depths[t];
+            int li = 0;
+            for (int k = 0; k < dep; ++k) {
+                const int f = P.feature_indices[(size_t)t * md + k];
+                const float thr = P.feature_values[(size_t)t * md + k];
+                li |= (xT[f * 33 + lane] > thr ? 1 : 0) << (dep - 1 - k);
+            }
+            leaf = P.tree_indices[t] + li;
+        } else {
+            const int *hf = P.heap_feat + (size_t)t * (1 << md);
+            const float *ht = P.heap_thr + (size_t)t * (1 << md);
+            int h = 0, f = hf[0];
+            if (f < 0) continue;
+            while (f >= 0) {
+                h = 2 * h + 1 + (xT[f * 33 + lane] > ht[h] ? 1 : 0);
+                f = (h < (1 << md) - 1) ? hf[h] : -1;
+            }
+            leaf = P.tree_indices[t] + P.heap_leaf[(size_t)t * (2 << md) + h];
+        }
+        const float *v = P.values + (size_t)leaf * P.D;
+        for (int o = 0; o < P.n_opts; ++o) {
+            const DevOpt op = P.opts[o];
+            const float lr = sched_lr(op, t);
+#pragma unroll
+            for (int d = 0; d < DM; ++d)
+                if (d >= op.start_idx && d < op.stop_idx) acc[d] = acc[d] - lr * v[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < DM; ++d) red[warp][lane][d] = acc[d];
+    __syncthreads();
+    if (warp == 0 && s0 + lane < P.N) {
+#pragma unroll
+        for (int d = 0; d < DM; ++d) {
+            if (d < P.D) {
+                float sum = red[0][lane][d];
+                sum = sum + red[1][lane][d]; sum = sum + red[2][lane][d]; sum = sum + red[3][lane][d];
+                partials[((size_t)chunk * P.N + s0 + lane) * P.D + d] = sum;
+            }
+        }
+    }
+}
+
+__global__ void predict_combine_kernel(const float *__restrict__ partials, const float *__restrict__ bias, float *__restrict__ preds,
+                                       int N, int D, int n_chunks, int add_bias) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)N * D) return;
+    float acc = add_bias ? bias[i % D] : preds[i];
+    for (int c = 0; c < n_chunks; ++c) acc = acc + partials[(size_t)c * N * D + i];
+    preds[i] = acc;
+}
+
+template <int DM>
+static void launch_predict_chunked(Model &m, const PredictParams &P, int n_chunks, int tpc, cudaStream_t s) {
+    const size_t smem = (size_t)P.F * 33 * sizeof(float);
+    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(predict_chunk_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    m.ws.pred_partials.ensure((size_t)n_chunks * P.N * P.D * sizeof(float));
+    dim3 grid(ceil_div(P.N, 32), n_chunks);
+    GB_LAUNCH(predict_chunk_kernel<DM>, grid, 128, smem, s, P, m.ws.pred_partials.as<float>(), tpc);
+    GB_LAUNCH(predict_combine_kernel, ceil_div(P.N * P.D, 256), 256, 0, s, m.ws.pred_partials.as<float>(), P.bias, P.preds, P.N, P.D,
+              n_chunks, P.add_bias);
+}
+
 void upload_optimizers(Model &m, cudaStream_t s) {
     std::vector<DevOpt> h(m.opts.size());
     for (size_t i = 0; i < m.opts.size(); ++i) {
@@ -110,6 +204,21 @@ void launch_predict(Model &m, const float *X, int N, int F, int start_tree, int 
     P.N = N; P.F = F; P.D = m.cfg.output_dim; P.md = m.cfg.max_depth; P.start_tree = start_tree; P.stop_tree = stop_tree;
     P.add_bias = add_bias ? 1 : 0; P.oblivious = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
     const int D = P.D;
+    // rollout shape: few samples, many trees -> cut the tree range into chunks (see predict_chunk_kernel)
+    const int n_t = stop_tree - start_tree;
+    const int tiles = ceil_div(N, 32);
+    if (n_t >= 1024 && tiles * 4 < 148 * 24 && D <= 8 && (size_t)F * 33 * 4 <= 200 * 1024) {
+        int n_chunks = ceil_div(148 * 8, tiles);
+        if (n_chunks > n_t / 128) n_chunks = n_t / 128;
+        if (n_chunks < 1) n_chunks = 1;
+        const int tpc = ceil_div(n_t, n_chunks);
+        n_chunks = ceil_div(n_t, tpc);
+        if (D <= 1) launch_predict_chunked<1>(m, P, n_chunks, tpc, s);
+        else if (D <= 2) launch_predict_chunked<2>(m, P, n_chunks, tpc, s);
+        else if (D <= 4) launch_predict_chunked<4>(m, P, n_chunks, tpc, s);
+        else launch_predict_chunked<8>(m, P, n_chunks, tpc, s);
+        return;
+    }
     if (D <= 1) launch_predict_dm<1>(P, s);
     else if (D <= 2) launch_predict_dm<2>(P, s);
     else if (D <= 4) launch_predict_dm<4>(P, s);

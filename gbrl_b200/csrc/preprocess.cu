@@ -39,25 +39,33 @@ ref_chain_kernel(float *mat, const float *mean, float *partial, long long n_elem
     const long long s = (long long)t * ept, e = (t == T - 1) ? n_elements : s + ept;
     float acc0 = 0.0f, acc1 = 0.0f;              // columns lane and lane + 32
     int c0 = (int)(s % D);                       // column of element i0
+    float raw_next = (s + lane < e) ? mat[s + lane] : 0.0f;
     for (long long i0 = s; i0 < e; i0 += 32) {
         const long long i = i0 + lane;
+        const float raw = raw_next;
+        raw_next = (i + 32 < e) ? mat[i + 32] : 0.0f;          // next group is in flight while this one is consumed
         float v = 0.0f;
         if (i < e) {
-            v = mat[i];
+            v = raw;
             if (mode == 1) {
                 const int col = (int)((c0 + lane) % D);
-                const float c = v - mean[col];
+                const float c = raw - mean[col];
                 mat[i] = c;
                 v = c * c;
             }
         }
         const int cnt = (e - i0) < 32 ? (int)(e - i0) : 32;
         int col = c0;
+        if (D == 1) {
 #pragma unroll 8
-        for (int j = 0; j < cnt; ++j) {
-            const float vj = __shfl_sync(0xffffffffu, v, j);
-            if ((col & 31) == lane) { if (col < 32) acc0 = acc0 + vj; else acc1 = acc1 + vj; }
-            ++col; if (col == D) col = 0;
+            for (int j = 0; j < cnt; ++j) acc0 = acc0 + __shfl_sync(0xffffffffu, v, j);     // every lane runs the chain
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < cnt; ++j) {
+                const float vj = __shfl_sync(0xffffffffu, v, j);
+                if ((col & 31) == lane) { if (col < 32) acc0 = acc0 + vj; else acc1 = acc1 + vj; }
+                ++col; if (col == D) col = 0;
+            }
         }
         c0 = (int)((c0 + 32) % D);
     }

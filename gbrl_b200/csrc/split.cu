@@ -250,15 +250,15 @@ struct SelectParams {
     Ctl *ctl;
 };
 
-__global__ void __launch_bounds__(256) select_greedy_kernel(SelectParams P, NodeArrays na) {
+__global__ void __launch_bounds__(1024) select_greedy_kernel(SelectParams P, NodeArrays na) {
     __shared__ float s_best;
     __shared__ int s_besti, s_count, s_begin, s_w;
     const int p = blockIdx.x, h = level_base(P.level) + p;
     if (na.state[h] != NODE_OPEN) return;
     {
         // arg-max over the per-feature bests (lowest candidate index on ties)
-        __shared__ float r_g[8];
-        __shared__ int r_i[8];
+        __shared__ float r_g[32];
+        __shared__ int r_i[32];
         float g = -INFINITY; int bi = INT_MAX;
         for (int t = threadIdx.x; t < P.F; t += blockDim.x) {
             const float2 v = P.tile_best[(size_t)p * P.F + t];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) select_greedy_kernel(SelectParams P, Node
         if ((threadIdx.x & 31) == 0) { r_g[threadIdx.x >> 5] = g; r_i[threadIdx.x >> 5] = bi; }
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w2 = 1; w2 < 8; ++w2)
+            for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2)
                 if (better(r_g[w2], r_i[w2], g, bi)) { g = r_g[w2]; bi = r_i[w2]; }
             s_best = g; s_besti = bi; s_count = 0; s_w = 0;
             na.best_gain[h] = g;
@@ -449,31 +449,41 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
                                             unsigned int *smask /*[2][STAGE/32]*/, const float *smean, float *accL, float *accR,
                                             int &nR, float &tnum, float &fnum) {
     constexpr int STAGE = RP_THREADS * R;
-    const int D = P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int DC = (R == 8) ? 1 : (R == 4) ? 2 : 0;     // compile-time output_dim on the two fast paths
+    const int D = DC > 0 ? DC : P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_stages = (n + STAGE - 1) / STAGE;
     constexpr int DG = R >= 8 ? 1 : R >= 4 ? 2 : R >= 2 ? 4 : 0;   // gradient values prefetched per row (== D on the fast paths)
     int rows[R];
     float xv[R];
     float gpre[R][DG > 0 ? DG : 1];
     const bool pre = (DG > 0) && (D <= DG);
-    // stage st -> registers: row ids, then (dependent) the feature value and the gradients of every row
-    auto issue = [&](int st) {
+    // Loads are split in two dependent steps that are issued one stage apart, so that no warp ever waits for a
+    // row id before it can issue the gathers that depend on it:
+    //   load_rows(st+2) -> registers      (coalesced read of `order`)
+    //   gather(st+1)    -> registers      (feature value + gradients of rows whose ids arrived a stage ago)
+    //   chain(st)       from shared memory
+    //   commit(st+1)    registers -> shared memory
+    int rows_n[R];
+    auto load_rows = [&](int st, int *dst) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int k = st * STAGE + r * RP_THREADS + tid;
-            rows[r] = (k < n) ? P.order[s0 + k] : -1;
+            dst[r] = (st < n_stages && k < n) ? P.order[s0 + k] : -1;
         }
+    };
+    auto gather = [&](const int *src) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            xv[r] = (rows[r] >= 0 && is_cand) ? P.X[(size_t)rows[r] * P.F + f] : -INFINITY;
-            if (pre && rows[r] >= 0) {
+            rows[r] = src[r];
+            xv[r] = (src[r] >= 0 && is_cand) ? P.X[(size_t)src[r] * P.F + f] : -INFINITY;
+            if (pre && src[r] >= 0) {
 #pragma unroll
                 for (int d = 0; d < (DG > 0 ? DG : 1); ++d)
-                    if (d < D) gpre[r][d] = P.bg[(size_t)rows[r] * D + d];
+                    if (d < D) gpre[r][d] = P.bg[(size_t)src[r] * D + d];
             }
         }
     };
-    auto commit = [&](int st, int buf) {
+    auto commit = [&](int buf) {
         float *g = sg + (size_t)buf * STAGE * D;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -491,14 +501,20 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
                 }
             }
         }
-        (void)st;
     };
-    issue(0);
-    commit(0, 0);
+    {
+        int r0[R];
+        load_rows(0, r0);
+        load_rows(1, rows_n);
+        gather(r0);
+        commit(0);
+    }
     __syncthreads();
     for (int st = 0; st < n_stages; ++st) {
         const int buf = st & 1;
-        if (st + 1 < n_stages) issue(st + 1);
+        int rows_nn[R];
+        if (st + 1 < n_stages) gather(rows_n);
+        load_rows(st + 2, rows_nn);
         if (warp == 0) {
             const float *g = sg + (size_t)buf * STAGE * D;
             const int cnt = min(STAGE, n - st * STAGE);
@@ -507,34 +523,45 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
                 const int c32 = min(32, cnt - w * 32);
                 if (PASS == 0) {
                     nR += __popc(mask & (c32 == 32 ? 0xffffffffu : ((1u << c32) - 1u)));
-                    if (D <= 32) {
-                        // fast path: batch 8 shared loads, then 8 predicated adds (the only true dependency is the
-                        // 4-cycle FADD chain of the side a row falls on)            node.cpp:341-350
+                    if (DC == 1 && c32 == 32) {
+                        // D == 1, full word: 8 x LDS.128 with immediate offsets, then 32 predicated adds; the only
+                        // true dependency is the 4-cycle FADD chain of the side a row falls on   (node.cpp:341-350)
+                        const float4 *g4 = reinterpret_cast<const float4 *>(g + (size_t)w * 32);
+                        float4 q4[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) q4[j] = g4[j];
+                        float aL = accL[0], aR = accR[0];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const unsigned int m4 = mask >> (4 * j);
+                            if (m4 & 1u) aR = aR + q4[j].x; else aL = aL + q4[j].x;
+                            if (m4 & 2u) aR = aR + q4[j].y; else aL = aL + q4[j].y;
+                            if (m4 & 4u) aR = aR + q4[j].z; else aL = aL + q4[j].z;
+                            if (m4 & 8u) aR = aR + q4[j].w; else aL = aL + q4[j].w;
+                        }
+                        accL[0] = aL; accR[0] = aR;     // every lane runs the same chain; lane 0 is the owner
+                    } else if (DC == 2 && c32 == 32) {
+                        // D == 2: lanes 0 / 1 own the two columns (stride-2 floats, immediate offsets)
+                        const float *gc = g + (size_t)w * 64 + (lane & 1);
+                        float aL = accL[0], aR = accR[0];
+#pragma unroll
+                        for (int b8 = 0; b8 < 4; ++b8) {
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = gc[(8 * b8 + j) * 2];
+                            const unsigned int m8 = mask >> (8 * b8);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (m8 & (1u << j)) aR = aR + v[j]; else aL = aL + v[j];
+                            }
+                        }
+                        if (lane < 2) { accL[0] = aL; accR[0] = aR; }
+                    } else if (D <= 32) {
+                        // generic D <= 32: batch 8 shared loads, then 8 predicated adds
                         const bool mine = lane < D;
                         const float *gcol = g + (size_t)(w * 32) * D + (mine ? lane : 0);
                         float aL = accL[0], aR = accR[0];
                         int t = 0;
-                        if (c32 == 32) {
-                            // full word: software-pipelined (the next 8 values are in flight while 8 are added)
-                            float v[8], vn[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = gcol[(size_t)j * D];
-#pragma unroll
-                            for (int b8 = 0; b8 < 4; ++b8) {
-                                if (b8 < 3) {
-#pragma unroll
-                                    for (int j = 0; j < 8; ++j) vn[j] = gcol[(size_t)(8 * (b8 + 1) + j) * D];
-                                }
-                                const unsigned int m8 = mask >> (8 * b8);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    if (m8 & (1u << j)) aR = aR + v[j]; else aL = aL + v[j];
-                                }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = vn[j];
-                            }
-                            t = 32;
-                        }
                         for (; t + 8 <= c32; t += 8) {
                             float v[8];
 #pragma unroll
@@ -574,7 +601,9 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
                 }
             }
         }
-        if (st + 1 < n_stages) commit(st + 1, buf ^ 1);
+        if (st + 1 < n_stages) commit(buf ^ 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) rows_n[r] = rows_nn[r];
         __syncthreads();
     }
 }
@@ -808,7 +837,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         P.replay_cap = ws.replay_cap; P.kappa = kappa; P.scores = ws.scores.as<float>();
         P.cand_flags = ws.cand_flags.as<uint8_t>(); P.tile_best = ws.tile_best.as<float2>();
         P.replay = ws.replay.as<ReplayItem>(); P.ctl = ctl;
-        GB_LAUNCH(select_greedy_kernel, nn, 256, 0, s, P, ws.na);
+        GB_LAUNCH(select_greedy_kernel, nn, 1024, 0, s, P, ws.na);
     } else {
         OblParams P;
         P.level = level; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = C; P.nn = nn; P.tie_replay = m.cfg.tie_replay;

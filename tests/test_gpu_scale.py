@@ -83,6 +83,48 @@ def test_predict_large_ensemble_is_sum_over_trees():
     assert np.abs(full - parts).max() <= 1e-5
 
 
+def _numpy_oblivious_predict(e, X, lrs, bias):
+    n = X.shape[0]
+    D = e["values"].shape[1]
+    out = np.tile(np.asarray(bias, np.float64), (n, 1))
+    for t in range(e["tree_indices"].shape[0]):
+        dep = int(e["depths"][t])
+        li = np.zeros(n, np.int64)
+        for k in range(dep):
+            li |= (X[:, e["feature_indices"][t, k]] > e["feature_values"][t, k]).astype(np.int64) << (dep - 1 - k)
+        out -= lrs[None, :] * e["values"][e["tree_indices"][t] + li].astype(np.float64)
+    return out
+
+
+def test_chunked_predict_rollout_shape():
+    """BASELINE config 4 shape (scaled): many trees x few observations goes through predict_chunk_kernel; it must
+    agree with a float64 evaluation of the same ensemble and with the sequential kernel (large-N path)."""
+    rng = np.random.default_rng(3)
+    n_trees, depth, f, d = 3000, 6, 128, 2
+    nl = n_trees << depth
+    e = {"tree_indices": (np.arange(n_trees, dtype=np.int32) << depth), "depths": np.full(n_trees, depth, np.int32),
+         "values": (0.01 * rng.standard_normal((nl, d))).astype(np.float32),
+         "feature_indices": rng.integers(0, f, (n_trees, depth)).astype(np.int32),
+         "feature_values": rng.standard_normal((n_trees, depth)).astype(np.float32),
+         "edge_weights": np.zeros((nl, depth), np.float32), "inequality_directions": np.zeros((nl, depth), bool)}
+    kw = dict(input_dim=f, output_dim=d, max_depth=depth, n_bins=256, split_score_func="cosine", generator_type="quantile",
+              batch_size=8192, grow_policy="oblivious")
+    m = configure(make_gpu(**kw), f, d, lrs=[(0.1, 0, 1), (0.01, 1, 2)], bias=[0.25, -0.5])
+    m._set_ensemble(e, f)
+    X = rng.standard_normal((8192, f)).astype(np.float32)
+    got = m.predict_numpy(X)                                  # chunked path
+    exp = _numpy_oblivious_predict(e, X, np.array([0.1, 0.01]), [0.25, -0.5])
+    assert np.abs(got - exp).max() <= 1e-5
+    Xbig = np.concatenate([X] * 5, 0)                          # 40960 rows -> sequential kernel
+    seq = m.predict_numpy(Xbig)[:8192]
+    assert np.abs(seq.astype(np.float64) - got).max() <= 1e-5
+    part = m.predict_numpy(X, 100, 2900)                       # tree sub-range through the chunked path
+    e2 = dict(e); e2["tree_indices"] = e["tree_indices"][100:2900]; e2["depths"] = e["depths"][100:2900]
+    e2["feature_indices"] = e["feature_indices"][100:2900]; e2["feature_values"] = e["feature_values"][100:2900]
+    exp2 = _numpy_oblivious_predict(e2, X, np.array([0.1, 0.01]), [0.25, -0.5])
+    assert np.abs(part - exp2).max() <= 1e-5
+
+
 def test_two_gpu_matches_single_gpu():
     import torch
     if torch.cuda.device_count() < 2:
