@@ -374,7 +374,7 @@ def main():
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
            "kernel_ms_per_step": breakdown, "final_loss": loss,
            "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
-                      "nodes_evaluated": stats["nodes_evaluated"]}}
+                      "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"]}}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -22,7 +22,7 @@ class Metadata(C.Structure):
         "input_dim", "output_dim", "policy_dim", "max_depth", "min_data_in_leaf", "n_bins", "par_th",
         "batch_size", "split_score_func", "generator_type", "grow_policy", "verbose", "n_num_features",
         "n_cat_features", "n_trees", "n_leaves", "iteration")] + [(n, C.c_longlong) for n in (
-            "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")]
+            "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")] + [("max_noise_ratio", C.c_float)]
 
 
 # every symbol include/gbrl_b200.h declares (tests check that the library exports all of them)

@@ -102,6 +102,7 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
     m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
     m.hist_rows = h.stat_hist_rows;
+    m.max_noise = __builtin_bit_cast(float, h.stat_max_noise);
 }
 
 static void check_features(Model &m, int n_features) {
@@ -551,7 +552,7 @@ int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
     o->n_num_features = m.n_num_features; o->n_cat_features = m.n_cat_features; o->n_trees = m.ens.n_trees;
     o->n_leaves = m.ens.n_leaves; o->iteration = m.iteration;
     o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
-    o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated;
+    o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated; o->max_noise_ratio = m.max_noise;
     API_END
 }
 

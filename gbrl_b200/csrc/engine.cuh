@@ -60,6 +60,7 @@ struct Ctl {
     int obl_has_replay;
     float obl_band;
     int bg_nonfinite;        // some build_grad is NaN/inf: the reference's scores are all NaN -> no split
+    unsigned int stat_max_noise;   // float bits: max over replayed candidates of |replayed - exact| / (2^-24 sqrt(n) |score|)
     long long stat_replay_items, stat_replay_nodes, stat_nodes_evaluated, stat_replay_overflow, stat_hist_rows;
 };
 
@@ -126,6 +127,7 @@ struct Model {
     long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0;
     bool have_candidates = false;
     long long hist_rows = 0;          // rows scanned by the histogram kernel (read back from Ctl)
+    float max_noise = 0.0f;           // see Ctl::stat_max_noise
     FitSession fs;
     DevBuf fit_x, fit_t, fit_batch_preds;
     // profiling

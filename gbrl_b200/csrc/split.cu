@@ -673,6 +673,7 @@ struct DecideParams {
     const ReplayItem *replay;
     const float *replay_scores;
     const int *obl_cands;
+    const float *scores;      // exact-tier scores [slot][C]
     Ctl *ctl;
 };
 
@@ -733,8 +734,14 @@ __global__ void __launch_bounds__(32) decide_greedy_kernel(DecideParams P, NodeA
         for (int i = rb + lane; i < rb + rc; i += 32) {
             const int cand = P.replay[i].cand;
             if (cand < 0) continue;
-            const float gain = P.replay_scores[i] * P.fw[cand / P.B] - parent;
+            const float sw = P.replay_scores[i] * P.fw[cand / P.B];
+            const float gain = sw - parent;
             if (gain > -INFINITY && better(gain, cand, bg_, bi)) { bg_ = gain; bi = cand; }
+            // calibration statistic of the band: observed rounding noise of the reference's sum, in units of
+            // 2^-24 * sqrt(n) * |score*w|  (exact-tier score*w = stored gain + exact parent)
+            const float sw_exact = P.scores[(size_t)p * P.C + cand] + na.parent_score[h];
+            const float unit = U24 * sqrtf((float)na.seg_len[h]) * fabsf(sw_exact);
+            if (unit > 0.0f && gain > -INFINITY) atomicMax(&P.ctl->stat_max_noise, __float_as_uint(fabsf(sw - sw_exact) / unit));
         }
         for (int o = 16; o > 0; o >>= 1) {
             const float og = __shfl_down_sync(0xffffffffu, bg_, o);
@@ -874,6 +881,7 @@ void launch_decide(Model &m, int level, cudaStream_t s) {
     P.hist_cur = ws.hist[level & 1].as<long long>(); P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
     P.rev_map = m.rev_num_map.as<int>(); P.replay = ws.replay.as<ReplayItem>(); P.replay_scores = ws.replay_scores.as<float>();
     P.obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap); P.ctl = ws.ctl.as<Ctl>();
+    P.scores = ws.scores.as<float>();
     if (m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS) GB_LAUNCH(decide_oblivious_kernel, 1, 256, 0, s, P, ws.na);
     else GB_LAUNCH(decide_greedy_kernel, P.nn, 32, 0, s, P, ws.na);
 }

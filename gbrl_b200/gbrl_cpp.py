@@ -378,7 +378,7 @@ class GBRL:
     def get_stats(self):
         md = self._meta()
         return {"kernel_launches": md.kernel_launches, "replay_items": md.replay_items, "replay_nodes": md.replay_nodes,
-                "replay_overflow": md.replay_overflow, "nodes_evaluated": md.nodes_evaluated,
+                "replay_overflow": md.replay_overflow, "nodes_evaluated": md.nodes_evaluated, "max_noise_ratio": float(md.max_noise_ratio),
                 "n_trees": md.n_trees, "n_leaves": md.n_leaves}
 
     def get_ensemble_data(self):

@@ -69,6 +69,8 @@ typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine 
     long long replay_nodes;      /* nodes for which the near-tie replay was triggered */
     long long replay_overflow;   /* replay requests dropped because the list was full (should be 0) */
     long long nodes_evaluated;   /* nodes whose candidates were scored */
+    float max_noise_ratio;       /* max over replayed candidates of |reference-order score - exact score| in units of
+                                    2^-24*sqrt(n)*|score|: the quantity band_kappa has to cover twice */
 } gbrl_b200_metadata;
 
 const char *gbrl_b200_last_error(void);

@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 GOLDEN = ["greedy_l2", "greedy_cos_ac", "obl_cos_ac", "obl_l2_uniform", "fit_greedy_l2_mb", "fit_obl_cos"]
 
 
+def _log_stats(tag, st):
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/noise_stats.txt", "a") as fh:
+        fh.write("%s | replay_nodes %d / %d evaluated, items %d, max_noise_ratio %.3f\n" % (
+            tag, st["replay_nodes"], st["nodes_evaluated"], st["replay_items"], st["max_noise_ratio"]))
+
+
 def _pair(ref_threads=1, fw=None, lrs=None, **kw):
     f, d = kw["input_dim"], kw["output_dim"]
     o = configure(make_oracle(ref_threads=ref_threads, **kw), f, d, lrs=lrs, fw=fw)
@@ -51,6 +59,7 @@ def test_step_parity_vs_oracle(n, f, d, depth, bins, score, grow, gen, iters, T)
     st = g.m.get_stats()
     assert st["replay_overflow"] == 0
     assert st["n_trees"] == iters
+    _log_stats("step n=%d f=%d d=%d depth=%d %s %s T=%d" % (n, f, d, depth, score, grow, T), st)
 
 
 @pytest.mark.parametrize("grow,score", [("greedy", "L2"), ("oblivious", "cosine")])

@@ -50,6 +50,12 @@ def test_full_size_tree_invariants(grow, score, n, f, d, depth):
     grads = (0.0 - y).astype(np.float32)
     m.step(X, None, grads)
     e = m.get_ensemble_data()
+    st = m.get_stats()
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/noise_stats.txt", "a") as fh:
+        fh.write("full-size %s %s n=%d | replay_nodes %d / %d evaluated, items %d, max_noise_ratio %.3f\n" % (
+            grow, score, n, st["replay_nodes"], st["nodes_evaluated"], st["replay_items"], st["max_noise_ratio"]))
     member = _check_tree_invariants(e, X, grads, depth, grow == "oblivious")
     # predict == bias - lr * value[leaf]
     lrs = np.array([0.1] * d, np.float32) if d == 1 else np.array([0.1] * (d - 1) + [0.05], np.float32)
