@@ -353,6 +353,22 @@ def main():
                "call": "GBRL.fit(host obs, host targets, iterations=%d, shuffle=False)" % K}
         del m2, Xh, yh
 
+    # ---- the same K iterations with the exact-arithmetic tier only (no reference-order replay of near-ties)
+    exact_only = None
+    if not args.no_replay and world == 1:
+        m3 = make_engine(c, local, ref_threads=cores, tie_replay=False)
+        m3.fit_begin(X, y, shuffle=False)
+        m3.fit_iterate(W, sync=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); m3.fit_iterate(K, sync=False); e1.record(); torch.cuda.synchronize()
+        ms3 = e0.elapsed_time(e1)
+        m3.fit_end()
+        exact_only = {"value": K / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3 / K,
+                      "note": "tie_replay=0: arg-max on exact integer-histogram sums only; differs from the reference only where "
+                              "the reference's own sequential-fp32 rounding noise decides between near-tied candidates"}
+        del m3
+
     # ---- CPU baseline on this box's host cores: bounded sample, scaled to the metric's unit
     cpu = None
     if not args.no_cpu_baseline and args.gpus == 1:
@@ -372,7 +388,7 @@ def main():
                           c["n"] * c["f"] * 2 / 1e6, c["n"] * c["f"] * 4 / 1e6),
                       "tie_replay": not args.no_replay, "ref_threads": cores},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-           "kernel_ms_per_step": breakdown, "final_loss": loss,
+           "kernel_ms_per_step": breakdown, "final_loss": loss, "exact_tier_only": exact_only,
            "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
                       "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"]}}
     print(json.dumps(out))
