@@ -48,9 +48,16 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     ws.N = N; ws.F = F; ws.D = D; ws.depth = md; ws.B = B;
     ws.nT = ceil_div(F, FT);
     ws.MAXN = (2 << md) - 1;
-    // feature tiles owned by this rank (contiguous block)
-    ws.tile_lo = (int)((long long)ws.nT * m.rank / m.world);
-    ws.tile_hi = (int)((long long)ws.nT * (m.rank + 1) / m.world);
+    // 2-D sharding of the histogram work: G_t tile groups x G_r row groups, G_t * G_r == world.
+    // Tile group tg owns a contiguous block of feature tiles; inside a tile group the 8192-row chunks of every
+    // node go round-robin to the G_r row groups.  The per-level all-reduce (integer sum) merges both dimensions.
+    int gt = m.world < ws.nT ? m.world : ws.nT;
+    while (gt > 1 && m.world % gt != 0) --gt;
+    const int gr = m.world / gt;
+    const int tg = m.rank % gt;
+    ws.row_groups = gr; ws.row_group = m.rank / gt;
+    ws.tile_lo = (int)((long long)ws.nT * tg / gt);
+    ws.tile_hi = (int)((long long)ws.nT * (tg + 1) / gt);
     const size_t n1 = (size_t)(N > 0 ? N : 1);
     ws.order[0].ensure(n1 * sizeof(int)); ws.order[1].ensure(n1 * sizeof(int));
     ws.nid.ensure(n1 * sizeof(int)); ws.rflag.ensure(n1); ws.rscan.ensure(n1 * sizeof(int));
@@ -61,7 +68,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     const size_t C = (size_t)F * B;
     ws.scores.ensure((C << lv) * sizeof(float));
     ws.cand_flags.ensure(C << lv);
-    ws.obl_tot.ensure(C * sizeof(float));
+    ws.obl_tot.ensure(2 * C * sizeof(float));
     size_t tb = (size_t)F << lv;
     if (tb < C / 256 + 1) tb = C / 256 + 1;
     ws.tile_best.ensure(tb * sizeof(float2));

@@ -28,7 +28,7 @@ namespace gb {
 // Decides, for every node of the level, whether its histogram is built directly or derived as
 // parent - sibling (only the smaller child is histogrammed), and emits the work items.
 __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int items_cap, int level, int max_depth,
-                                  int nT_local, int use_subtraction, int oblivious) {
+                                  int nT_local, int use_subtraction, int oblivious, int row_groups, int row_group) {
     __shared__ int s_cnt[1024];
     __shared__ int s_total;
     __shared__ unsigned long long s_rows;
@@ -55,7 +55,15 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
                 }
                 if (!oblivious && len == 0) direct = 1;            // nothing to add, histogram stays zero
                 na.direct[h] = direct;
-                if (direct && len > 0) { my = ceil_div(len, ITEM_ROWS) * nT_local; atomicAdd(&s_rows, (unsigned long long)len); }
+                if (direct && len > 0) {
+                    const int chunks = ceil_div(len, ITEM_ROWS);
+                    // chunks c with c % row_groups == row_group belong to this rank
+                    const int mine = chunks > row_group ? (chunks - row_group + row_groups - 1) / row_groups : 0;
+                    my = mine * nT_local;
+                    long long rows_mine = 0;
+                    for (int c = row_group; c < chunks; c += row_groups) rows_mine += min(len, (c + 1) * ITEM_ROWS) - c * ITEM_ROWS;
+                    atomicAdd(&s_rows, (unsigned long long)rows_mine);
+                }
             }
         }
         // block exclusive scan of `my`
@@ -71,8 +79,8 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
         const int off = s_total + incl - my;
         if (my > 0) {
             int w = off;
-            const int chunks = my / nT_local;
-            for (int c = 0; c < chunks; ++c)
+            const int chunks = ceil_div(len, ITEM_ROWS);
+            for (int c = row_group; c < chunks; c += row_groups)
                 for (int t = 0; t < nT_local; ++t) {
                     if (w < items_cap) {
                         Item it;
@@ -97,7 +105,8 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
 void launch_plan_level(Model &m, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
     GB_LAUNCH(plan_level_kernel, 1, 1024, 0, s, ws.na, ws.ctl.as<Ctl>(), ws.items.as<Item>(), ws.items_cap, level,
-              m.cfg.max_depth, ws.tile_hi - ws.tile_lo, m.cfg.use_subtraction, m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS);
+              m.cfg.max_depth, ws.tile_hi - ws.tile_lo, m.cfg.use_subtraction, m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS,
+              ws.row_groups, ws.row_group);
 }
 
 // ---------------------------------------------------------------- the histogram kernel

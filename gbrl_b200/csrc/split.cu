@@ -336,24 +336,32 @@ struct OblParams {
     const float *fw;
     const int *rev_map;
     float *obl_tot;            // [C]
+    float *obl_nb;             // [C] rounding-noise scale of the total: w * sum_nodes sqrt(n_node) * |score|
     float2 *blk_best;          // [nblocks]
     ReplayItem *replay;
     int *obl_cands;            // candidate list of replay (stored after the items, see launcher)
     Ctl *ctl;
 };
 
-__global__ void __launch_bounds__(256) obl_reduce_kernel(OblParams P) {
+__global__ void __launch_bounds__(256) obl_reduce_kernel(OblParams P, NodeArrays na) {
     __shared__ float s_gain[256];
     __shared__ int s_idx[256];
     const int c = blockIdx.x * 256 + threadIdx.x;
     float tot = -INFINITY;
     int idx = INT_MAX;
     if (c < P.C) {
-        float s = 0.0f;
-        for (int p = 0; p < P.nn; ++p) s += P.scores[(size_t)p * P.C + c];   // fitter.cpp:427-430, node order
+        float s = 0.0f, nb = 0.0f;
+        const int base = level_base(P.level);
+        for (int p = 0; p < P.nn; ++p) {
+            const float sp = P.scores[(size_t)p * P.C + c];
+            s += sp;                                                         // fitter.cpp:427-430, node order
+            if (sp > -INFINITY) nb += sqrtf((float)na.seg_len[base + p]) * fabsf(sp);
+        }
         const int f = c / P.B;
-        s = s * P.fw[P.rev_map[f]];                                          // fitter.cpp:432-435
+        const float wf = P.fw[P.rev_map[f]];
+        s = s * wf;                                                          // fitter.cpp:432-435
         P.obl_tot[c] = s;
+        P.obl_nb[c] = nb * fabsf(wf);
         if (s > -INFINITY) { tot = s; idx = c; }
     }
     s_gain[threadIdx.x] = tot; s_idx[threadIdx.x] = idx;
@@ -382,14 +390,16 @@ __global__ void __launch_bounds__(256) obl_select_kernel(OblParams P, NodeArrays
         s_best = g; s_besti = (bi == INT_MAX) ? -1 : bi; s_count = 0; s_w = 0; s_ok = 0;
         P.ctl->obl_best = g; P.ctl->obl_best_idx = s_besti; P.ctl->obl_has_replay = 0;
         atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, (unsigned long long)P.nn);
-        s_band = P.kappa * U24 * sqrtf((float)P.N) * fabsf(g) + FLT_MIN;
+        // per-node sequential sums carry noise ~ 2^-24 sqrt(n_node) |score|; the total's noise scale is their sum
+        s_band = 0.5f * P.kappa * U24 * (s_besti >= 0 ? P.obl_nb[s_besti] : 0.0f) + FLT_MIN;
     }
     __syncthreads();
     const float g = s_best;
     if (!P.tie_replay || s_besti < 0) return;
     const float lim = g - s_band;
+    const float half = 0.5f * P.kappa * U24;
     auto in_band = [&](int i) -> bool {
-        if (!(P.obl_tot[i] >= lim)) return false;
+        if (!(P.obl_tot[i] + half * P.obl_nb[i] >= lim)) return false;
         const int j = i % P.B;
         if (j > 0 && (P.cand_flags[i] & 2) && P.obl_tot[i - 1] > -INFINITY) return false;   // dominated by j-1
         return true;
@@ -850,9 +860,9 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         P.level = level; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = C; P.nn = nn; P.tie_replay = m.cfg.tie_replay;
         P.replay_cap = ws.replay_cap; P.nblocks = ceil_div(C, 256); P.kappa = kappa; P.N = ws.N;
         P.scores = ws.scores.as<float>(); P.cand_flags = ws.cand_flags.as<uint8_t>(); P.fw = m.feature_weights.as<float>();
-        P.rev_map = m.rev_num_map.as<int>(); P.obl_tot = ws.obl_tot.as<float>();
+        P.rev_map = m.rev_num_map.as<int>(); P.obl_tot = ws.obl_tot.as<float>(); P.obl_nb = ws.obl_tot.as<float>() + C;
         P.blk_best = ws.tile_best.as<float2>(); P.replay = ws.replay.as<ReplayItem>(); P.obl_cands = obl_cands; P.ctl = ctl;
-        GB_LAUNCH(obl_reduce_kernel, P.nblocks, 256, 0, s, P);
+        GB_LAUNCH(obl_reduce_kernel, P.nblocks, 256, 0, s, P, ws.na);
         GB_LAUNCH(obl_select_kernel, 1, 256, 0, s, P, ws.na);
     }
     if (m.cfg.tie_replay) {

@@ -10,20 +10,35 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+def shard(n_tiles, rank, world):
+    """Same arithmetic as prepare_workspace() in gbrl_b200/csrc/capi.cu: G_t tile groups x G_r row groups."""
+    gt = min(world, n_tiles)
+    while gt > 1 and world % gt != 0:
+        gt -= 1
+    gr = world // gt
+    tg, rg = rank % gt, rank // gt
+    return (n_tiles * tg) // gt, (n_tiles * (tg + 1)) // gt, gr, rg
+
+
 def tile_range(n_tiles, rank, world):
-    """Same arithmetic as prepare_workspace() in gbrl_b200/csrc/capi.cu."""
-    return (n_tiles * rank) // world, (n_tiles * (rank + 1)) // world
+    lo, hi, _, _ = shard(n_tiles, rank, world)
+    return lo, hi
 
 
 @pytest.mark.parametrize("n_tiles", [1, 2, 3, 4, 8, 13])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_tile_ownership_partitions_all_tiles(n_tiles, world):
-    owned = []
+def test_work_ownership_partitions_all_tiles_and_chunks(n_tiles, world):
+    """Every (tile, row-chunk) pair of a node is histogrammed by exactly one rank."""
+    n_chunks = 11
+    owner = {}
     for r in range(world):
-        lo, hi = tile_range(n_tiles, r, world)
-        assert 0 <= lo <= hi <= n_tiles
-        owned += list(range(lo, hi))
-    assert owned == list(range(n_tiles))
+        lo, hi, gr, rg = shard(n_tiles, r, world)
+        assert 0 <= lo < hi <= n_tiles and 0 <= rg < gr
+        for t in range(lo, hi):
+            for c in range(rg, n_chunks, gr):
+                assert (t, c) not in owner
+                owner[(t, c)] = r
+    assert len(owner) == n_tiles * n_chunks
 
 
 def _free_port():
