@@ -456,8 +456,47 @@ class GBRL:
     def _nyi(self, *a, **k):
         raise NotImplementedError("not on the fit/predict hot path (SURVEY.md 8): use the reference implementation")
 
-    save = export = print_tree = plot_tree = print_ensemble_metadata = tree_shap = ensemble_shap = _nyi
+    export = print_tree = plot_tree = print_ensemble_metadata = tree_shap = ensemble_shap = _nyi
+
+    # ------------------------------------------------------------------ checkpoint (reference wire format)
+    def save(self, path):
+        """GBRL::saveToFile (gbrl.cpp:1130-1173): writes the reference's `.gbrl_model` format, so a model trained here
+        loads in the reference (CPU) and vice versa."""
+        from . import model_io
+        md = self._meta()
+        meta = {"n_leaves": md.n_leaves, "n_trees": md.n_trees, "input_dim": md.input_dim, "output_dim": md.output_dim,
+                "policy_dim": md.policy_dim, "max_depth": md.max_depth, "min_data_in_leaf": md.min_data_in_leaf,
+                "n_bins": md.n_bins, "par_th": md.par_th, "cv_beta": self._kw["cv_beta"], "verbose": md.verbose,
+                "batch_size": md.batch_size, "use_cv": 0, "split_score_func": md.split_score_func,
+                "generator_type": md.generator_type, "grow_policy": md.grow_policy, "n_num_features": md.n_num_features,
+                "n_cat_features": 0, "iteration": md.iteration}
+        e = self.get_ensemble_data()
+        rev_num = np.empty(self._input_dim, np.int32)
+        rev_cat = np.empty(self._input_dim, np.int32)
+        _capi.check(self._lib.gbrl_b200_get_feature_mapping(self._h, None, None, rev_num.ctypes.data_as(C.POINTER(C.c_int)),
+                                                            rev_cat.ctypes.data_as(C.POINTER(C.c_int))))
+        e["reverse_num_feature_mapping"], e["reverse_cat_feature_mapping"] = rev_num, rev_cat
+        model_io.write_model(path, meta, e, self.get_optimizers(), self.learner_name)
+        return 0
 
     @staticmethod
-    def load(path):
-        raise NotImplementedError(".gbrl_model load is a 'next' row (SURVEY.md 8f-2)")
+    def load(path, device="cuda", **engine_kwargs):
+        """GBRL::loadFromFile (gbrl.cpp:1175-1252) for numerical-feature SGD models; the model lands on the GPU."""
+        from . import model_io
+        meta, e, opts, name = model_io.read_model(path)
+        if meta["n_cat_features"] != 0 or (e["is_numerics"] is not None and not np.all(e["is_numerics"])):
+            raise NotImplementedError("categorical features are out of scope of the B200 engine (SURVEY 2.1 #19)")
+        m = GBRL(input_dim=meta["input_dim"], output_dim=meta["output_dim"], policy_dim=meta["policy_dim"],
+                 max_depth=meta["max_depth"], min_data_in_leaf=meta["min_data_in_leaf"], n_bins=meta["n_bins"],
+                 par_th=meta["par_th"], cv_beta=meta["cv_beta"], split_score_func=_SCORE_R[meta["split_score_func"]],
+                 generator_type=_GEN_R[meta["generator_type"]], batch_size=meta["batch_size"],
+                 grow_policy=_GROW_R[meta["grow_policy"]], verbose=meta["verbose"], device=device, learner_name=name,
+                 **engine_kwargs)
+        m.set_bias(e["bias"])
+        m.set_feature_weights(e["feature_weights"])
+        m.set_feature_mapping(e["feature_mapping"], e["mapping_numerics"])
+        for o in opts:
+            m.set_optimizer(o["algo"], o["scheduler_func"], o["init_lr"], o["start_idx"], o["stop_idx"], o["stop_lr"], o["T"])
+        if meta["n_trees"] > 0:
+            m._set_ensemble(e, meta["n_num_features"])
+        return m

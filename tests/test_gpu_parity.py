@@ -216,3 +216,39 @@ def test_error_behaviour_matches_reference():
     assert m.get_num_trees() == 0
     p = m.predict_numpy(X)                       # no trees: bias only (predictor.cpp:125-128)
     assert np.array_equal(p, np.zeros((n, d), np.float32))
+
+
+def test_checkpoint_roundtrip_with_reference(tmp_path):
+    """a model trained on the GPU saves in the reference's `.gbrl_model` format; the reference loads it on
+    CPU and predicts the same; the file the reference writes loads back into the GPU engine."""
+    from oracle.oracle import load_reference
+    ref = load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from gbrl_b200 import GBRL
+    n, f, d = 2000, 9, 2
+    X, y = synth(n, f, d, 81)
+    for grow in ("greedy", "oblivious"):
+        kw = dict(input_dim=f, output_dim=d, max_depth=4, n_bins=64, split_score_func="cosine", generator_type="quantile",
+                  batch_size=n, grow_policy=grow)
+        g = GpuAdaptor(configure(make_gpu(**kw), f, d, bias=[0.2, -0.3]))
+        for it in range(3):
+            p = g.predict(X).reshape(n, d)
+            g.step(X, (p - y).astype(np.float32))
+        path = str(tmp_path / ("gpu_%s.gbrl_model" % grow))
+        assert g.m.save(path) == 0
+        r = ref.GBRL.load(path)
+        pr = np.array(r.predict(X, None), copy=True).reshape(n, d)
+        assert np.abs(pr.astype(np.float64) - g.predict(X).reshape(n, d)).max() <= TOL
+        path2 = str(tmp_path / ("ref_%s.gbrl_model" % grow))
+        assert r.save(path2) == 0
+        g2 = GBRL.load(path2)
+        assert g2.get_num_trees() == 3
+        assert np.abs(g2.predict_numpy(X).reshape(n, d).astype(np.float64) - pr).max() <= TOL
+        # training continues after a load (same trees as continuing the original model)
+        p = g.predict(X).reshape(n, d)
+        grads = (p - y).astype(np.float32)
+        g.step(X, grads)
+        g2.step(X, None, grads)
+        compare_ensembles(g.ensemble(), g2.get_ensemble_data(), "continue after load")
+        test_checkpoint_roundtrip_with_reference.keep = getattr(test_checkpoint_roundtrip_with_reference, "keep", []) + [r]
