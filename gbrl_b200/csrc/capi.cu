@@ -72,7 +72,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     size_t tb = (size_t)F << lv;
     if (tb < C / 256 + 1) tb = C / 256 + 1;
     ws.tile_best.ensure(tb * sizeof(float2));
-    ws.items_cap = (N / ITEM_ROWS + (1 << md) + 1) * (ws.tile_hi - ws.tile_lo > 0 ? ws.tile_hi - ws.tile_lo : 1);
+    ws.items_cap = (N / 2048 + (1 << md) + 1) * (ws.tile_hi - ws.tile_lo > 0 ? ws.tile_hi - ws.tile_lo : 1);   // 2048 = smallest item
     ws.items.ensure((size_t)ws.items_cap * sizeof(Item));
     ws.replay_cap = 1 << 18;
     if ((size_t)ws.replay_cap < 4 * ((size_t)1 << md)) ws.replay_cap = 4 << md;

@@ -33,8 +33,38 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
     __shared__ int s_total;
     __shared__ unsigned long long s_rows;
     const int base = level_base(level), nn = 1 << level;
-    if (threadIdx.x == 0) { s_total = 0; s_rows = 0; }
+    __shared__ unsigned long long s_direct_rows;
+    __shared__ int s_item_rows;
+    if (threadIdx.x == 0) { s_total = 0; s_rows = 0; s_direct_rows = 0; }
     __syncthreads();
+    // pass 0: rows that will be scanned at this level -> item size.  Items are at most ITEM_ROWS rows (int32 overflow
+    // bound of the shared-memory partial sums) and shrink (down to 2048) when the level has too few rows to give
+    // every SM a few items, which is what limits latency hiding on the deep levels.
+    for (int n0 = 0; n0 < nn; n0 += blockDim.x) {
+        const int p = n0 + threadIdx.x;
+        if (p < nn) {
+            const int h = base + p;
+            if (na.state[h] == NODE_OPEN) {
+                const int len = na.seg_len[h];
+                int direct = 1;
+                if (level > 0 && use_subtraction) {
+                    const int sib = (h & 1) ? h + 1 : h - 1;
+                    const int slen = na.seg_len[sib];
+                    direct = (len < slen) || (len == slen && (h & 1));
+                }
+                if (direct && len > 0) atomicAdd(&s_direct_rows, (unsigned long long)len);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long want = (long long)(s_direct_rows / (unsigned long long)(row_groups > 0 ? row_groups : 1)) * nT_local / (148 * 6);
+        int ir = ITEM_ROWS;
+        while (ir > 2048 && ir / 2 >= want) ir >>= 1;
+        s_item_rows = ir;
+    }
+    __syncthreads();
+    const int item_rows = s_item_rows;
     for (int n0 = 0; n0 < nn; n0 += blockDim.x) {
         const int p = n0 + threadIdx.x;
         int my = 0, len = 0, start = 0, slot = p;
@@ -56,12 +86,12 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
                 if (!oblivious && len == 0) direct = 1;            // nothing to add, histogram stays zero
                 na.direct[h] = direct;
                 if (direct && len > 0) {
-                    const int chunks = ceil_div(len, ITEM_ROWS);
+                    const int chunks = ceil_div(len, item_rows);
                     // chunks c with c % row_groups == row_group belong to this rank
                     const int mine = chunks > row_group ? (chunks - row_group + row_groups - 1) / row_groups : 0;
                     my = mine * nT_local;
                     long long rows_mine = 0;
-                    for (int c = row_group; c < chunks; c += row_groups) rows_mine += min(len, (c + 1) * ITEM_ROWS) - c * ITEM_ROWS;
+                    for (int c = row_group; c < chunks; c += row_groups) rows_mine += min(len, (c + 1) * item_rows) - c * item_rows;
                     atomicAdd(&s_rows, (unsigned long long)rows_mine);
                 }
             }
@@ -79,14 +109,14 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
         const int off = s_total + incl - my;
         if (my > 0) {
             int w = off;
-            const int chunks = ceil_div(len, ITEM_ROWS);
+            const int chunks = ceil_div(len, item_rows);
             for (int c = row_group; c < chunks; c += row_groups)
                 for (int t = 0; t < nT_local; ++t) {
                     if (w < items_cap) {
                         Item it;
                         it.slot = slot; it.tile = t;
-                        it.k0 = start + c * ITEM_ROWS;
-                        it.k1 = min(start + len, it.k0 + ITEM_ROWS);
+                        it.k0 = start + c * item_rows;
+                        it.k1 = min(start + len, it.k0 + item_rows);
                         items[w] = it;
                     }
                     ++w;

@@ -457,7 +457,7 @@ constexpr int RP_THREADS = 128;
 template <int R, int PASS>
 __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, float *sg /*[2][STAGE*D]*/,
                                             unsigned int *smask /*[2][STAGE/32]*/, const float *smean, float *accL, float *accR,
-                                            int &nR, float &tnum, float &fnum) {
+                                            int *s_nright, float &tnum, float &fnum) {
     constexpr int STAGE = RP_THREADS * R;
     constexpr int DC = (R == 8) ? 1 : (R == 4) ? 2 : 0;     // compile-time output_dim on the two fast paths
     const int D = DC > 0 ? DC : P.D, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -500,7 +500,7 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
             const int slot = r * RP_THREADS + tid;
             const bool right = rows[r] >= 0 && (xv[r] > tv);                     // node.cpp:339
             const unsigned int m = __ballot_sync(0xffffffffu, right);
-            if (lane == 0) smask[buf * (STAGE / 32) + slot / 32] = m;
+            if (lane == 0) { smask[buf * (STAGE / 32) + slot / 32] = m; if (PASS == 0 && m) atomicAdd(s_nright, __popc(m)); }
             if (rows[r] >= 0) {
                 if (pre) {
 #pragma unroll
@@ -528,11 +528,49 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
         if (warp == 0) {
             const float *g = sg + (size_t)buf * STAGE * D;
             const int cnt = min(STAGE, n - st * STAGE);
-            for (int w = 0; w * 32 < cnt; ++w) {
+            int w_begin = 0;
+            if (DC == 1 && PASS == 0) {
+                // D == 1: the whole stage as one software-pipelined chain.  The 32 values and the side mask of word
+                // w+1 are loaded (LDS.128 x 8) while the 32 predicated adds of word w run; the only dependency left on
+                // the critical path is the 4-cycle FADD chain per side (node.cpp:341-350).
+                const int full = cnt / 32;
+                if (full > 0) {
+                    const unsigned int gaddr = (unsigned int)__cvta_generic_to_shared(g);
+                    const unsigned int *mk = smask + buf * (STAGE / 32);
+                    float4 cur[8], nxt[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur[j].x), "=f"(cur[j].y), "=f"(cur[j].z), "=f"(cur[j].w) : "r"(gaddr + 16u * j));
+                    unsigned int mcur = mk[0], mnxt = 0;
+                    float aL = accL[0], aR = accR[0];
+                    for (int w = 0; w < full; ++w) {
+                        if (w + 1 < full) {
+                            const unsigned int a2 = gaddr + 128u * (w + 1);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(nxt[j].x), "=f"(nxt[j].y), "=f"(nxt[j].z), "=f"(nxt[j].w) : "r"(a2 + 16u * j));
+                            mnxt = mk[w + 1];
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const unsigned int m4 = mcur >> (4 * j);
+                            if (m4 & 1u) aR = aR + cur[j].x; else aL = aL + cur[j].x;
+                            if (m4 & 2u) aR = aR + cur[j].y; else aL = aL + cur[j].y;
+                            if (m4 & 4u) aR = aR + cur[j].z; else aL = aL + cur[j].z;
+                            if (m4 & 8u) aR = aR + cur[j].w; else aL = aL + cur[j].w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+                        mcur = mnxt;
+                    }
+                    accL[0] = aL; accR[0] = aR;
+                    w_begin = full;
+                }
+            }
+            for (int w = w_begin; w * 32 < cnt; ++w) {
                 const unsigned int mask = smask[buf * (STAGE / 32) + w];
                 const int c32 = min(32, cnt - w * 32);
                 if (PASS == 0) {
-                    nR += __popc(mask & (c32 == 32 ? 0xffffffffu : ((1u << c32) - 1u)));
                     if (DC == 1 && c32 == 32) {
                         // D == 1, full word: 8 x LDS.128 with immediate offsets, then 32 predicated adds; the only
                         // true dependency is the 4-cycle FADD chain of the side a row falls on   (node.cpp:341-350)
@@ -634,10 +672,13 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
         const int f = cand >= 0 ? cand / P.B : 0;
         const float tv = cand >= 0 ? P.thr[cand] : INFINITY;
         float accL[2] = {0.0f, 0.0f}, accR[2] = {0.0f, 0.0f};    // lane d and lane d+32 (D <= 64)
-        int nR = 0;
+        __shared__ int s_nright;
+        if (threadIdx.x == 0) s_nright = 0;
+        __syncthreads();
         float tnum = 0.0f, fnum = 0.0f;
-        replay_pass<R, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, nR, tnum, fnum);
-        const int nL = n - nR;     // valid in warp 0
+        replay_pass<R, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
+        const int nR = s_nright;   // all ballots are committed before the last barrier of the pass
+        const int nL = n - nR;
         const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
         const float lcf = (float)nL, rcf = (float)nR;
         float ln = 0.0f, rn = 0.0f;
@@ -658,7 +699,7 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
         if (P.score_func == GBRL_B200_SCORE_L2) {
             result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
         } else {
-            replay_pass<R, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, nR, tnum, fnum);
+            replay_pass<R, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
             if (cand >= 0) {
                 const float num = tnum + fnum;
                 const float den = rn * rcf + ln * lcf;
