@@ -46,6 +46,7 @@ struct ReplayItem {    // re-score (node, candidate) in the reference's sequenti
 struct Ctl {
     int n_items;             // histogram items of the current level
     int n_replay;            // replay items of the current level
+    int n_partials;          // histogram partials handed out at the current level (pool index)
     int replay_overflow;
     int qexp;                // fixed-point exponent of build_grads: q = rint(g * 2^qexp)
     int qexp_raw;            // same for the raw gradients (leaf values)
@@ -94,6 +95,8 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     int row_offset = 0;             // first row of the current mini-batch inside the code matrix
     DevBuf codes, thr, thrT, bg, order[2], nid, rflag, rscan, chunk_sums, hist[2], scores, cand_flags;
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
+    DevBuf pair_first, pair_nitems, pl_count, pl_ids, partials;   // histogram pairs (node x local tile) and staged partials
+    int max_partials = 0, pl_stride = 0, n_sms = 0;
     DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage, pred_partials;
     NodeArrays na{};
     size_t sort_tmp_bytes = 0;
