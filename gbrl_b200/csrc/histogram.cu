@@ -14,9 +14,10 @@
 //     plane[w][code][feature], so bank == feature: every ATOMS.ADD is bank-conflict free by
 //     construction, whatever the codes are (ncu: 1.05 wavefronts per atomic).
 //   * integer accumulation (north_star: "int32 atomics into shared-memory histograms"): build_grads
-//     are converted to 36-bit fixed point q = hi*2^18 + lo; count, lo and hi are accumulated in three
-//     int32 planes (8192 rows * 2^18 < 2^31); after every item the planes are folded into per-CTA
-//     int64 / int32 shared accumulators, which are written out only when the CTA leaves a pair:
+//     are converted to 30-bit fixed point q = hi*2^9 + lo and accumulated with TWO atomics per (sample, feature):
+//     plane A += (1 << 20) + lo  (count in the top 12 bits, sum of lo below), plane B += hi; every 2048 rows the
+//     planes are folded into per-CTA int64 / int32 shared accumulators (2048 * 2^9 = 2^20, 2048 * 2^20 = 2^31, so
+//     nothing can overflow), which are written out only when the CTA leaves a pair:
 //       - pair owned by this CTA alone  -> plain stores into the global int64 histogram
 //       - pair shared by several CTAs   -> plain stores of a partial (96 KB) + hist_reduce_kernel
 //     so the global histogram costs no atomics at all (the first version flushed 16K REDG.ADD.64 per item and
@@ -134,8 +135,8 @@ void launch_plan_level(Model &m, int level, cudaStream_t s) {
 
 // ---------------------------------------------------------------- the histogram kernel
 // dynamic shared memory:
-//   3 int32 planes of (NB+1)*FT   count / lo / hi of the current item (row 0 = dump row for code 0, which keeps
-//                                 the inner loop branch-free)                                            98,688 B
+//   2 int32 planes of (NB+1)*FT   A = count<<20 | sum lo, B = sum hi of the current <=2048 rows (row 0 = dump row for
+//                                 code 0, which keeps the inner loop branch-free)                         65,792 B
 //   acc_sum int64[HENT], acc_cnt int32[HENT]   the CTA's running totals of the current pair              98,304 B
 // The code matrix stores code*64 (u16), so the byte offset of (code, feature fs) inside a plane = stored*2 + fs*4.
 __device__ __forceinline__ void red_shared(unsigned int addr, int v) {
@@ -158,7 +159,7 @@ struct HistParams {
 __global__ void __launch_bounds__(HIST2_THREADS, 1) hist_kernel(HistParams P) {
     extern __shared__ int sh[];
     constexpr int PB = HPLANE * 4;               // plane size in bytes
-    long long *acc_sum = reinterpret_cast<long long *>(sh + 3 * HPLANE);
+    long long *acc_sum = reinterpret_cast<long long *>(sh + 2 * HPLANE);
     int *acc_cnt = reinterpret_cast<int *>(acc_sum + HENT);
     __shared__ int s_pid;
     const int n_items = P.ctl->n_items;
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(HIST2_THREADS, 1) hist_kernel(HistParams P) {
     const int rl = (lane >> 3) & 3, g = lane & 7;
     const int HS = 1 + P.D;
 
-    for (int i = threadIdx.x; i < 3 * HPLANE; i += HIST2_THREADS) sh[i] = 0;
+    for (int i = threadIdx.x; i < 2 * HPLANE; i += HIST2_THREADS) sh[i] = 0;
     for (int i = threadIdx.x; i < HENT; i += HIST2_THREADS) { acc_sum[i] = 0; acc_cnt[i] = 0; }
     __syncthreads();
 
@@ -266,45 +267,46 @@ __global__ void __launch_bounds__(HIST2_THREADS, 1) hist_kernel(HistParams P) {
         auto add_half = [&](const uint2 *b, const float *gv) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
-                const long long q = __float2ll_rn(gv[s] * scale);
-                const int lo = (int)(q & ((1ll << LO_BITS) - 1));
-                const int hi = (int)(q >> LO_BITS);
+                const int q = __float2int_rn(gv[s] * scale);                    // |q| <= 2^28
+                const int a = (1 << CNT_SHIFT) + (q & ((1 << LO_BITS) - 1));      // count unit + lo
+                const int hi = q >> LO_BITS;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const unsigned int cs = __byte_perm(upper[k] ? b[s].y : b[s].x, 0u, psel[k]);   // code * 64, zero-extended
                     const unsigned int addr = lbase[k] + cs * 2u;
-                    red_shared(addr, 1);
-                    red_shared_off<PB>(addr, lo);
-                    red_shared_off<2 * PB>(addr, hi);
+                    red_shared(addr, a);
+                    red_shared_off<PB>(addr, hi);
                 }
             }
         };
-        int kb = it.k0 + warp * 32;
-        int cur_row = (kb + lane < it.k1) ? P.order[kb + lane] : -1;
-        load_half(cur_row, 0, bA, gA);
-        for (; kb < it.k1; kb += STEP) {
-            const int kn = kb + STEP + lane;
-            const int next_row = (kn < it.k1) ? P.order[kn] : -1;   // row ids of the next block
-            load_half(cur_row, 1, bB, gB);
-            add_half(bA, gA);
-            load_half(next_row, 0, bA, gA);
-            add_half(bB, gB);
-            cur_row = next_row;
-        }
-        __syncthreads();
-        // fold the item's int32 planes into the running totals (8 entries per thread), clear the planes
-        for (int e = threadIdx.x; e < HENT; e += HIST2_THREADS) {
-            const int se = e + FT;                              // shared row = bin + 1
-            const int cnt = sh[se];
-            if (cnt != 0) {
-                const unsigned int l = (unsigned int)sh[HPLANE + se];
-                const int h = sh[2 * HPLANE + se];
-                acc_cnt[e] += cnt;
-                acc_sum[e] += ((long long)h << LO_BITS) + (long long)l;
-                sh[se] = 0; sh[HPLANE + se] = 0; sh[2 * HPLANE + se] = 0;
+        for (int c0 = it.k0; c0 < it.k1; c0 += FOLD_ROWS) {
+            const int c1 = min(it.k1, c0 + FOLD_ROWS);
+            int kb = c0 + warp * 32;
+            int cur_row = (kb + lane < c1) ? P.order[kb + lane] : -1;
+            load_half(cur_row, 0, bA, gA);
+            for (; kb < c1; kb += STEP) {
+                const int kn = kb + STEP + lane;
+                const int next_row = (kn < c1) ? P.order[kn] : -1;   // row ids of the next block
+                load_half(cur_row, 1, bB, gB);
+                add_half(bA, gA);
+                load_half(next_row, 0, bA, gA);
+                add_half(bB, gB);
+                cur_row = next_row;
             }
+            __syncthreads();
+            // fold the planes of these <= 2048 rows into the running totals (8 entries per thread), clear the planes
+            for (int e = threadIdx.x; e < HENT; e += HIST2_THREADS) {
+                const int se = e + FT;                              // shared row = bin + 1
+                const unsigned int a = (unsigned int)sh[se];
+                if (a != 0u) {
+                    const int h = sh[HPLANE + se];
+                    acc_cnt[e] += (int)(a >> CNT_SHIFT);
+                    acc_sum[e] += ((long long)h << LO_BITS) + (long long)(a & ((1u << CNT_SHIFT) - 1u));
+                    sh[se] = 0; sh[HPLANE + se] = 0;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     if (cur_pair >= 0) emit(cur_pair, cur_slot, cur_tile);
 }
@@ -323,6 +325,7 @@ hist_reduce_kernel(const int *__restrict__ partials, const int *__restrict__ pl_
     long long *hb = hist + ((size_t)slot * nT_total + (tile_lo + tile)) * (size_t)HENT * HS;
     for (int e = blockIdx.y * 256 + threadIdx.x; e < HENT; e += gridDim.y * 256) {
         long long c = 0, sm = 0;
+#pragma unroll 4
         for (int k = 0; k < np; ++k) {
             const int pid = pl_ids[(size_t)pair * pl_stride + k];
             if (pid >= max_partials) continue;
@@ -342,7 +345,7 @@ void launch_histogram(Model &m, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
     const int n_sms = ws.n_sms;
     static bool attr = false;
-    const size_t smem = (size_t)3 * HPLANE * sizeof(int) + (size_t)HENT * (sizeof(long long) + sizeof(int));
+    const size_t smem = (size_t)2 * HPLANE * sizeof(int) + (size_t)HENT * (sizeof(long long) + sizeof(int));
     if (!attr) {
         GB_CUDA(cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
@@ -366,7 +369,7 @@ void launch_histogram(Model &m, int level, cudaStream_t s) {
             GB_CUDA(cudaMemsetAsync(ws.pl_count.p, 0, (size_t)n_pairs * sizeof(int), s));
         }
         GB_LAUNCH(hist_kernel, n_sms, HIST2_THREADS, smem, s, P);
-        GB_LAUNCH(hist_reduce_kernel, dim3(n_pairs, 8), 256, 0, s, ws.partials.as<int>(), ws.pl_count.as<int>(), ws.pl_ids.as<int>(),
+        GB_LAUNCH(hist_reduce_kernel, dim3(n_pairs, 32), 256, 0, s, ws.partials.as<int>(), ws.pl_count.as<int>(), ws.pl_ids.as<int>(),
                   P.hist, nT_local, ws.tile_lo, ws.nT, ws.D, d0, P.write_count, ws.pl_stride, ws.max_partials);
     }
 }

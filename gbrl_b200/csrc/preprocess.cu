@@ -117,7 +117,9 @@ __global__ void qexp_kernel(Ctl *ctl, int which) {
     if (mx > 0.0f) {
         int k;
         frexpf(mx, &k);            // mx = m * 2^k, m in [0.5, 1)  ->  mx < 2^k
-        e = (Q_BITS - 2) - k;
+        // build_grads go through the int32 histogram planes (Q_BITS); the raw gradients of the leaf values are summed
+        // in int64 directly and can keep 40 bits
+        e = ((which == 0 ? Q_BITS : 42) - 2) - k;
         if (e > 120) e = 120;
         if (e < -120) e = -120;
     }
