@@ -12,11 +12,9 @@ namespace gb {
 // ---------------------------------------------------------------- constants
 constexpr int FT = 32;            // features per histogram tile (one per lane: bank == feature)
 constexpr int NB = 256;           // histogram bins per feature (codes 1..256; code 0 never goes right)
-constexpr int ITEM_ROWS = 8192;   // rows per histogram work item (scheduling granularity)
-constexpr int FOLD_ROWS = 2048;   // rows between two folds of the int32 planes into the int64 accumulators
-constexpr int LO_BITS = 9;        // fixed-point split: q = hi * 2^9 + lo, lo in [0, 2^9)
-constexpr int CNT_SHIFT = 20;     // plane A = count << 20 | sum(lo):  2048 * 2^9 = 2^20, 2048 < 2^12
-constexpr int Q_BITS = 30;        // |q| <= 2^28: hi = q >> 9 fits 2^20, 2048 * 2^20 = 2^31
+constexpr int ITEM_ROWS = 8192;   // max rows per histogram work item (bounds the int32 smem partial sums)
+constexpr int LO_BITS = 18;       // fixed-point split: q = hi * 2^18 + lo, lo in [0, 2^18)
+constexpr int Q_BITS = 36;        // |q| < 2^35  (8192 rows * 2^18 < 2^31, 8192 * 2^17 = 2^30)
 constexpr int MAX_DEPTH_SUPPORTED = 12;
 constexpr int MAX_OPTS = 64;
 constexpr int HIST_THREADS = 512;
