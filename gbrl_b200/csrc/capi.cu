@@ -92,12 +92,6 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     if ((size_t)ws.replay_cap < 4 * ((size_t)1 << md)) ws.replay_cap = 4 << md;
     ws.replay.ensure((size_t)ws.replay_cap * (sizeof(ReplayItem) + sizeof(int)));
     ws.replay_scores.ensure((size_t)ws.replay_cap * sizeof(float));
-    if (m.cfg.tie_replay) {
-        ws.rp_gbuf.ensure(n1 * D * sizeof(float));
-        ws.rp_plane_words = (int)(n1 / 32 + ((size_t)1 << md) + 2);
-        ws.rp_flags.ensure((size_t)64 * ws.rp_plane_words * sizeof(unsigned int));
-        ws.rp_wbase.ensure(((size_t)1 << md) * sizeof(int) + 16);
-    }
     // node arrays carved from one allocation
     const size_t MN = ws.MAXN;
     const size_t bytes = MN * D * sizeof(long long) + MN * 10 * sizeof(int) + MN * 4 * sizeof(float);

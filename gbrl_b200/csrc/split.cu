@@ -444,90 +444,7 @@ struct ReplayParams {
     const ReplayItem *items;
     float *out;
     const Ctl *ctl;
-    // prep stage (replay_prep_*): gradients gathered into order-space and per-(plane, row) side bits
-    const int *nid;
-    float *gbuf;               // [N][D]: gbuf[k] = bg[order[k]] for rows of nodes that have replay items
-    unsigned int *flagbuf;     // [planes][plane_words]: bit (k - seg_start) of word wbase[node] + (k - seg_start)/32
-    int *wbase;                // [nodes of the level]: first flag word of the node's segment inside a plane
-    int planes, plane_words, level, nn, oblivious;
 };
-
-// ---------------------------------------------------------------- replay prep
-// The chain kernel must not gather: one SM can only keep a few hundred scattered sector requests in flight, which made
-// the per-row gathers (order -> feature value -> gradient) the bottleneck of the first version.  The gathers are
-// therefore done here, by the whole GPU: (a) gradients of flagged nodes are copied into order-space, (b) the side
-// bit x[f] > thr of every (replay item, row) is stored in a bit plane.  Items of different nodes share a plane
-// (their segments are disjoint): greedy -> plane = rank of the item inside its node, oblivious -> plane = candidate.
-constexpr int RP_PLANES = 64;
-
-__device__ __forceinline__ int replay_plane(const ReplayParams &P, const NodeArrays &na, int it, int h, int cand) {
-    if (cand < 0) return -2;                                   // parent item: every row on the left, no bits needed
-    const int pl = P.oblivious ? it / P.nn : it - na.rep_begin[h];
-    return pl < P.planes ? pl : -1;                            // -1: no plane left -> gather path
-}
-
-__global__ void replay_seg_kernel(ReplayParams P, NodeArrays na) {
-    // exclusive scan of ceil(seg_len / 32) over the nodes of the level (single CTA, <= 4096 nodes)
-    __shared__ int s_carry;
-    __shared__ int s_scan[1024];
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    const int base = level_base(P.level);
-    for (int n0 = 0; n0 < P.nn; n0 += 1024) {
-        const int p = n0 + threadIdx.x;
-        const int v = p < P.nn ? (na.seg_len[base + p] + 31) / 32 : 0;
-        s_scan[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int t = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-            __syncthreads();
-            s_scan[threadIdx.x] += t;
-            __syncthreads();
-        }
-        if (p < P.nn) P.wbase[p] = s_carry + s_scan[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry += s_scan[1023];
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256) replay_gather_kernel(ReplayParams P, NodeArrays na, int N) {
-    if (P.ctl->n_replay == 0) return;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < N; k += (long long)gridDim.x * blockDim.x) {
-        const int i = P.order[k];
-        const int h = P.nid[i];
-        const bool flagged = P.oblivious ? (level_of(h) == P.level) : (na.rep_count[h] > 0);
-        if (flagged)
-            for (int d = 0; d < P.D; ++d) P.gbuf[(size_t)k * P.D + d] = P.bg[(size_t)i * P.D + d];
-    }
-}
-
-// unit = (item, one of 64 row chunks); a warp turns 32 consecutive rows into one flag word
-__global__ void __launch_bounds__(256) replay_flags_kernel(ReplayParams P, NodeArrays na) {
-    const int n_items = P.ctl->n_replay;
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long units = (long long)n_items * 64;
-    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-        const int it = (int)(u >> 6), chunk = (int)(u & 63);
-        const ReplayItem item = P.items[it];
-        const int h = item.node, cand = item.cand;
-        const int plane = replay_plane(P, na, it, h, cand);
-        if (plane < 0) continue;
-        const int s0 = na.seg_start[h], n = na.seg_len[h];
-        const int f = cand / P.B;
-        const float tv = P.thr[cand];
-        unsigned int *fw = P.flagbuf + (size_t)plane * P.plane_words + P.wbase[h - level_base(P.level)];
-        const int n_words = (n + 31) / 32;
-        // words w = chunk*8 + wib, then += 64*8 (each CTA pass covers 8 words = 256 rows)
-        for (int w = chunk * 8 + wib; w < n_words; w += 64 * 8) {
-            const int k = w * 32 + lane;
-            bool right = false;
-            if (k < n) right = P.X[(size_t)P.order[s0 + k] * P.F + f] > tv;                 // node.cpp:339
-            const unsigned int m = __ballot_sync(0xffffffffu, right);
-            if (lane == 0) fw[w] = m;
-        }
-    }
-}
 
 // One 128-thread CTA per item.  Rows of the node are visited in ascending sample order (== reference
 // sample_indices).  The chain itself is inherently sequential (every float add depends on the previous one), so
@@ -538,8 +455,7 @@ __global__ void __launch_bounds__(256) replay_flags_kernel(ReplayParams P, NodeA
 constexpr int RP_THREADS = 128;
 
 template <int R, int PASS>
-__device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, int plane,
-                                            const unsigned int *fwords, float *sg /*[2][STAGE*D]*/,
+__device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, float *sg /*[2][STAGE*D]*/,
                                             unsigned int *smask /*[2][STAGE/32]*/, const float *smean, float *accL, float *accR,
                                             int *s_nright, float &tnum, float &fnum) {
     constexpr int STAGE = RP_THREADS * R;
@@ -558,52 +474,40 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
     //   chain(st)       from shared memory
     //   commit(st+1)    registers -> shared memory
     int rows_n[R];
-    // streaming mode (plane != -1): the prep kernels already gathered the gradients into order-space (gbuf) and the
-    // side bits into fwords, so a "row id" is just the position k and every load below is coalesced.
-    const bool stream = plane != -1;
     auto load_rows = [&](int st, int *dst) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int k = st * STAGE + r * RP_THREADS + tid;
-            dst[r] = (st < n_stages && k < n) ? (stream ? s0 + k : P.order[s0 + k]) : -1;
+            dst[r] = (st < n_stages && k < n) ? P.order[s0 + k] : -1;
         }
     };
     auto gather = [&](const int *src) {
-        const float *gsrc = stream ? P.gbuf : P.bg;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             rows[r] = src[r];
-            xv[r] = (!stream && src[r] >= 0 && is_cand) ? P.X[(size_t)src[r] * P.F + f] : -INFINITY;
+            xv[r] = (src[r] >= 0 && is_cand) ? P.X[(size_t)src[r] * P.F + f] : -INFINITY;
             if (pre && src[r] >= 0) {
 #pragma unroll
                 for (int d = 0; d < (DG > 0 ? DG : 1); ++d)
-                    if (d < D) gpre[r][d] = gsrc[(size_t)src[r] * D + d];
+                    if (d < D) gpre[r][d] = P.bg[(size_t)src[r] * D + d];
             }
         }
     };
-    auto commit = [&](int buf, int commit_stage) {
+    auto commit = [&](int buf) {
         float *g = sg + (size_t)buf * STAGE * D;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int slot = r * RP_THREADS + tid;
             const bool right = rows[r] >= 0 && (xv[r] > tv);                     // node.cpp:339
-            unsigned int m = __ballot_sync(0xffffffffu, right);
-            if (lane == 0) {
-                if (stream) {                                                    // bits precomputed by replay_flags_kernel
-                    const int w = (commit_stage * STAGE + slot) / 32;
-                    m = (plane >= 0 && w * 32 < n) ? fwords[w] : 0u;
-                }
-                smask[buf * (STAGE / 32) + slot / 32] = m;
-                if (PASS == 0 && m) atomicAdd(s_nright, __popc(m));
-            }
+            const unsigned int m = __ballot_sync(0xffffffffu, right);
+            if (lane == 0) { smask[buf * (STAGE / 32) + slot / 32] = m; if (PASS == 0 && m) atomicAdd(s_nright, __popc(m)); }
             if (rows[r] >= 0) {
                 if (pre) {
 #pragma unroll
                     for (int d = 0; d < (DG > 0 ? DG : 1); ++d)
                         if (d < D) g[(size_t)slot * D + d] = gpre[r][d];
                 } else {
-                    const float *gsrc = stream ? P.gbuf : P.bg;
-                    for (int d = 0; d < D; ++d) g[(size_t)slot * D + d] = gsrc[(size_t)rows[r] * D + d];
+                    for (int d = 0; d < D; ++d) g[(size_t)slot * D + d] = P.bg[(size_t)rows[r] * D + d];
                 }
             }
         }
@@ -613,7 +517,7 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
         load_rows(0, r0);
         load_rows(1, rows_n);
         gather(r0);
-        commit(0, 0);
+        commit(0);
     }
     __syncthreads();
     for (int st = 0; st < n_stages; ++st) {
@@ -745,7 +649,7 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
                 }
             }
         }
-        if (st + 1 < n_stages) commit(buf ^ 1, st + 1);
+        if (st + 1 < n_stages) commit(buf ^ 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) rows_n[r] = rows_nn[r];
         __syncthreads();
@@ -772,9 +676,7 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
         if (threadIdx.x == 0) s_nright = 0;
         __syncthreads();
         float tnum = 0.0f, fnum = 0.0f;
-        const int plane = replay_plane(P, na, it, h, cand);
-        const unsigned int *fwords = plane >= 0 ? P.flagbuf + (size_t)plane * P.plane_words + P.wbase[h - level_base(P.level)] : nullptr;
-        replay_pass<R, 0>(P, s0, n, f, tv, cand >= 0, plane, fwords, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
+        replay_pass<R, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
         const int nR = s_nright;   // all ballots are committed before the last barrier of the pass
         const int nL = n - nR;
         const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
@@ -797,7 +699,7 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
         if (P.score_func == GBRL_B200_SCORE_L2) {
             result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
         } else {
-            replay_pass<R, 1>(P, s0, n, f, tv, cand >= 0, plane, fwords, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
+            replay_pass<R, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
             if (cand >= 0) {
                 const float num = tnum + fnum;
                 const float den = rn * rcf + ln * lcf;
@@ -1009,16 +911,6 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         R.F = ws.F; R.B = ws.B; R.D = ws.D; R.score_func = m.cfg.split_score_func; R.min_data = m.cfg.min_data_in_leaf;
         R.X = X; R.bg = ws.bg.as<float>(); R.order = ws.order[0].as<int>(); R.thr = ws.thr.as<float>();
         R.items = ws.replay.as<ReplayItem>(); R.out = ws.replay_scores.as<float>(); R.ctl = ctl;
-        R.nid = ws.nid.as<int>(); R.gbuf = ws.rp_gbuf.as<float>(); R.flagbuf = ws.rp_flags.as<unsigned int>(); R.wbase = ws.rp_wbase.as<int>();
-        R.planes = RP_PLANES; R.plane_words = ws.rp_plane_words; R.level = level; R.nn = nn; R.oblivious = obl ? 1 : 0;
-        GB_LAUNCH(replay_seg_kernel, 1, 1024, 0, s, R, ws.na);
-        {
-            int grid = ceil_div(ws.N, 256 * 8);
-            if (grid > 1184) grid = 1184;
-            if (grid < 1) grid = 1;
-            GB_LAUNCH(replay_gather_kernel, grid, 256, 0, s, R, ws.na, ws.N);
-        }
-        GB_LAUNCH(replay_flags_kernel, 148 * 8, 256, 0, s, R, ws.na);
         // rows per thread per stage: 8 (1024-row stages) for D == 1 down to 1 for wide outputs, so that a stage's
         // gradients fit in registers while they are in flight and two stages fit in shared memory
         const int D = ws.D;
