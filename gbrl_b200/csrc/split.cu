@@ -452,9 +452,10 @@ struct ReplayParams {
 // (order -> feature value -> gradients; the loads are issued before the chain of the current stage starts and
 // land in registers while it runs), warp 0 runs the chain out of shared memory, lane d owning output dimension d.
 // The Cosine numerators are one chain over (row, col) (mat_vec_dot_sum) and are run by every lane redundantly.
-constexpr int RP_THREADS = 128;
+// CTA size: 512 threads (16 warps gather a stage of 4096 rows for D == 1 while warp 0 runs the chain) for narrow
+// outputs, 128 threads for wide ones (the stage has to fit in shared memory twice)
 
-template <int R, int PASS>
+template <int R, int PASS, int RP_THREADS>
 __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, float *sg /*[2][STAGE*D]*/,
                                             unsigned int *smask /*[2][STAGE/32]*/, const float *smean, float *accL, float *accR,
                                             int *s_nright, float &tnum, float &fnum) {
@@ -656,7 +657,7 @@ __device__ __forceinline__ void replay_pass(const ReplayParams &P, int s0, int n
     }
 }
 
-template <int R>
+template <int R, int RP_THREADS>
 __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, NodeArrays na) {
     extern __shared__ float s_dyn[];
     constexpr int STAGE = RP_THREADS * R;
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
         if (threadIdx.x == 0) s_nright = 0;
         __syncthreads();
         float tnum = 0.0f, fnum = 0.0f;
-        replay_pass<R, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
+        replay_pass<R, 0, RP_THREADS>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
         const int nR = s_nright;   // all ballots are committed before the last barrier of the pass
         const int nL = n - nR;
         const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
         if (P.score_func == GBRL_B200_SCORE_L2) {
             result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
         } else {
-            replay_pass<R, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
+            replay_pass<R, 1, RP_THREADS>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, accL, accR, &s_nright, tnum, fnum);
             if (cand >= 0) {
                 const float num = tnum + fnum;
                 const float den = rn * rcf + ln * lcf;
@@ -915,12 +916,13 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         // gradients fit in registers while they are in flight and two stages fit in shared memory
         const int D = ws.D;
         const int rpt = D <= 1 ? 8 : D <= 2 ? 4 : D <= 4 ? 2 : 1;
-        const size_t smem = ((size_t)2 * RP_THREADS * rpt * D + 2 * D) * sizeof(float) + (size_t)2 * (RP_THREADS * rpt / 32) * sizeof(unsigned int);
-        if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (rpt == 8) GB_LAUNCH(replay_kernel<8>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
-        else if (rpt == 4) GB_LAUNCH(replay_kernel<4>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
-        else if (rpt == 2) GB_LAUNCH(replay_kernel<2>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
-        else GB_LAUNCH(replay_kernel<1>, 148 * 4, RP_THREADS, smem, s, R, ws.na);
+        const int T = D <= 4 ? 512 : 128;
+        const size_t smem = ((size_t)2 * T * rpt * D + 2 * D) * sizeof(float) + (size_t)2 * (T * rpt / 32) * sizeof(unsigned int);
+        if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(replay_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (rpt == 8) GB_LAUNCH((replay_kernel<8, 512>), 148 * 4, 512, smem, s, R, ws.na);
+        else if (rpt == 4) GB_LAUNCH((replay_kernel<4, 512>), 148 * 4, 512, smem, s, R, ws.na);
+        else if (rpt == 2) GB_LAUNCH((replay_kernel<2, 512>), 148 * 4, 512, smem, s, R, ws.na);
+        else GB_LAUNCH((replay_kernel<1, 128>), 148 * 4, 128, smem, s, R, ws.na);
     }
 }
 
