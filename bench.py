@@ -30,6 +30,8 @@ WORKLOADS = {
     "c2": dict(n=1_000_000, f=128, d=1, depth=6, grow="greedy", score="L2", lrs=[(0.1, 0, 1)]),
     "c3": dict(n=4_000_000, f=64, d=2, depth=8, grow="oblivious", score="cosine", lrs=[(0.1, 0, 1), (0.01, 1, 2)]),
     "c5": dict(n=8_000_000, f=256, d=1, depth=6, grow="greedy", score="L2", lrs=[(0.1, 0, 1)]),
+    # PPO-minibatch shape driven through GBRL.step (shared actor-critic tree: 3 policy outputs + value), gbrl defaults
+    "rl": dict(n=32_768, f=64, d=4, depth=4, grow="greedy", score="cosine", lrs=[(0.1, 0, 3), (0.01, 3, 4)]),
 }
 # predict-only workload (BASELINE config 4): 100k oblivious trees d6, D=2, batch 8192 x 128 (PPO rollout shape)
 PREDICT = dict(n=8192, f=128, d=2, depth=6, n_trees=100_000, lrs=[(0.1, 0, 1), (0.01, 1, 2)])
@@ -225,6 +227,43 @@ def bench_predict(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ step() API (RL path)
+def bench_step_api(args):
+    """GBRL_SB3's call pattern: every update calls predict(obs) then step(obs, grads) with device tensors; step()
+    recomputes the quantile candidates from the batch (fitter.cpp:72-90), bins it and grows one tree."""
+    import torch
+    c = WORKLOADS["rl"]
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    dev = torch.device("cuda", 0)
+    X, y = synth_torch(c["n"], c["f"], c["d"], 0, dev)
+    m = make_engine(c, 0, ref_threads=os.cpu_count() or 1, tie_replay=not args.no_replay)
+    ti = lambda t: (t.data_ptr(), tuple(t.shape), "torch.float32", "cuda")
+
+    def one():
+        p = torch.from_dlpack(m.predict(ti(X), None))
+        g = (p.reshape(c["n"], c["d"]) - y).contiguous()
+        m.step(ti(X), None, ti(g))
+    for _ in range(W):
+        one()
+    m.profile(True)
+    torch.cuda.synchronize()
+    l0 = m.get_stats()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        one()
+    ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / K
+    prof = m.get_profile()
+    out = {"metric": "boosting-iters/sec (step API: predict + step per call)", "value": 1000.0 / ms, "unit": UNIT, "n_gpus": 1,
+           "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": workload_name("rl") + ", device tensors, predict(all trees) + step per iteration"},
+           "kernel_ms_per_step": {k: round(v["ms"] / K, 4) for k, v in prof.items() if isinstance(v, dict) and v["ms"] > 0},
+           "gpu_launches": int(m.get_stats()["kernel_launches"] - l0), "replay": {k: m.get_stats()[k] for k in ("replay_nodes", "replay_items", "nodes_evaluated")}}
+    print(json.dumps(out))
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -232,7 +271,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])   # "rl" is part of WORKLOADS
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-replay", action="store_true", help="exact-arithmetic arg-max only (see DESIGN.md, near-tie replay)")
@@ -241,6 +280,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "c4":
         return bench_predict(args)
+    if args.workload == "rl":
+        return bench_step_api(args)
     c = WORKLOADS[args.workload]
     K, W = max(args.steps, 1), max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -14,6 +14,7 @@
 // SURVEY 8f lists as "next"); everything else here is hand-written.
 #include "engine.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_sort.cuh>
 #include <cfloat>
 
 namespace gb {
@@ -34,10 +35,12 @@ __global__ void transpose_slab_kernel(const float *__restrict__ X, float *__rest
     }
 }
 
-// split_candidate_generator.cpp:216-240: thr[f][b] = sorted[cum_b - 1]
-__global__ void pick_quantiles_kernel(const float *__restrict__ sorted_col, float *__restrict__ thr, int N, int B, int f) {
+// split_candidate_generator.cpp:216-240: thr[f][b] = sorted[cum_b - 1]; blockIdx.y = column inside the sorted slab
+__global__ void pick_quantiles_kernel(const float *__restrict__ sorted_cols, float *__restrict__ thr, int N, int B, int f0) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const float *sorted_col = sorted_cols + (size_t)blockIdx.y * N;
+    const int f = f0 + blockIdx.y;
     int actual = B + 1;
     int spb = N / actual, rem = N % actual;
     long long cum = (long long)(b + 1) * spb + (b + 1 < rem ? b + 1 : rem);
@@ -96,21 +99,43 @@ void compute_thresholds(Model &m, const float *X, int N, int F, cudaStream_t s) 
     if (m.cfg.generator_type == GBRL_B200_GEN_UNIFORM) {
         GB_LAUNCH(uniform_thresholds_kernel, F, 256, 0, s, X, ws.thr.as<float>(), N, F, B);
     } else {
-        // exact order statistics: per-column radix sort of a transposed 32-column slab
+        // exact order statistics of every column: sort a transposed 32-column slab.
+        //   N <= 256K  : one cub::DeviceSegmentedSort call per slab (32 segments) -- a handful of launches per
+        //                slab, which is what matters at RL batch sizes;
+        //   larger N   : one device-wide cub::DeviceRadixSort per column.
+        const bool segmented = N <= 262144;
         ws.colbuf[0].ensure((size_t)32 * N * sizeof(float));
-        ws.colbuf[1].ensure((size_t)N * sizeof(float));
+        ws.colbuf[1].ensure((size_t)(segmented ? 32 : 1) * N * sizeof(float));
         size_t tmp = 0;
-        cub::DeviceRadixSort::SortKeys(nullptr, tmp, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), N, 0, 32, s);
+        if (segmented) {
+            ws.sort_offsets.ensure(33 * sizeof(int));
+            int h_off[33];
+            for (int i = 0; i <= 32; ++i) h_off[i] = i * N;
+            GB_CUDA(cudaMemcpyAsync(ws.sort_offsets.p, h_off, sizeof(h_off), cudaMemcpyHostToDevice, s));
+            GB_CUDA(cudaStreamSynchronize(s));      // h_off is a stack buffer
+            cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), 32 * N, 32,
+                                               ws.sort_offsets.as<int>(), ws.sort_offsets.as<int>() + 1, s);
+        } else {
+            cub::DeviceRadixSort::SortKeys(nullptr, tmp, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), N, 0, 32, s);
+        }
         ws.sort_tmp.ensure(tmp);
         for (int f0 = 0; f0 < F; f0 += 32) {
             int nf = F - f0 < 32 ? F - f0 : 32;
             GB_LAUNCH(transpose_slab_kernel, ceil_div(N, 32), 256, 0, s, X, ws.colbuf[0].as<float>(), N, F, f0, nf);
-            for (int c = 0; c < nf; ++c) {
+            if (segmented) {
                 size_t t2 = tmp;
-                GB_CUDA(cub::DeviceRadixSort::SortKeys(ws.sort_tmp.p, t2, ws.colbuf[0].as<float>() + (size_t)c * N,
-                                                       ws.colbuf[1].as<float>(), N, 0, 32, s));
+                GB_CUDA(cub::DeviceSegmentedSort::SortKeys(ws.sort_tmp.p, t2, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), nf * N, nf,
+                                                           ws.sort_offsets.as<int>(), ws.sort_offsets.as<int>() + 1, s));
                 g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-                GB_LAUNCH(pick_quantiles_kernel, ceil_div(B, 256), 256, 0, s, ws.colbuf[1].as<float>(), ws.thr.as<float>(), N, B, f0 + c);
+                GB_LAUNCH(pick_quantiles_kernel, dim3(ceil_div(B, 256), nf), 256, 0, s, ws.colbuf[1].as<float>(), ws.thr.as<float>(), N, B, f0);
+            } else {
+                for (int c = 0; c < nf; ++c) {
+                    size_t t2 = tmp;
+                    GB_CUDA(cub::DeviceRadixSort::SortKeys(ws.sort_tmp.p, t2, ws.colbuf[0].as<float>() + (size_t)c * N,
+                                                           ws.colbuf[1].as<float>(), N, 0, 32, s));
+                    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
+                    GB_LAUNCH(pick_quantiles_kernel, dim3(ceil_div(B, 256), 1), 256, 0, s, ws.colbuf[1].as<float>(), ws.thr.as<float>(), N, B, f0 + c);
+                }
             }
         }
     }

@@ -97,6 +97,7 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
     DevBuf pair_first, pair_nitems, pl_count, pl_ids, partials;   // histogram pairs (node x local tile) and staged partials
     int max_partials = 0, pl_stride = 0, n_sms = 0;
+    DevBuf sort_offsets;
     DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage, pred_partials;
     NodeArrays na{};
     size_t sort_tmp_bytes = 0;
