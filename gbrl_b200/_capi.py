@@ -22,7 +22,8 @@ class Metadata(C.Structure):
         "input_dim", "output_dim", "policy_dim", "max_depth", "min_data_in_leaf", "n_bins", "par_th",
         "batch_size", "split_score_func", "generator_type", "grow_policy", "verbose", "n_num_features",
         "n_cat_features", "n_trees", "n_leaves", "iteration")] + [(n, C.c_longlong) for n in (
-            "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")] + [("max_noise_ratio", C.c_float)]
+            "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")] + [("max_noise_ratio", C.c_float)] + [
+                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow")]
 
 
 # every symbol include/gbrl_b200.h declares (tests check that the library exports all of them)
@@ -34,7 +35,7 @@ EXPORTS = [
     "gbrl_b200_fit", "gbrl_b200_fit_begin", "gbrl_b200_fit_iterate", "gbrl_b200_fit_end", "gbrl_b200_profile",
     "gbrl_b200_get_profile", "gbrl_b200_predict", "gbrl_b200_get_metadata", "gbrl_b200_get_ensemble",
     "gbrl_b200_set_ensemble", "gbrl_b200_get_candidates", "gbrl_b200_get_root_scores", "gbrl_b200_dist_unique_id",
-    "gbrl_b200_dist_init", "gbrl_b200_dist_shutdown", "gbrl_b200_microbench",
+    "gbrl_b200_dist_init", "gbrl_b200_dist_shutdown", "gbrl_b200_microbench", "gbrl_b200_diag_chain_sums",
 ]
 
 _lib = None
@@ -82,6 +83,7 @@ def lib():
     L.gbrl_b200_dist_init.argtypes = [vp, u8p, C.c_int, C.c_int]
     L.gbrl_b200_dist_shutdown.argtypes = [vp]
     L.gbrl_b200_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.gbrl_b200_diag_chain_sums.argtypes = [fp, C.c_longlong, C.c_int, C.c_int, C.c_int, fp, fp, fp, C.c_int]
     _lib = L
     return L
 

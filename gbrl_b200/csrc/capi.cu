@@ -18,6 +18,8 @@ void dist_unique_id(uint8_t id[128]);
 void dist_init(Model &m, const uint8_t id[128], int rank, int world);
 void dist_shutdown(Model &m);
 double microbench(int which, int iters);
+void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode, const float *host_mean, float *host_partial,
+                     float *host_centered, int impl);
 
 // ---------------------------------------------------------------- DevBuf
 void DevBuf::ensure(size_t n, bool keep, cudaStream_t s) {
@@ -123,6 +125,7 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
     m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
     m.hist_rows = h.stat_hist_rows;
+    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow;
     m.max_noise = __builtin_bit_cast(float, h.stat_max_noise);
 }
 
@@ -574,6 +577,7 @@ int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
     o->n_leaves = m.ens.n_leaves; o->iteration = m.iteration;
     o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
     o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated; o->max_noise_ratio = m.max_noise;
+    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow;
     API_END
 }
 
@@ -677,6 +681,14 @@ int gbrl_b200_dist_shutdown(gbrl_b200_model *h) {
 int gbrl_b200_microbench(int which, int iters, double *result) {
     API_BEGIN
     *result = gb::microbench(which, iters);
+    API_END
+}
+
+int gbrl_b200_diag_chain_sums(const float *mat, long long n_elements, int D, int T, int mode, const float *mean, float *partial,
+                              float *centered, int impl) {
+    API_BEGIN
+    GB_CHECK(D >= 1 && T >= 1 && n_elements >= 0, "diag_chain_sums: bad arguments");
+    gb::diag_chain_sums(mat, n_elements, D, T, mode, mean, partial, centered, impl);
     API_END
 }
 

@@ -13,6 +13,7 @@
 // The reference's float sums are sequential chains; to reproduce their bits each (thread-partition, column)
 // chain is evaluated by one CUDA thread in the same order (no FMA: the engine is compiled with -fmad=false).
 #include "engine.cuh"
+#include "chain.cuh"
 
 namespace gb {
 
@@ -71,6 +72,156 @@ ref_chain_kernel(float *mat, const float *mean, float *partial, long long n_elem
     }
     if (lane < D) partial[(size_t)t * D + lane] = acc0;
     if (lane + 32 < D) partial[(size_t)t * D + lane + 32] = acc1;
+}
+
+
+// ---------------------------------------------------------------- parallel evaluation of the same chains (D <= 4)
+// One 512-thread CTA per reference thread t.  The element range of t is streamed through shared memory in stages of
+// 512*R rows (R = 8 / 4 / 2 rows per lane for D = 1 / 2 / 3-4; elements outside [s, e) are stored as +0, which a
+// float chain ignores).  Per stage: phase A -- every warp summarises its own 32*R-row sub-block for every column
+// chain in the chain's current binade (chain.cuh); phase B -- warp d walks the 16 summaries of column d in order,
+// applying each one if it is valid for the actual running sum and otherwise running that sub-block as a plain
+// sequential float chain.  The result is bit-identical to ref_chain_kernel (and to the reference's loop).
+constexpr int DC_THREADS = 512, DC_WARPS = DC_THREADS / 32;
+
+template <int D>
+__global__ void __launch_bounds__(DC_THREADS)
+dense_chain_kernel(float *mat, const float *mean, float *partial, long long n_elements, int T, int mode) {
+    constexpr int R = D == 1 ? 8 : D == 2 ? 4 : 2;
+    constexpr int STAGE_ROWS = DC_THREADS * R, SUB_ROWS = 32 * R;
+    __shared__ __align__(16) float sg[2][DC_THREADS * 8];
+    __shared__ int4 s_tab[4][DC_WARPS];
+    __shared__ float s_state[4], s_invu[4];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long ept = n_elements / T;
+    const long long s = (long long)t * ept, e = (t == T - 1) ? n_elements : s + ept;
+    const long long base0 = (s / D) * D;                 // stage 0 starts at the row that holds element s
+    constexpr int SE = STAGE_ROWS * D, EPT = R * D;      // elements per stage / per thread
+    const int n_stages = (int)((e - base0 + SE - 1) / SE);
+    float nxt[8];
+    auto load = [&](int st) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < EPT) {
+                const int o = j * DC_THREADS + tid;
+                const long long idx = base0 + (long long)st * SE + o;
+                float v = 0.0f;
+                if (st < n_stages && idx >= s && idx < e) {
+                    const float raw = mat[idx];
+                    if (mode == 1) {
+                        const float c = raw - mean[o % D];
+                        mat[idx] = c;
+                        v = c * c;
+                    } else v = raw;
+                }
+                nxt[j] = v;
+            }
+        }
+    };
+    auto commit = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < EPT) sg[buf][j * DC_THREADS + tid] = nxt[j];
+    };
+    auto lane_vals = [&](int buf, int w, float (&v)[8]) {     // the lane's R rows x D columns of sub-block w
+        const float *p = &sg[buf][(w * SUB_ROWS + lane * R) * D];
+        if (EPT == 8) {
+            const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (j < EPT) ? p[j] : 0.0f;
+        }
+    };
+    if (tid < 4) s_state[tid] = 0.0f;
+    load(0); commit(0);
+    __syncthreads();
+    for (int st = 0; st < n_stages; ++st) {
+        const int buf = st & 1;
+        load(st + 1);
+        {   // phase A
+            float v[8];
+            lane_vals(buf, warp, v);
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                float inv_u, u;
+                const bool ok = seq::epoch_of(s_state[d], inv_u, u);
+                if (tid == 0) s_invu[d] = ok ? inv_u : 0.0f;
+                if (ok) {
+                    float x[R];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) x[r] = v[r * D + d];
+                    const seq::Tab tb = seq::warp_summarize<R>(x, inv_u);
+                    if (lane == 0) s_tab[d][warp] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+                }
+            }
+        }
+        __syncthreads();
+        if (warp < D) {   // phase B: warp d owns column chain d
+            const int d = warp;
+            float acc = s_state[d];
+            const float inv_a = s_invu[d];
+            for (int w = 0; w < DC_WARPS; ++w) {
+                float inv_u, u;
+                bool done = false;
+                if (seq::epoch_of(acc, inv_u, u)) {
+                    seq::Tab tb;
+                    if (inv_u == inv_a) { const int4 q = s_tab[d][w]; tb.a0 = q.x; tb.a1 = q.y; tb.mn = q.z; tb.mx = q.w; }
+                    else {
+                        float v[8], x[R];
+                        lane_vals(buf, w, v);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            float val = v[r * D];
+#pragma unroll
+                            for (int dd = 1; dd < D; ++dd) val = (d == dd) ? v[r * D + dd] : val;
+                            x[r] = val;
+                        }
+                        tb = seq::warp_summarize<R>(x, inv_u);
+                    }
+                    done = seq::apply(tb, acc, inv_u, u);
+                }
+                if (!done) {
+                    const float *p = &sg[buf][(w * SUB_ROWS) * D + d];
+                    for (int r0 = 0; r0 < SUB_ROWS; r0 += 8) {
+                        float q[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) q[j] = p[(r0 + j) * D];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc = acc + q[j];
+                    }
+                }
+            }
+            if (lane == 0) s_state[d] = acc;
+        }
+        commit(buf ^ 1);
+        __syncthreads();
+    }
+    if (tid < D) partial[(size_t)t * D + tid] = s_state[tid];
+}
+
+static void launch_ref_chain(float *mat, const float *mean, float *partial, long long ne, int D, int T, int mode, cudaStream_t s) {
+    if (D == 1) GB_LAUNCH(dense_chain_kernel<1>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
+    else if (D == 2) GB_LAUNCH(dense_chain_kernel<2>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
+    else if (D == 3) GB_LAUNCH(dense_chain_kernel<3>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
+    else if (D == 4) GB_LAUNCH(dense_chain_kernel<4>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
+    else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, mat, mean, partial, ne, D, T, mode);
+}
+
+// test hook: thread-partitioned chain sums of a host matrix through launch_ref_chain (impl 0) or the one-thread-per-
+// chain reference kernel (impl 1)
+void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode, const float *host_mean, float *host_partial,
+                     float *host_centered, int impl) {
+    DevBuf mat, mean, partial;
+    mat.ensure((size_t)(ne > 0 ? ne : 1) * sizeof(float)); mean.ensure((size_t)D * sizeof(float)); partial.ensure((size_t)T * D * sizeof(float));
+    GB_CUDA(cudaMemcpy(mat.p, host_mat, (size_t)ne * sizeof(float), cudaMemcpyHostToDevice));
+    if (host_mean) GB_CUDA(cudaMemcpy(mean.p, host_mean, (size_t)D * sizeof(float), cudaMemcpyHostToDevice));
+    GB_CUDA(cudaMemset(partial.p, 0, (size_t)T * D * sizeof(float)));
+    if (impl == 0) launch_ref_chain(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode, 0);
+    else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, 0, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode);
+    GB_CUDA(cudaDeviceSynchronize());
+    GB_CUDA(cudaMemcpy(host_partial, partial.p, (size_t)T * D * sizeof(float), cudaMemcpyDeviceToHost));
+    if (host_centered) GB_CUDA(cudaMemcpy(host_centered, mat.p, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
 // merge partials in thread order (d = 0..T*D-1, column d % D), then finish
@@ -138,7 +289,7 @@ void column_mean_ref(Model &m, const float *mat, int N, int D, float *out_dev, c
     const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
     ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
     float *partial = ws.lrs.as<float>();
-    GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, const_cast<float *>(mat), nullptr, partial, ne, D, T, 0);
+    launch_ref_chain(const_cast<float *>(mat), nullptr, partial, ne, D, T, 0, s);
     GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, out_dev, D, T, N, 0);
 }
 
@@ -157,9 +308,9 @@ void build_grads(Model &m, const float *grads, int N, cudaStream_t s) {
         const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
         ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
         float *partial = ws.lrs.as<float>(), *mean = partial + (size_t)T * D, *stdv = mean + D;
-        GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, ws.bg.as<float>(), nullptr, partial, ne, D, T, 0);
+        launch_ref_chain(ws.bg.as<float>(), nullptr, partial, ne, D, T, 0, s);
         GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, mean, D, T, N, 0);
-        GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, ws.bg.as<float>(), mean, partial, ne, D, T, 1);
+        launch_ref_chain(ws.bg.as<float>(), mean, partial, ne, D, T, 1, s);
         GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, stdv, D, T, N, 1);
         GB_LAUNCH(divide_and_max_kernel, grid, 256, 0, s, ws.bg.as<float>(), stdv, ctl, ne, D, 1, 0);
     } else if (ne > 0) {

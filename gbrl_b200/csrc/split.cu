@@ -18,6 +18,7 @@
 //      within that noise band of the exact best, both are re-scored by replay_kernel with exactly the
 //      reference's chain of float operations, so the chosen split is the reference's, bit for bit.
 #include "engine.cuh"
+#include "chain.cuh"
 #include <cfloat>
 #include <climits>
 
@@ -716,6 +717,272 @@ __global__ void __launch_bounds__(RP_THREADS) replay_kernel(ReplayParams P, Node
     }
 }
 
+
+// ---------------------------------------------------------------- replay, parallel chains (output_dim <= 4)
+// Same result as replay_kernel, bit for bit, but the float chains are evaluated by the parallel chain evaluator of
+// chain.cuh instead of one dependent FADD per row.  CTA = 512 threads per item, stages of 512*R rows (R = 8 / 4 / 2
+// rows per lane for D = 1 / 2 / 3-4).  Loads are software-pipelined exactly as in replay_kernel (row ids two stages
+// ahead, gathers one stage ahead).  Per stage:
+//   phase A  every warp summarises its own sub-block (32*R rows) for every chain, in the chain's current binade;
+//   phase B  warp c walks the 16 summaries of chain c in order: valid for the actual running sum -> one integer add,
+//            otherwise the sub-block is run as the plain sequential float chain (node.cpp:341-350 order).
+// Chains: PASS 0 -> (side, output dim): per-side sums of build_grads; PASS 1 -> side: the mat_vec_dot_sum chain over
+// (row, col) of g * mean (math_ops.h:432-449).
+template <int DCT> struct ParCfg {
+    static constexpr int R = DCT == 1 ? 8 : DCT == 2 ? 4 : 2;
+    static constexpr int T = 512, NW = 16, STAGE = T * R, SUB = 32 * R, EPL = R * DCT;
+};
+
+template <int DCT, int PASS>
+__device__ __forceinline__ void replay_pass_par(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, float *sg,
+                                                unsigned int *smask, const float *smean, int *s_nright, float *s_state,
+                                                int4 (*s_tab)[16], float *s_invu, int &n_fast, int &n_slow) {
+    using C = ParCfg<DCT>;
+    constexpr int R = C::R, T = C::T, NW = C::NW, STAGE = C::STAGE, SUB = C::SUB, EPL = C::EPL, D = DCT;
+    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    constexpr int KE = PASS == 0 ? R : 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_stages = (n + STAGE - 1) / STAGE;
+    int rows[R], rows_n[R];
+    float xv[R], gpre[R][D];
+    auto load_rows = [&](int st, int *dst) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = st * STAGE + r * T + tid;
+            dst[r] = (st < n_stages && k < n) ? P.order[s0 + k] : -1;
+        }
+    };
+    auto gather = [&](const int *src) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            rows[r] = src[r];
+            xv[r] = (src[r] >= 0 && is_cand) ? P.X[(size_t)src[r] * P.F + f] : -INFINITY;
+            if (src[r] >= 0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) gpre[r][d] = P.bg[(size_t)src[r] * D + d];
+            }
+        }
+    };
+    auto commit = [&](int buf) {
+        float *g = sg + (size_t)buf * STAGE * D;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int slot = r * T + tid;
+            const bool right = rows[r] >= 0 && (xv[r] > tv);                     // node.cpp:339
+            const unsigned int m = __ballot_sync(0xffffffffu, right);
+            if (lane == 0) { smask[buf * (STAGE / 32) + slot / 32] = m; if (PASS == 0 && m) atomicAdd(s_nright, __popc(m)); }
+            if (rows[r] >= 0) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) g[(size_t)slot * D + d] = gpre[r][d];
+            }
+        }
+    };
+    // the lane's R rows x D values of sub-block w (chain order), their side bits and validity bits
+    auto lane_vals = [&](int buf, int w, int cnt, float (&v)[8], unsigned int &mb, unsigned int &vb) {
+        const int rb = w * SUB + lane * R;
+        const float *p = sg + (size_t)buf * STAGE * D + (size_t)rb * D;
+        if (EPL == 8) {
+            const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                if (j < EPL) { const float2 a = *reinterpret_cast<const float2 *>(p + j); v[j] = a.x; v[j + 1] = a.y; }
+                else { v[j] = 0.0f; v[j + 1] = 0.0f; }
+            }
+        }
+        mb = (smask[buf * (STAGE / 32) + (rb >> 5)] >> (rb & 31)) & ((1u << R) - 1u);
+        const int nv = min(max(cnt - rb, 0), R);
+        vb = (1u << nv) - 1u;
+    };
+    auto summarize = [&](int buf, int w, int c, int cnt, float inv_u) -> seq::Tab {
+        float v[8], x[KE];
+        unsigned int mb, vb;
+        lane_vals(buf, w, cnt, v, mb, vb);
+        if (PASS == 0) {
+            const int side = c / D, d = c - side * D;
+            const unsigned int sel = (side ? mb : ~mb) & vb;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float val = v[r * D];
+#pragma unroll
+                for (int dd = 1; dd < D; ++dd) val = (d == dd) ? v[r * D + dd] : val;
+                x[r < KE ? r : 0] = ((sel >> r) & 1u) ? val : 0.0f;
+            }
+        } else {
+            const unsigned int sel = (c ? mb : ~mb) & vb;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = j / D, d = j - r * D;
+                x[j < KE ? j : 0] = (j < EPL && ((sel >> r) & 1u)) ? v[j] * smean[c * D + d] : 0.0f;
+            }
+        }
+        return seq::warp_summarize<KE>(x, inv_u);
+    };
+    // plain sequential float chain over sub-block w (every lane runs the same chain)
+    auto sequential = [&](int buf, int w, int c, int cnt, float acc) -> float {
+        const float *g = sg + (size_t)buf * STAGE * D;
+        const int side = PASS == 0 ? c / D : c, d0 = PASS == 0 ? c - side * D : 0;
+#pragma unroll 1
+        for (int wd = 0; wd < R; ++wd) {
+            const int rbase = w * SUB + wd * 32;
+            const int nv = min(max(cnt - rbase, 0), 32);
+            if (nv == 0) break;
+            const unsigned int bits = smask[buf * (STAGE / 32) + (rbase >> 5)];
+            const unsigned int sel = (side ? bits : ~bits) & (nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u));
+            if (!sel) continue;
+            if (PASS == 0) {
+#pragma unroll
+                for (int t0 = 0; t0 < 32; t0 += 8) {
+                    float q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) q[j] = g[(size_t)(rbase + t0 + j) * D + d0];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if ((sel >> (t0 + j)) & 1u) acc = acc + q[j];
+                }
+            } else {
+#pragma unroll
+                for (int t0 = 0; t0 < 32; t0 += 4) {
+                    float q[4][D];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) q[j][d] = g[(size_t)(rbase + t0 + j) * D + d] * smean[c * D + d];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((sel >> (t0 + j)) & 1u) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) acc = acc + q[j][d];
+                        }
+                }
+            }
+        }
+        return acc;
+    };
+
+    if (tid < 8) s_state[tid] = 0.0f;
+    {
+        int r0[R];
+        load_rows(0, r0);
+        load_rows(1, rows_n);
+        gather(r0);
+        commit(0);
+    }
+    __syncthreads();
+    for (int st = 0; st < n_stages; ++st) {
+        const int buf = st & 1;
+        const int cnt = min(STAGE, n - st * STAGE);
+        int rows_nn[R];
+        if (st + 1 < n_stages) gather(rows_n);
+        load_rows(st + 2, rows_nn);
+        // ---- phase A
+        if (warp * SUB < cnt) {
+#pragma unroll 1
+            for (int c = 0; c < NCH; ++c) {
+                float inv_u, u;
+                const bool ok = seq::epoch_of(s_state[c], inv_u, u);
+                if (tid == 0) s_invu[c] = ok ? inv_u : 0.0f;
+                if (ok) {
+                    const seq::Tab tb = summarize(buf, warp, c, cnt, inv_u);
+                    if (lane == 0) s_tab[c][warp] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase B
+        if (warp < NCH) {
+            const int c = warp;
+            float acc = s_state[c];
+            const float inv_a = s_invu[c];
+            const int nsub = (cnt + SUB - 1) / SUB;
+#pragma unroll 1
+            for (int w = 0; w < nsub; ++w) {
+                float inv_u, u;
+                bool done = false;
+                if (seq::epoch_of(acc, inv_u, u)) {
+                    seq::Tab tb;
+                    if (inv_u == inv_a) { const int4 q = s_tab[c][w]; tb.a0 = q.x; tb.a1 = q.y; tb.mn = q.z; tb.mx = q.w; }
+                    else tb = summarize(buf, w, c, cnt, inv_u);
+                    done = seq::apply(tb, acc, inv_u, u);
+                }
+                if (done) ++n_fast;
+                else { acc = sequential(buf, w, c, cnt, acc); ++n_slow; }
+            }
+            if (lane == 0) s_state[c] = acc;
+        }
+        if (st + 1 < n_stages) commit(buf ^ 1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) rows_n[r] = rows_nn[r];
+        __syncthreads();
+    }
+}
+
+template <int DCT>
+__global__ void __launch_bounds__(512) replay_par_kernel(ReplayParams P, NodeArrays na, Ctl *ctl_stats) {
+    using C = ParCfg<DCT>;
+    constexpr int D = DCT, STAGE = C::STAGE;
+    __shared__ __align__(16) float sg[2 * STAGE * D];
+    __shared__ unsigned int smask[2 * (STAGE / 32)];
+    __shared__ float smean[2 * D];
+    __shared__ float s_state[8], s_invu[8];
+    __shared__ int4 s_tab[8][16];
+    __shared__ int s_nright;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = P.ctl->n_replay;
+    int n_fast = 0, n_slow = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const ReplayItem item = P.items[it];
+        const int h = item.node, cand = item.cand;
+        const int s0 = na.seg_start[h], n = na.seg_len[h];
+        const int f = cand >= 0 ? cand / P.B : 0;
+        const float tv = cand >= 0 ? P.thr[cand] : INFINITY;
+        if (threadIdx.x == 0) s_nright = 0;
+        __syncthreads();
+        replay_pass_par<DCT, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, &s_nright, s_state, s_tab, s_invu, n_fast, n_slow);
+        const int nR = s_nright;   // all ballots are committed before the last barrier of the pass
+        const int nL = n - nR;
+        const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
+        const float lcf = (float)nL, rcf = (float)nR;
+        float ln = 0.0f, rn = 0.0f;
+        if (n == 0 && threadIdx.x < 8) s_state[threadIdx.x] = 0.0f;   // no stage ran
+        __syncthreads();
+        if (warp == 0) {
+            float lrec, rrec;
+            if (cand >= 0) { lrec = nL > 0 ? 1.0f / lcf : 0.0f; rrec = nR > 0 ? 1.0f / rcf : 0.0f; }
+            else { lrec = 1.0f / lcf; rrec = 0.0f; }   // parent: n_samples_recip = 1/n (split_candidate_generator.cpp:265,296)
+            if (lane < D) { smean[lane] = s_state[lane] * lrec; smean[D + lane] = s_state[D + lane] * rrec; }
+            __syncwarp();
+            for (int d = 0; d < D; ++d) { ln = ln + smean[d] * smean[d]; rn = rn + smean[D + d] * smean[D + d]; }  // squared_norm
+        }
+        __syncthreads();
+        float result = 0.0f;
+        if (P.score_func == GBRL_B200_SCORE_L2) {
+            result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
+        } else {
+            replay_pass_par<DCT, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, &s_nright, s_state, s_tab, s_invu, n_fast, n_slow);
+            if (n == 0 && threadIdx.x < 8) s_state[threadIdx.x] = 0.0f;
+            __syncthreads();
+            const float fnum = s_state[0], tnum = s_state[1];
+            if (cand >= 0) {
+                const float num = tnum + fnum;
+                const float den = rn * rcf + ln * lcf;
+                result = (den == 0.0f) ? 0.0f : num / sqrtf(den);
+            } else {
+                const float den = ln * lcf;
+                result = (n == 0 || den == 0.0f) ? 0.0f : fnum / sqrtf(den);
+            }
+        }
+        if (invalid) result = -INFINITY;
+        if (threadIdx.x == 0) P.out[it] = result;
+        __syncthreads();
+    }
+    if (lane == 0 && warp < 8 && (n_fast | n_slow)) {
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_fast, (unsigned long long)n_fast);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_slow, (unsigned long long)n_slow);
+    }
+}
+
 // ---------------------------------------------------------------- decisions
 struct DecideParams {
     int level, nT, F, B, D, C, max_depth, nn;
@@ -915,14 +1182,19 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         // rows per thread per stage: 8 (1024-row stages) for D == 1 down to 1 for wide outputs, so that a stage's
         // gradients fit in registers while they are in flight and two stages fit in shared memory
         const int D = ws.D;
-        const int rpt = D <= 1 ? 8 : D <= 2 ? 4 : D <= 4 ? 2 : 1;
-        const int T = D <= 4 ? 512 : 128;
-        const size_t smem = ((size_t)2 * T * rpt * D + 2 * D) * sizeof(float) + (size_t)2 * (T * rpt / 32) * sizeof(unsigned int);
-        if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(replay_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (rpt == 8) GB_LAUNCH((replay_kernel<8, 512>), 148 * 4, 512, smem, s, R, ws.na);
-        else if (rpt == 4) GB_LAUNCH((replay_kernel<4, 512>), 148 * 4, 512, smem, s, R, ws.na);
-        else if (rpt == 2) GB_LAUNCH((replay_kernel<2, 512>), 148 * 4, 512, smem, s, R, ws.na);
-        else GB_LAUNCH((replay_kernel<1, 128>), 148 * 4, 128, smem, s, R, ws.na);
+        if (D <= 4) {
+            // bit-exact parallel chains (chain.cuh)
+            if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), 148 * 2, 512, 0, s, R, ws.na, ctl);
+            else if (D == 2) GB_LAUNCH((replay_par_kernel<2>), 148 * 2, 512, 0, s, R, ws.na, ctl);
+            else if (D == 3) GB_LAUNCH((replay_par_kernel<3>), 148 * 2, 512, 0, s, R, ws.na, ctl);
+            else GB_LAUNCH((replay_par_kernel<4>), 148 * 2, 512, 0, s, R, ws.na, ctl);
+        } else {
+            // wide outputs: one lane per output dimension runs its chain sequentially (parallel over D instead of over rows)
+            const int T = 128;
+            const size_t smem = ((size_t)2 * T * D + 2 * D) * sizeof(float) + (size_t)2 * (T / 32) * sizeof(unsigned int);
+            if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(replay_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GB_LAUNCH((replay_kernel<1, 128>), 148 * 4, 128, smem, s, R, ws.na);
+        }
     }
 }
 
