@@ -435,7 +435,9 @@ def main():
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
            "kernel_ms_per_step": breakdown, "final_loss": loss, "exact_tier_only": exact_only,
            "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
-                      "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"]}}
+                      "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"],
+                      "chain_blocks_fast": stats["chain_blocks_fast"], "chain_blocks_slow": stats["chain_blocks_slow"],
+                      "chain_lanes_seq": stats["chain_lanes_seq"]}}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

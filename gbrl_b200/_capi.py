@@ -23,7 +23,7 @@ class Metadata(C.Structure):
         "batch_size", "split_score_func", "generator_type", "grow_policy", "verbose", "n_num_features",
         "n_cat_features", "n_trees", "n_leaves", "iteration")] + [(n, C.c_longlong) for n in (
             "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")] + [("max_noise_ratio", C.c_float)] + [
-                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow")]
+                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow", "chain_lanes_seq")]
 
 
 # every symbol include/gbrl_b200.h declares (tests check that the library exports all of them)
@@ -83,7 +83,7 @@ def lib():
     L.gbrl_b200_dist_init.argtypes = [vp, u8p, C.c_int, C.c_int]
     L.gbrl_b200_dist_shutdown.argtypes = [vp]
     L.gbrl_b200_microbench.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
-    L.gbrl_b200_diag_chain_sums.argtypes = [fp, C.c_longlong, C.c_int, C.c_int, C.c_int, fp, fp, fp, C.c_int]
+    L.gbrl_b200_diag_chain_sums.argtypes = [fp, C.c_longlong, C.c_int, C.c_int, C.c_int, fp, fp, fp, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 

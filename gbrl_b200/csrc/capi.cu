@@ -19,7 +19,7 @@ void dist_init(Model &m, const uint8_t id[128], int rank, int world);
 void dist_shutdown(Model &m);
 double microbench(int which, int iters);
 void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode, const float *host_mean, float *host_partial,
-                     float *host_centered, int impl);
+                     float *host_centered, int impl, double *info);
 
 // ---------------------------------------------------------------- DevBuf
 void DevBuf::ensure(size_t n, bool keep, cudaStream_t s) {
@@ -94,6 +94,14 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     if ((size_t)ws.replay_cap < 4 * ((size_t)1 << md)) ws.replay_cap = 4 << md;
     ws.replay.ensure((size_t)ws.replay_cap * (sizeof(ReplayItem) + sizeof(int)));
     ws.replay_scores.ensure((size_t)ws.replay_cap * sizeof(float));
+    if (m.cfg.tie_replay && D <= 4) {
+        // replay streams (split.cu): planes for 64 full-size candidates, i.e. all items of a level unless the near-tie
+        // band is unusually crowded (those items are gathered directly by their chain CTA)
+        ws.rgrad.ensure(n1 * D * sizeof(float));
+        ws.rbits_words = (long long)((n1 + 255) / 256) * 8 * 64 + 4096;
+        ws.rbits.ensure((size_t)ws.rbits_words * sizeof(unsigned int));
+        ws.rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
+    }
     // node arrays carved from one allocation
     const size_t MN = ws.MAXN;
     const size_t bytes = MN * D * sizeof(long long) + MN * 10 * sizeof(int) + MN * 4 * sizeof(float);
@@ -125,7 +133,7 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
     m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
     m.hist_rows = h.stat_hist_rows;
-    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow;
+    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow; m.chain_seq = h.stat_chain_seq;
     m.max_noise = __builtin_bit_cast(float, h.stat_max_noise);
 }
 
@@ -577,7 +585,7 @@ int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
     o->n_leaves = m.ens.n_leaves; o->iteration = m.iteration;
     o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
     o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated; o->max_noise_ratio = m.max_noise;
-    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow;
+    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow; o->chain_lanes_seq = m.chain_seq;
     API_END
 }
 
@@ -685,10 +693,10 @@ int gbrl_b200_microbench(int which, int iters, double *result) {
 }
 
 int gbrl_b200_diag_chain_sums(const float *mat, long long n_elements, int D, int T, int mode, const float *mean, float *partial,
-                              float *centered, int impl) {
+                              float *centered, int impl, double *info) {
     API_BEGIN
     GB_CHECK(D >= 1 && T >= 1 && n_elements >= 0, "diag_chain_sums: bad arguments");
-    gb::diag_chain_sums(mat, n_elements, D, T, mode, mean, partial, centered, impl);
+    gb::diag_chain_sums(mat, n_elements, D, T, mode, mean, partial, centered, impl, info);
     API_END
 }
 

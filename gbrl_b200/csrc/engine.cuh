@@ -63,7 +63,7 @@ struct Ctl {
     int bg_nonfinite;        // some build_grad is NaN/inf: the reference's scores are all NaN -> no split
     unsigned int stat_max_noise;   // float bits: max over replayed candidates of |replayed - exact| / (2^-24 sqrt(n) |score|)
     long long stat_replay_items, stat_replay_nodes, stat_nodes_evaluated, stat_replay_overflow, stat_hist_rows;
-    long long stat_chain_fast, stat_chain_slow;   // replay sub-blocks: parallel evaluator / sequential fallback
+    long long stat_chain_fast, stat_chain_slow, stat_chain_seq;   // replay sub-blocks: applied from summary / advanced piecewise; lanes run sequentially
 };
 
 // per-node arrays, heap indexed, MAXN = 2^(max_depth+1)-1 entries each
@@ -96,6 +96,8 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     int row_offset = 0;             // first row of the current mini-batch inside the code matrix
     DevBuf codes, thr, thrT, bg, order[2], nid, rflag, rscan, chunk_sums, hist[2], scores, cand_flags;
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
+    DevBuf rgrad, rbits, rmeta;          // replay streams: order-space build_grads, side-bit planes, per-item offsets / modes / counts
+    long long rbits_words = 0;
     DevBuf pair_first, pair_nitems, pl_count, pl_ids, partials;   // histogram pairs (node x local tile) and staged partials
     int max_partials = 0, pl_stride = 0, n_sms = 0;
     DevBuf sort_offsets;
@@ -130,7 +132,7 @@ struct Model {
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
     // statistics
-    long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0, chain_fast = 0, chain_slow = 0;
+    long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0, chain_fast = 0, chain_slow = 0, chain_seq = 0;
     bool have_candidates = false;
     long long hist_rows = 0;          // rows scanned by the histogram kernel (read back from Ctl)
     float max_noise = 0.0f;           // see Ctl::stat_max_noise

@@ -85,21 +85,20 @@ ref_chain_kernel(float *mat, const float *mean, float *partial, long long n_elem
 constexpr int DC_THREADS = 512, DC_WARPS = DC_THREADS / 32;
 
 template <int D>
-__global__ void __launch_bounds__(DC_THREADS)
-dense_chain_kernel(float *mat, const float *mean, float *partial, long long n_elements, int T, int mode) {
+__global__ void __launch_bounds__(DC_THREADS, 1)
+dense_chain_kernel(float *mat, const float *mean, float *partial, long long n_elements, int T, int mode, long long *stats) {
     constexpr int R = D == 1 ? 8 : D == 2 ? 4 : 2;
     constexpr int STAGE_ROWS = DC_THREADS * R, SUB_ROWS = 32 * R;
-    __shared__ __align__(16) float sg[2][DC_THREADS * 8];
-    __shared__ int4 s_tab[4][DC_WARPS];
-    __shared__ float s_state[4], s_invu[4];
+    constexpr int SE = STAGE_ROWS * D, EPT = R * D;      // elements per stage / per thread
+    extern __shared__ __align__(16) float sg[];          // 3 stage buffers of DC_THREADS * 8 floats
+    __shared__ seq::StageShared sh;
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long ept = n_elements / T;
     const long long s = (long long)t * ept, e = (t == T - 1) ? n_elements : s + ept;
     const long long base0 = (s / D) * D;                 // stage 0 starts at the row that holds element s
-    constexpr int SE = STAGE_ROWS * D, EPT = R * D;      // elements per stage / per thread
     const int n_stages = (int)((e - base0 + SE - 1) / SE);
-    float nxt[8];
-    auto load = [&](int st) {
+    float nx1[8], nx2[8];                                // two stages in flight
+    auto load = [&](int st, float (&dst)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (j < EPT) {
@@ -114,114 +113,107 @@ dense_chain_kernel(float *mat, const float *mean, float *partial, long long n_el
                         v = c * c;
                     } else v = raw;
                 }
-                nxt[j] = v;
+                dst[j] = v;
             }
         }
     };
-    auto commit = [&](int buf) {
+    auto commit = [&](int b, const float (&src)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < EPT) sg[buf][j * DC_THREADS + tid] = nxt[j];
+            if (j < EPT) sg[b * (DC_THREADS * 8) + j * DC_THREADS + tid] = src[j];
     };
-    auto lane_vals = [&](int buf, int w, float (&v)[8]) {     // the lane's R rows x D columns of sub-block w
-        const float *p = &sg[buf][(w * SUB_ROWS + lane * R) * D];
+    // the lane's R consecutive elements of column chain c in sub-block w of stage buffer b
+    auto load_x = [&](int b, int c, int w, float (&x)[R]) {
+        const float *p = &sg[b * (DC_THREADS * 8) + (w * SUB_ROWS + lane * R) * D];
+        float v[8];
         if (EPT == 8) {
-            const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            const float4 a = *reinterpret_cast<const float4 *>(p), q = *reinterpret_cast<const float4 *>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = (j < EPT) ? p[j] : 0.0f;
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float val = v[r * D];
+#pragma unroll
+            for (int dd = 1; dd < D; ++dd) val = (c == dd) ? v[r * D + dd] : val;
+            x[r] = val;
+        }
     };
-    if (tid < 4) s_state[tid] = 0.0f;
-    load(0); commit(0);
+    int n_fast = 0, n_adv = 0, n_seq = 0;
+    seq::pipe_init(sh);
+    load(0, nx1); commit(0, nx1);
+    load(1, nx1); commit(1, nx1);
+    load(2, nx1); load(3, nx2);
     __syncthreads();
+    int bc = 0;                                          // buffer of the current stage (st % 3)
     for (int st = 0; st < n_stages; ++st) {
-        const int buf = st & 1;
-        load(st + 1);
-        {   // phase A
-            float v[8];
-            lane_vals(buf, warp, v);
+        const int bn = bc == 2 ? 0 : bc + 1, bf = bn == 2 ? 0 : bn + 1;
+        auto lc = [&](int c, int w, float (&x)[R]) { load_x(bc, c, w, x); };
+        auto ln = [&](int c, int w, float (&x)[R]) { load_x(bn, c, w, x); };
+        seq::run_stage_pipe<R>(sh, D, st & 1, DC_WARPS, lc, st + 1 < n_stages ? DC_WARPS : 0, ln, n_fast, n_adv, n_seq);
+        commit(bf, nx1);                                 // stage st + 2 (its buffer held stage st - 1)
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                float inv_u, u;
-                const bool ok = seq::epoch_of(s_state[d], inv_u, u);
-                if (tid == 0) s_invu[d] = ok ? inv_u : 0.0f;
-                if (ok) {
-                    float x[R];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) x[r] = v[r * D + d];
-                    const seq::Tab tb = seq::warp_summarize<R>(x, inv_u);
-                    if (lane == 0) s_tab[d][warp] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
-                }
-            }
-        }
-        __syncthreads();
-        if (warp < D) {   // phase B: warp d owns column chain d
-            const int d = warp;
-            float acc = s_state[d];
-            const float inv_a = s_invu[d];
-            for (int w = 0; w < DC_WARPS; ++w) {
-                float inv_u, u;
-                bool done = false;
-                if (seq::epoch_of(acc, inv_u, u)) {
-                    seq::Tab tb;
-                    if (inv_u == inv_a) { const int4 q = s_tab[d][w]; tb.a0 = q.x; tb.a1 = q.y; tb.mn = q.z; tb.mx = q.w; }
-                    else {
-                        float v[8], x[R];
-                        lane_vals(buf, w, v);
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            float val = v[r * D];
-#pragma unroll
-                            for (int dd = 1; dd < D; ++dd) val = (d == dd) ? v[r * D + dd] : val;
-                            x[r] = val;
-                        }
-                        tb = seq::warp_summarize<R>(x, inv_u);
-                    }
-                    done = seq::apply(tb, acc, inv_u, u);
-                }
-                if (!done) {
-                    const float *p = &sg[buf][(w * SUB_ROWS) * D + d];
-                    for (int r0 = 0; r0 < SUB_ROWS; r0 += 8) {
-                        float q[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) q[j] = p[(r0 + j) * D];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc = acc + q[j];
-                    }
-                }
-            }
-            if (lane == 0) s_state[d] = acc;
-        }
-        commit(buf ^ 1);
+        for (int j = 0; j < 8; ++j) nx1[j] = nx2[j];
+        load(st + 4, nx2);
+        bc = bn;
         __syncthreads();
     }
-    if (tid < D) partial[(size_t)t * D + tid] = s_state[tid];
+    if (tid < D) partial[(size_t)t * D + tid] = sh.state[tid];
+    if (stats && lane == 0 && warp < D) {
+        atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_fast);
+        atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_adv);
+        atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_seq);
+    }
 }
 
-static void launch_ref_chain(float *mat, const float *mean, float *partial, long long ne, int D, int T, int mode, cudaStream_t s) {
-    if (D == 1) GB_LAUNCH(dense_chain_kernel<1>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
-    else if (D == 2) GB_LAUNCH(dense_chain_kernel<2>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
-    else if (D == 3) GB_LAUNCH(dense_chain_kernel<3>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
-    else if (D == 4) GB_LAUNCH(dense_chain_kernel<4>, T, DC_THREADS, 0, s, mat, mean, partial, ne, T, mode);
+constexpr size_t DC_SMEM = (size_t)3 * DC_THREADS * 8 * sizeof(float);
+
+template <int D>
+static void launch_dense(float *mat, const float *mean, float *partial, long long ne, int T, int mode, cudaStream_t s, long long *stats) {
+    static bool attr = false;
+    if (!attr) { GB_CUDA(cudaFuncSetAttribute(dense_chain_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM)); attr = true; }
+    GB_LAUNCH(dense_chain_kernel<D>, T, DC_THREADS, DC_SMEM, s, mat, mean, partial, ne, T, mode, stats);
+}
+
+static void launch_ref_chain(float *mat, const float *mean, float *partial, long long ne, int D, int T, int mode, cudaStream_t s,
+                             long long *stats = nullptr) {
+    if (D == 1) launch_dense<1>(mat, mean, partial, ne, T, mode, s, stats);
+    else if (D == 2) launch_dense<2>(mat, mean, partial, ne, T, mode, s, stats);
+    else if (D == 3) launch_dense<3>(mat, mean, partial, ne, T, mode, s, stats);
+    else if (D == 4) launch_dense<4>(mat, mean, partial, ne, T, mode, s, stats);
     else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, mat, mean, partial, ne, D, T, mode);
 }
 
 // test hook: thread-partitioned chain sums of a host matrix through launch_ref_chain (impl 0) or the one-thread-per-
 // chain reference kernel (impl 1)
 void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode, const float *host_mean, float *host_partial,
-                     float *host_centered, int impl) {
-    DevBuf mat, mean, partial;
+                     float *host_centered, int impl, double *info /* [4]: kernel ms, blocks fast, blocks advanced, lanes sequential */) {
+    DevBuf mat, mean, partial, stats;
     mat.ensure((size_t)(ne > 0 ? ne : 1) * sizeof(float)); mean.ensure((size_t)D * sizeof(float)); partial.ensure((size_t)T * D * sizeof(float));
+    stats.ensure(4 * sizeof(long long), true);
     GB_CUDA(cudaMemcpy(mat.p, host_mat, (size_t)ne * sizeof(float), cudaMemcpyHostToDevice));
     if (host_mean) GB_CUDA(cudaMemcpy(mean.p, host_mean, (size_t)D * sizeof(float), cudaMemcpyHostToDevice));
     GB_CUDA(cudaMemset(partial.p, 0, (size_t)T * D * sizeof(float)));
-    if (impl == 0) launch_ref_chain(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode, 0);
-    else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, 0, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode);
+    cudaEvent_t e0, e1;
+    GB_CUDA(cudaEventCreate(&e0)); GB_CUDA(cudaEventCreate(&e1));
     GB_CUDA(cudaDeviceSynchronize());
+    GB_CUDA(cudaEventRecord(e0, 0));
+    if (impl == 0) launch_ref_chain(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode, 0, stats.as<long long>());
+    else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, 0, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode);
+    GB_CUDA(cudaEventRecord(e1, 0));
+    GB_CUDA(cudaDeviceSynchronize());
+    float ms = 0.0f;
+    GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     GB_CUDA(cudaMemcpy(host_partial, partial.p, (size_t)T * D * sizeof(float), cudaMemcpyDeviceToHost));
     if (host_centered) GB_CUDA(cudaMemcpy(host_centered, mat.p, (size_t)ne * sizeof(float), cudaMemcpyDeviceToHost));
+    if (info) {
+        long long h[4];
+        GB_CUDA(cudaMemcpy(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost));
+        info[0] = ms; info[1] = (double)h[0]; info[2] = (double)h[1]; info[3] = (double)h[2];
+    }
 }
 
 // merge partials in thread order (d = 0..T*D-1, column d % D), then finish

@@ -308,6 +308,8 @@ __global__ void __launch_bounds__(1024) select_greedy_kernel(SelectParams P, Nod
         if (beg + n_items > P.replay_cap) {
             atomicAdd(&P.ctl->replay_overflow, 1);
             s_begin = -1;
+            // the range was handed out all the same: make its in-bounds part harmless (parent items of this node)
+            for (int i = beg; i < P.replay_cap && i < beg + n_items; ++i) { P.replay[i].node = h; P.replay[i].cand = -1; }
         } else {
             s_begin = beg;
             na.rep_begin[h] = beg; na.rep_count[h] = n_items; na.band[h] = band;
@@ -735,8 +737,8 @@ template <int DCT> struct ParCfg {
 
 template <int DCT, int PASS>
 __device__ __forceinline__ void replay_pass_par(const ReplayParams &P, int s0, int n, int f, float tv, bool is_cand, float *sg,
-                                                unsigned int *smask, const float *smean, int *s_nright, float *s_state,
-                                                int4 (*s_tab)[16], float *s_invu, int &n_fast, int &n_slow) {
+                                                unsigned int *smask, const float *smean, int *s_nright, seq::StageShared &sh,
+                                                int &n_fast, int &n_slow, int &n_seq) {
     using C = ParCfg<DCT>;
     constexpr int R = C::R, T = C::T, NW = C::NW, STAGE = C::STAGE, SUB = C::SUB, EPL = C::EPL, D = DCT;
     constexpr int NCH = PASS == 0 ? 2 * D : 2;
@@ -795,8 +797,9 @@ __device__ __forceinline__ void replay_pass_par(const ReplayParams &P, int s0, i
         const int nv = min(max(cnt - rb, 0), R);
         vb = (1u << nv) - 1u;
     };
-    auto summarize = [&](int buf, int w, int c, int cnt, float inv_u) -> seq::Tab {
-        float v[8], x[KE];
+    // the lane's KE consecutive elements of chain c in sub-block w (0 for rows of the other side / past the end)
+    auto load_x = [&](int buf, int w, int c, int cnt, float (&x)[KE]) {
+        float v[8];
         unsigned int mb, vb;
         lane_vals(buf, w, cnt, v, mb, vb);
         if (PASS == 0) {
@@ -817,51 +820,9 @@ __device__ __forceinline__ void replay_pass_par(const ReplayParams &P, int s0, i
                 x[j < KE ? j : 0] = (j < EPL && ((sel >> r) & 1u)) ? v[j] * smean[c * D + d] : 0.0f;
             }
         }
-        return seq::warp_summarize<KE>(x, inv_u);
-    };
-    // plain sequential float chain over sub-block w (every lane runs the same chain)
-    auto sequential = [&](int buf, int w, int c, int cnt, float acc) -> float {
-        const float *g = sg + (size_t)buf * STAGE * D;
-        const int side = PASS == 0 ? c / D : c, d0 = PASS == 0 ? c - side * D : 0;
-#pragma unroll 1
-        for (int wd = 0; wd < R; ++wd) {
-            const int rbase = w * SUB + wd * 32;
-            const int nv = min(max(cnt - rbase, 0), 32);
-            if (nv == 0) break;
-            const unsigned int bits = smask[buf * (STAGE / 32) + (rbase >> 5)];
-            const unsigned int sel = (side ? bits : ~bits) & (nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u));
-            if (!sel) continue;
-            if (PASS == 0) {
-#pragma unroll
-                for (int t0 = 0; t0 < 32; t0 += 8) {
-                    float q[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) q[j] = g[(size_t)(rbase + t0 + j) * D + d0];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if ((sel >> (t0 + j)) & 1u) acc = acc + q[j];
-                }
-            } else {
-#pragma unroll
-                for (int t0 = 0; t0 < 32; t0 += 4) {
-                    float q[4][D];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int d = 0; d < D; ++d) q[j][d] = g[(size_t)(rbase + t0 + j) * D + d] * smean[c * D + d];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if ((sel >> (t0 + j)) & 1u) {
-#pragma unroll
-                            for (int d = 0; d < D; ++d) acc = acc + q[j][d];
-                        }
-                }
-            }
-        }
-        return acc;
     };
 
-    if (tid < 8) s_state[tid] = 0.0f;
+    if (tid < 8) sh.state[tid] = 0.0f;
     {
         int r0[R];
         load_rows(0, r0);
@@ -876,41 +837,8 @@ __device__ __forceinline__ void replay_pass_par(const ReplayParams &P, int s0, i
         int rows_nn[R];
         if (st + 1 < n_stages) gather(rows_n);
         load_rows(st + 2, rows_nn);
-        // ---- phase A
-        if (warp * SUB < cnt) {
-#pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
-                float inv_u, u;
-                const bool ok = seq::epoch_of(s_state[c], inv_u, u);
-                if (tid == 0) s_invu[c] = ok ? inv_u : 0.0f;
-                if (ok) {
-                    const seq::Tab tb = summarize(buf, warp, c, cnt, inv_u);
-                    if (lane == 0) s_tab[c][warp] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
-                }
-            }
-        }
-        __syncthreads();
-        // ---- phase B
-        if (warp < NCH) {
-            const int c = warp;
-            float acc = s_state[c];
-            const float inv_a = s_invu[c];
-            const int nsub = (cnt + SUB - 1) / SUB;
-#pragma unroll 1
-            for (int w = 0; w < nsub; ++w) {
-                float inv_u, u;
-                bool done = false;
-                if (seq::epoch_of(acc, inv_u, u)) {
-                    seq::Tab tb;
-                    if (inv_u == inv_a) { const int4 q = s_tab[c][w]; tb.a0 = q.x; tb.a1 = q.y; tb.mn = q.z; tb.mx = q.w; }
-                    else tb = summarize(buf, w, c, cnt, inv_u);
-                    done = seq::apply(tb, acc, inv_u, u);
-                }
-                if (done) ++n_fast;
-                else { acc = sequential(buf, w, c, cnt, acc); ++n_slow; }
-            }
-            if (lane == 0) s_state[c] = acc;
-        }
+        auto lx = [&](int c, int w, float (&x)[KE]) { load_x(buf, w, c, cnt, x); };
+        seq::run_stage<KE>(sh, NCH, (cnt + SUB - 1) / SUB, lx, n_fast, n_slow, n_seq);   // ends with a barrier
         if (st + 1 < n_stages) commit(buf ^ 1);
 #pragma unroll
         for (int r = 0; r < R; ++r) rows_n[r] = rows_nn[r];
@@ -919,19 +847,19 @@ __device__ __forceinline__ void replay_pass_par(const ReplayParams &P, int s0, i
 }
 
 template <int DCT>
-__global__ void __launch_bounds__(512) replay_par_kernel(ReplayParams P, NodeArrays na, Ctl *ctl_stats) {
+__global__ void __launch_bounds__(512, 1) replay_par_kernel(ReplayParams P, NodeArrays na, Ctl *ctl_stats, const int *mode, int replay_cap) {
     using C = ParCfg<DCT>;
     constexpr int D = DCT, STAGE = C::STAGE;
     __shared__ __align__(16) float sg[2 * STAGE * D];
     __shared__ unsigned int smask[2 * (STAGE / 32)];
     __shared__ float smean[2 * D];
-    __shared__ float s_state[8], s_invu[8];
-    __shared__ int4 s_tab[8][16];
+    __shared__ seq::StageShared sh;
     __shared__ int s_nright;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_items = P.ctl->n_replay;
-    int n_fast = 0, n_slow = 0;
+    const int n_items = min(P.ctl->n_replay, replay_cap);
+    int n_fast = 0, n_slow = 0, n_seq = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        if (mode != nullptr && mode[it] != 2) continue;          // streamed by replay_stream_kernel
         const ReplayItem item = P.items[it];
         const int h = item.node, cand = item.cand;
         const int s0 = na.seg_start[h], n = na.seg_len[h];
@@ -939,19 +867,18 @@ __global__ void __launch_bounds__(512) replay_par_kernel(ReplayParams P, NodeArr
         const float tv = cand >= 0 ? P.thr[cand] : INFINITY;
         if (threadIdx.x == 0) s_nright = 0;
         __syncthreads();
-        replay_pass_par<DCT, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, &s_nright, s_state, s_tab, s_invu, n_fast, n_slow);
+        replay_pass_par<DCT, 0>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, &s_nright, sh, n_fast, n_slow, n_seq);
         const int nR = s_nright;   // all ballots are committed before the last barrier of the pass
         const int nL = n - nR;
         const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
         const float lcf = (float)nL, rcf = (float)nR;
         float ln = 0.0f, rn = 0.0f;
-        if (n == 0 && threadIdx.x < 8) s_state[threadIdx.x] = 0.0f;   // no stage ran
         __syncthreads();
         if (warp == 0) {
             float lrec, rrec;
             if (cand >= 0) { lrec = nL > 0 ? 1.0f / lcf : 0.0f; rrec = nR > 0 ? 1.0f / rcf : 0.0f; }
             else { lrec = 1.0f / lcf; rrec = 0.0f; }   // parent: n_samples_recip = 1/n (split_candidate_generator.cpp:265,296)
-            if (lane < D) { smean[lane] = s_state[lane] * lrec; smean[D + lane] = s_state[D + lane] * rrec; }
+            if (lane < D) { smean[lane] = sh.state[lane] * lrec; smean[D + lane] = sh.state[D + lane] * rrec; }
             __syncwarp();
             for (int d = 0; d < D; ++d) { ln = ln + smean[d] * smean[d]; rn = rn + smean[D + d] * smean[D + d]; }  // squared_norm
         }
@@ -960,10 +887,9 @@ __global__ void __launch_bounds__(512) replay_par_kernel(ReplayParams P, NodeArr
         if (P.score_func == GBRL_B200_SCORE_L2) {
             result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
         } else {
-            replay_pass_par<DCT, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, &s_nright, s_state, s_tab, s_invu, n_fast, n_slow);
-            if (n == 0 && threadIdx.x < 8) s_state[threadIdx.x] = 0.0f;
+            replay_pass_par<DCT, 1>(P, s0, n, f, tv, cand >= 0, sg, smask, smean, &s_nright, sh, n_fast, n_slow, n_seq);
             __syncthreads();
-            const float fnum = s_state[0], tnum = s_state[1];
+            const float fnum = sh.state[0], tnum = sh.state[1];
             if (cand >= 0) {
                 const float num = tnum + fnum;
                 const float den = rn * rcf + ln * lcf;
@@ -980,6 +906,265 @@ __global__ void __launch_bounds__(512) replay_par_kernel(ReplayParams P, NodeArr
     if (lane == 0 && warp < 8 && (n_fast | n_slow)) {
         atomicAdd((unsigned long long *)&ctl_stats->stat_chain_fast, (unsigned long long)n_fast);
         atomicAdd((unsigned long long *)&ctl_stats->stat_chain_slow, (unsigned long long)n_slow);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_seq, (unsigned long long)n_seq);
+    }
+}
+
+
+// ---------------------------------------------------------------- replay, streamed (the default path for D <= 4)
+// A single CTA cannot gather a large node fast enough (one 32-byte sector per row for the feature value, one for the
+// gradients): the whole GPU prepares contiguous streams first, the chain CTA of an item then only streams them.
+//   replay_plan_kernel    word offset of every item's side-bit plane (8-word groups); items that do not fit -> direct
+//   replay_gather_kernel  order-space copy of build_grads for the rows of every node that has replay items
+//   replay_bits_kernel    side bit (x > threshold, node.cpp:339) of every (item, row), 32 rows per word, + right counts
+//   replay_stream_kernel  the chains (chain.cuh) over the streams; same arithmetic as replay_par_kernel
+struct StreamParams {
+    float *G;                  // [N x D] build_grads in `order` space
+    unsigned int *bits;        // side-bit planes
+    int *woff;                 // [n_items + 1] word offset of the item's plane (prefix; parents / direct items have 0 words)
+    int *mode;                 // [n_items] 0 = streamed, 1 = parent (no plane), 2 = direct (plane did not fit)
+    int *nright;               // [n_items]
+    long long cap_words;
+    int replay_cap, N, oblivious;
+    const int *nid;
+};
+
+__global__ void __launch_bounds__(1024) replay_plan_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
+    __shared__ int s_scan[1024];
+    __shared__ long long s_carry;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_items; i0 += 1024) {
+        const int it = i0 + threadIdx.x;
+        int words = 0, md = 1;
+        if (it < n_items) {
+            const ReplayItem item = P.items[it];
+            if (item.cand >= 0) { words = ((na.seg_len[item.node] + 255) >> 8) << 3; md = 0; }   // 8-word groups
+        }
+        s_scan[threadIdx.x] = words;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const long long carry = s_carry;
+        const long long excl = carry + s_scan[threadIdx.x] - words;
+        if (it < n_items) {
+            if (md == 0 && excl + words > S.cap_words) md = 2;
+            // direct items keep their (unused) slot in the prefix so that the prefix stays monotone
+            S.woff[it] = (int)min(excl, S.cap_words);
+            S.mode[it] = md;
+            S.nright[it] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_scan[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S.woff[n_items] = (int)min(s_carry, S.cap_words);
+}
+
+__global__ void __launch_bounds__(256) replay_gather_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
+    if (P.ctl->n_replay <= 0) return;
+    const int D = P.D;
+    const bool all = S.oblivious != 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S.N; k += gridDim.x * blockDim.x) {
+        const int row = P.order[k];
+        if (!all && na.rep_count[S.nid[row]] <= 0) continue;
+        for (int d = 0; d < D; ++d) S.G[(size_t)k * D + d] = P.bg[(size_t)row * D + d];
+    }
+}
+
+// one warp per 8-word group (256 rows) of a plane
+__global__ void __launch_bounds__(256) replay_bits_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (n_items <= 0) return;
+    const int lane = threadIdx.x & 31;
+    const int total_groups = S.woff[n_items] >> 3;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_groups; g += warps) {
+        const int gw = g << 3;
+        // last item whose offset is <= gw (upper bound - 1): items without words share the offset of their successor
+        int lo = 0, hi = n_items;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (S.woff[mid] <= gw) lo = mid + 1; else hi = mid;
+        }
+        const int it = lo - 1;
+        if (S.mode[it] != 0) continue;
+        const ReplayItem item = P.items[it];
+        const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
+        const int f = item.cand / P.B;
+        const float tv = P.thr[item.cand];
+        const int k0 = (gw - S.woff[it]) << 5;
+        int cnt = 0;
+        float xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j * 32 + lane;
+            xv[j] = k < n ? P.X[(size_t)P.order[s0 + k] * P.F + f] : -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned int m = __ballot_sync(0xffffffffu, xv[j] > tv);      // node.cpp:339
+            if (lane == j) S.bits[gw + j] = m;
+            cnt += __popc(m);
+        }
+        if (lane == 0 && cnt) atomicAdd(&S.nright[it], cnt);
+    }
+}
+
+template <int DCT, int PASS>
+__device__ __forceinline__ void stream_pass(const float *G, const unsigned int *W, int n, float *sg /*[3][STAGE*D]*/, unsigned int *smask /*[3][MW]*/,
+                                            const float *smean, seq::StageShared &sh, int &n_fast, int &n_slow, int &n_seq) {
+    using C = ParCfg<DCT>;
+    constexpr int R = C::R, T = C::T, STAGE = C::STAGE, SUB = C::SUB, EPL = C::EPL, D = DCT, MW = STAGE / 32;
+    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    constexpr int KE = PASS == 0 ? R : 8;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n_stages = (n + STAGE - 1) / STAGE;
+    const long long ne = (long long)n * D;
+    float nx1[8], nx2[8];
+    unsigned int mw1 = 0, mw2 = 0;
+    auto load = [&](int st, float (&dst)[8], unsigned int &mw) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < EPL) {
+                const long long e = (long long)st * (STAGE * D) + j * T + tid;
+                dst[j] = (st < n_stages && e < ne) ? G[e] : 0.0f;
+            }
+        }
+        mw = 0u;
+        if (tid < MW && W != nullptr && st < n_stages) {
+            const int wi = st * MW + tid;
+            if ((long long)wi * 32 < n) mw = W[wi];
+        }
+    };
+    auto commit = [&](int b, const float (&src)[8], unsigned int mw) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < EPL) sg[b * (STAGE * D) + j * T + tid] = src[j];
+        if (tid < MW) smask[b * MW + tid] = mw;
+    };
+    // the lane's KE consecutive elements of chain c in sub-block w of stage buffer b; rows past the end hold +0 and
+    // count as "left"
+    auto load_x = [&](int b, int c, int w, float (&x)[KE]) {
+        const int rb = w * SUB + lane * R;
+        const float *p = sg + b * (STAGE * D) + rb * D;
+        float v[8];
+        if (EPL == 8) {
+            const float4 a = *reinterpret_cast<const float4 *>(p), q = *reinterpret_cast<const float4 *>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                if (j < EPL) { const float2 a = *reinterpret_cast<const float2 *>(p + j); v[j] = a.x; v[j + 1] = a.y; }
+                else { v[j] = 0.0f; v[j + 1] = 0.0f; }
+            }
+        }
+        const unsigned int mb = (smask[b * MW + (rb >> 5)] >> (rb & 31)) & ((1u << R) - 1u);
+        if (PASS == 0) {
+            const int side = c / D, d = c - side * D;
+            const unsigned int sel = side ? mb : ~mb;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float val = v[r * D];
+#pragma unroll
+                for (int dd = 1; dd < D; ++dd) val = (d == dd) ? v[r * D + dd] : val;
+                x[r < KE ? r : 0] = ((sel >> r) & 1u) ? val : 0.0f;
+            }
+        } else {
+            const unsigned int sel = c ? mb : ~mb;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = j / D, d = j - r * D;
+                x[j < KE ? j : 0] = (j < EPL && ((sel >> r) & 1u)) ? v[j] * smean[c * D + d] : 0.0f;
+            }
+        }
+    };
+    seq::pipe_init(sh);
+    load(0, nx1, mw1); commit(0, nx1, mw1);
+    load(1, nx1, mw1); commit(1, nx1, mw1);
+    load(2, nx1, mw1); load(3, nx2, mw2);
+    __syncthreads();
+    int bc = 0;
+    for (int st = 0; st < n_stages; ++st) {
+        const int bn = bc == 2 ? 0 : bc + 1, bf = bn == 2 ? 0 : bn + 1;
+        const int cnt = min(STAGE, n - st * STAGE);
+        const int cnt_next = st + 1 < n_stages ? min(STAGE, n - (st + 1) * STAGE) : 0;
+        auto lc = [&](int c, int w, float (&x)[KE]) { load_x(bc, c, w, x); };
+        auto ln = [&](int c, int w, float (&x)[KE]) { load_x(bn, c, w, x); };
+        seq::run_stage_pipe<KE>(sh, NCH, st & 1, (cnt + SUB - 1) / SUB, lc, (cnt_next + SUB - 1) / SUB, ln, n_fast, n_slow, n_seq);
+        commit(bf, nx1, mw1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nx1[j] = nx2[j];
+        mw1 = mw2;
+        load(st + 4, nx2, mw2);
+        bc = bn;
+        __syncthreads();
+    }
+}
+
+template <int DCT>
+__global__ void __launch_bounds__(512, 1) replay_stream_kernel(ReplayParams P, NodeArrays na, StreamParams S, Ctl *ctl_stats) {
+    using C = ParCfg<DCT>;
+    constexpr int D = DCT, STAGE = C::STAGE;
+    extern __shared__ __align__(16) float s_dyn_stream[];         // [3][STAGE*D] floats, then [3][STAGE/32] mask words
+    float *sg = s_dyn_stream;
+    unsigned int *smask = reinterpret_cast<unsigned int *>(sg + 3 * STAGE * D);
+    __shared__ float smean[2 * D];
+    __shared__ seq::StageShared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    int n_fast = 0, n_slow = 0, n_seq = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int md = S.mode[it];
+        if (md == 2) continue;                                   // replay_par_kernel gathers this one itself
+        const ReplayItem item = P.items[it];
+        const int h = item.node, cand = item.cand;
+        const int s0 = na.seg_start[h], n = na.seg_len[h];
+        const float *G = S.G + (size_t)s0 * D;
+        const unsigned int *W = md == 0 ? S.bits + S.woff[it] : nullptr;
+        stream_pass<DCT, 0>(G, W, n, sg, smask, smean, sh, n_fast, n_slow, n_seq);
+        const int nR = md == 0 ? S.nright[it] : 0;
+        const int nL = n - nR;
+        const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
+        const float lcf = (float)nL, rcf = (float)nR;
+        float ln = 0.0f, rn = 0.0f;
+        if (warp == 0) {
+            float lrec, rrec;
+            if (cand >= 0) { lrec = nL > 0 ? 1.0f / lcf : 0.0f; rrec = nR > 0 ? 1.0f / rcf : 0.0f; }
+            else { lrec = 1.0f / lcf; rrec = 0.0f; }   // parent: n_samples_recip = 1/n (split_candidate_generator.cpp:265,296)
+            if (lane < D) { smean[lane] = sh.state[lane] * lrec; smean[D + lane] = sh.state[D + lane] * rrec; }
+            __syncwarp();
+            for (int d = 0; d < D; ++d) { ln = ln + smean[d] * smean[d]; rn = rn + smean[D + d] * smean[D + d]; }  // squared_norm
+        }
+        __syncthreads();
+        float result = 0.0f;
+        if (P.score_func == GBRL_B200_SCORE_L2) {
+            result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
+        } else {
+            stream_pass<DCT, 1>(G, W, n, sg, smask, smean, sh, n_fast, n_slow, n_seq);
+            const float fnum = sh.state[0], tnum = sh.state[1];
+            if (cand >= 0) {
+                const float num = tnum + fnum;
+                const float den = rn * rcf + ln * lcf;
+                result = (den == 0.0f) ? 0.0f : num / sqrtf(den);
+            } else {
+                const float den = ln * lcf;
+                result = (n == 0 || den == 0.0f) ? 0.0f : fnum / sqrtf(den);
+            }
+        }
+        if (invalid) result = -INFINITY;
+        if (threadIdx.x == 0) P.out[it] = result;
+        __syncthreads();
+    }
+    if (lane == 0 && warp < 8 && (n_fast | n_slow)) {
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_fast, (unsigned long long)n_fast);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_slow, (unsigned long long)n_slow);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_seq, (unsigned long long)n_seq);
     }
 }
 
@@ -1149,6 +1334,15 @@ void launch_scan(Model &m, int level, cudaStream_t s) {
     else launch_scan_dm<32>(P, ws.na, grid, s);
 }
 
+template <int DCT>
+static void launch_stream(const ReplayParams &R, const NodeArrays &na, const StreamParams &S, Ctl *ctl, cudaStream_t s) {
+    using C = ParCfg<DCT>;
+    const size_t smem = (size_t)3 * C::STAGE * DCT * sizeof(float) + (size_t)3 * (C::STAGE / 32) * sizeof(unsigned int);
+    static bool attr = false;
+    if (!attr) { GB_CUDA(cudaFuncSetAttribute(replay_stream_kernel<DCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    GB_LAUNCH((replay_stream_kernel<DCT>), 148 * 2, 512, smem, s, R, na, S, ctl);
+}
+
 void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
     const bool obl = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
@@ -1183,11 +1377,28 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         // gradients fit in registers while they are in flight and two stages fit in shared memory
         const int D = ws.D;
         if (D <= 4) {
-            // bit-exact parallel chains (chain.cuh)
-            if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), 148 * 2, 512, 0, s, R, ws.na, ctl);
-            else if (D == 2) GB_LAUNCH((replay_par_kernel<2>), 148 * 2, 512, 0, s, R, ws.na, ctl);
-            else if (D == 3) GB_LAUNCH((replay_par_kernel<3>), 148 * 2, 512, 0, s, R, ws.na, ctl);
-            else GB_LAUNCH((replay_par_kernel<4>), 148 * 2, 512, 0, s, R, ws.na, ctl);
+            // bit-exact parallel chains (chain.cuh) over streams prepared by the whole GPU
+            StreamParams S;
+            S.G = ws.rgrad.as<float>(); S.bits = ws.rbits.as<unsigned int>(); S.woff = ws.rmeta.as<int>();
+            S.mode = S.woff + ws.replay_cap + 1; S.nright = S.mode + ws.replay_cap;
+            S.cap_words = ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
+            S.nid = ws.nid.as<int>();
+            GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
+            GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
+            GB_LAUNCH(replay_bits_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
+            if (D <= 1) {
+                launch_stream<1>(R, ws.na, S, ctl, s);
+                GB_LAUNCH((replay_par_kernel<1>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+            } else if (D == 2) {
+                launch_stream<2>(R, ws.na, S, ctl, s);
+                GB_LAUNCH((replay_par_kernel<2>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+            } else if (D == 3) {
+                launch_stream<3>(R, ws.na, S, ctl, s);
+                GB_LAUNCH((replay_par_kernel<3>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+            } else {
+                launch_stream<4>(R, ws.na, S, ctl, s);
+                GB_LAUNCH((replay_par_kernel<4>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+            }
         } else {
             // wide outputs: one lane per output dimension runs its chain sequentially (parallel over D instead of over rows)
             const int T = 128;

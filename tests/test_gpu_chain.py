@@ -33,7 +33,7 @@ def _seq_partials(mat, D, T, mode, mean):
     return out, cen
 
 
-def _gpu_partials(mat, D, T, mode, mean, impl=0):
+def _gpu_partials(mat, D, T, mode, mean, impl=0, info=None):
     from gbrl_b200 import _capi
     L = _capi.lib()
     flat = np.ascontiguousarray(mat.reshape(-1), np.float32)
@@ -42,7 +42,8 @@ def _gpu_partials(mat, D, T, mode, mean, impl=0):
     mean = np.ascontiguousarray(mean if mean is not None else np.zeros(D), np.float32)
     fp = C.POINTER(C.c_float)
     _capi.check(L.gbrl_b200_diag_chain_sums(flat.ctypes.data_as(fp), flat.size, D, T, mode, mean.ctypes.data_as(fp),
-                                            part.ctypes.data_as(fp), cen.ctypes.data_as(fp), impl))
+                                            part.ctypes.data_as(fp), cen.ctypes.data_as(fp), impl,
+                                            info.ctypes.data_as(C.POINTER(C.c_double)) if info is not None else None))
     return part.reshape(T, D), cen
 
 
