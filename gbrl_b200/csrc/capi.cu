@@ -75,7 +75,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     if (tb < C / 256 + 1) tb = C / 256 + 1;
     ws.tile_best.ensure(tb * sizeof(float2));
     const int nTl = ws.tile_hi - ws.tile_lo > 0 ? ws.tile_hi - ws.tile_lo : 1;
-    ws.items_cap = (N / ITEM_ROWS + (1 << md) + 1) * nTl;
+    ws.items_cap = (N / 1536 + (1 << md) + 1) * nTl;      // smallest item size any histogram variant asks for (hist_item_rows)
     if (!ws.n_sms) {
         cudaDeviceProp prop;
         GB_CUDA(cudaGetDeviceProperties(&prop, m.device));

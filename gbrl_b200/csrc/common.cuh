@@ -14,7 +14,8 @@ constexpr int FT = 32;            // features per histogram tile (one per lane: 
 constexpr int NB = 256;           // histogram bins per feature (codes 1..256; code 0 never goes right)
 constexpr int ITEM_ROWS = 8192;   // max rows per histogram work item (bounds the int32 smem partial sums)
 constexpr int LO_BITS = 18;       // fixed-point split: q = hi * 2^18 + lo, lo in [0, 2^18)
-constexpr int Q_BITS = 36;        // |q| < 2^35  (8192 rows * 2^18 < 2^31, 8192 * 2^17 = 2^30)
+constexpr int Q_BITS = 34;        // |q| < 2^32: lo < 2^18 (8192 rows * 2^18 = 2^31 per fold), |hi| < 2^14 (8 items * 8192 rows * 2^14 = 2^30 per flush)
+constexpr int FLUSH_ITEMS = 8;    // a CTA flushes its shared-memory histogram to HBM at the latest after this many items of one (node, tile)
 constexpr int MAX_DEPTH_SUPPORTED = 12;
 constexpr int MAX_OPTS = 64;
 constexpr int HIST_THREADS = 512;

@@ -169,6 +169,7 @@ void raw_grad_scale(Model &m, const float *grads, int N, cudaStream_t s);       
 void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, cudaStream_t s);
 // histogram.cu
 void launch_plan_level(Model &m, int level, cudaStream_t s);
+int hist_item_rows(const Model &m);
 void launch_histogram(Model &m, int level, cudaStream_t s);
 // split.cu
 void launch_scan(Model &m, int level, cudaStream_t s);

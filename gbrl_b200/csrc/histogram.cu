@@ -28,8 +28,8 @@ namespace gb {
 // Decides, for every node of the level, whether its histogram is built directly or derived as
 // parent - sibling (only the smaller child is histogrammed), and emits the work items.
 __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int items_cap, int level, int max_depth,
-                                  int nT_local, int use_subtraction, int oblivious, int row_groups, int row_group) {
-    __shared__ int s_cnt[1024];
+                                  int nT_local, int use_subtraction, int oblivious, int row_groups, int row_group, int item_rows_max) {
+    __shared__ int s_cnt[1024], s_off[1024], s_len[1024], s_start[1024];
     __shared__ int s_total;
     __shared__ unsigned long long s_rows;
     const int base = level_base(level), nn = 1 << level;
@@ -59,7 +59,7 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
     __syncthreads();
     if (threadIdx.x == 0) {
         const long long want = (long long)(s_direct_rows / (unsigned long long)(row_groups > 0 ? row_groups : 1)) * nT_local / (148 * 6);
-        int ir = ITEM_ROWS;
+        int ir = item_rows_max;
         // (measured: smaller items do not pay off while every item ends with a full 8192-entry REDG flush)
         (void)want;
         s_item_rows = ir;
@@ -108,20 +108,29 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
         }
         const int incl = s_cnt[threadIdx.x];
         const int off = s_total + incl - my;
-        if (my > 0) {
-            int w = off;
-            const int chunks = ceil_div(len, item_rows);
-            for (int c = row_group; c < chunks; c += row_groups)
-                for (int t = 0; t < nT_local; ++t) {
-                    if (w < items_cap) {
-                        Item it;
-                        it.slot = slot; it.tile = t;
-                        it.k0 = start + c * item_rows;
-                        it.k1 = min(start + len, it.k0 + item_rows);
-                        items[w] = it;
-                    }
-                    ++w;
+        // the items of every node of this pass are written cooperatively (a large node has thousands of them)
+        __syncthreads();
+        s_cnt[threadIdx.x] = my;
+        s_off[threadIdx.x] = off; s_len[threadIdx.x] = len; s_start[threadIdx.x] = start;
+        __syncthreads();
+        const int in_pass = min((int)blockDim.x, nn - n0);
+        for (int q = 0; q < in_pass; ++q) {
+            const int qmy = s_cnt[q];
+            if (qmy <= 0) continue;
+            const int qlen = s_len[q], qstart = s_start[q], qoff = s_off[q];
+            const int chunks = ceil_div(qlen, item_rows);
+            const int mine = chunks > row_group ? (chunks - row_group + row_groups - 1) / row_groups : 0;   // chunks of this rank
+            for (int j = threadIdx.x; j < qmy; j += blockDim.x) {
+                // pair-major order: tile outer, row chunk inner
+                const int t = j / mine, c = row_group + (j - t * mine) * row_groups;
+                if (qoff + j < items_cap) {
+                    Item it;
+                    it.slot = n0 + q; it.tile = t;
+                    it.k0 = qstart + c * item_rows;
+                    it.k1 = min(qstart + qlen, it.k0 + item_rows);
+                    items[qoff + j] = it;
                 }
+            }
         }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_total += incl;
@@ -133,11 +142,17 @@ __global__ void plan_level_kernel(NodeArrays na, Ctl *ctl, Item *items, int item
     }
 }
 
+// rows per work item: the streaming kernel wants NWARPS * 64 (two 32-row blocks per warp), the per-item kernel 8192
+int hist_item_rows(const Model &m) {
+    if (m.cfg.hist_variant != 0) return ITEM_ROWS;
+    return m.cfg.output_dim == 1 ? 32 * 64 : 24 * 64;
+}
+
 void launch_plan_level(Model &m, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
     GB_LAUNCH(plan_level_kernel, 1, 1024, 0, s, ws.na, ws.ctl.as<Ctl>(), ws.items.as<Item>(), ws.items_cap, level,
               m.cfg.max_depth, ws.tile_hi - ws.tile_lo, m.cfg.use_subtraction, m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS,
-              ws.row_groups, ws.row_group);
+              ws.row_groups, ws.row_group, hist_item_rows(m));
 }
 
 // ---------------------------------------------------------------- the histogram kernel
@@ -275,6 +290,225 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
     }
 }
 
+// ---------------------------------------------------------------- streaming variant (1 CTA per SM)
+// Same arithmetic and the same global histogram as hist_kernel; what changes is how rows reach the atomics:
+//   * one CTA of HS_WARPS warps per SM and ONE shared-memory histogram, which leaves room for a per-warp ring of
+//     HS_STAGES x 16 rows of codes (64 B per row and tile) + gradients filled by cp.async (LDGSTS): rows are
+//     gathered two stages (32 rows per warp, ~96 KB per SM) ahead of the atomics without costing registers, which
+//     is what hides the HBM / L2 latency of the `order` gather on the deeper levels;
+//   * items arrive pair-major ((node, tile) outer, row chunk inner) and a CTA owns a contiguous range of them, so
+//     the shared histogram is carried from item to item (lo -> hi carry fold after every item) and is flushed to
+//     HBM only when the (node, tile) pair changes or after FLUSH_ITEMS items: ~n_sms + n_pairs flushes per level
+//     instead of one per item.
+constexpr int HS_STAGE_ROWS = 16;
+constexpr int HS_FOLD_ITEMS = 4;     // lo planes: 4 items x 2048 rows x 2^18 = 2^31
+constexpr int HS_FLUSH_ITEMS = 32;   // hi planes: 32 items x 2048 rows x 2^14 = 2^30
+
+__device__ __forceinline__ void cp_async_16(unsigned int dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(unsigned int dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int ND, int NWARPS, int NST>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, const int *__restrict__ order,
+                   const Item *__restrict__ items, const Ctl *__restrict__ ctl, long long *__restrict__ hist, int codes_rows,
+                   int row_offset, int D, int d0, int nT_local, int tile_lo, int nT_total, int write_count) {
+    extern __shared__ int sh[];
+    constexpr int W = 1 + 2 * ND;
+    constexpr int PB = HPLANE * 4;               // plane size in bytes
+    constexpr int NTHREADS = NWARPS * 32;
+    constexpr int RING_GRAD = HS_STAGE_ROWS * 64;              // a ring stage: 16 rows x 64 B of codes, then 16 x ND gradients
+    constexpr int RING_STAGE = RING_GRAD + HS_STAGE_ROWS * 4 * ND;
+    const int n_items = ctl->n_items;
+    const float scale = exp2f((float)ctl->qexp);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rl = (lane >> 3) & 3, g = lane & 7;
+    const int HS = 1 + D;
+    // contiguous range of items of this CTA
+    const int i0 = (int)((long long)n_items * blockIdx.x / gridDim.x), i1 = (int)((long long)n_items * (blockIdx.x + 1) / gridDim.x);
+    if (i0 >= i1) return;
+    for (int i = threadIdx.x; i < W * HPLANE; i += NTHREADS) sh[i] = 0;
+    const unsigned int sbase = (unsigned int)__cvta_generic_to_shared(sh);
+    const unsigned int ring = sbase + (unsigned int)(W * PB) + (unsigned int)(warp * NST * RING_STAGE);
+    unsigned int lbase[4], psel[4];
+    bool upper[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int ms = (k + rl) & 3;
+        lbase[k] = sbase + (unsigned int)(g * 4 + ms) * 4u;
+        upper[k] = (ms & 2) != 0;
+        const unsigned int lo = 2u * (ms & 1), hi = lo + 1u;
+        psel[k] = lo | (hi << 4) | (4u << 8) | (4u << 12);
+    }
+    __syncthreads();
+
+    // flush: (bin, feature) e -> global [slot][tile][bin][feature][1+D]; shared row = bin + 1
+    auto flush = [&](const Item &it) {
+        long long *hb = hist + ((size_t)it.slot * nT_total + (tile_lo + it.tile)) * (size_t)(NB * FT) * HS;
+        for (int e = threadIdx.x; e < NB * FT; e += NTHREADS) {
+            const int se = e + FT;
+            const int cnt = sh[se];
+            if (cnt != 0) {
+                if (write_count) red_add64(hb + (size_t)e * HS, (long long)cnt);
+                sh[se] = 0;
+#pragma unroll
+                for (int dd = 0; dd < ND; ++dd) {
+                    const unsigned int l = (unsigned int)sh[(1 + 2 * dd) * HPLANE + se];
+                    const int h = sh[(2 + 2 * dd) * HPLANE + se];
+                    const long long tot = ((long long)h << LO_BITS) + (long long)l;
+                    if (tot != 0) red_add64(hb + (size_t)e * HS + 1 + d0 + dd, tot);
+                    sh[(1 + 2 * dd) * HPLANE + se] = 0;
+                    sh[(2 + 2 * dd) * HPLANE + se] = 0;
+                }
+            }
+        }
+        // the dump rows (code 0) are never flushed; keep them from overflowing
+        for (int e = threadIdx.x; e < FT; e += NTHREADS)
+#pragma unroll
+            for (int w = 0; w < W; ++w) sh[w * HPLANE + e] = 0;
+    };
+    // carry fold: lo keeps 18 bits, the rest moves to hi (lo is read as unsigned: it may have reached 2^31)
+    auto fold = [&]() {
+        for (int e = threadIdx.x; e < (NB + 1) * FT; e += NTHREADS) {
+#pragma unroll
+            for (int dd = 0; dd < ND; ++dd) {
+                const unsigned int l = (unsigned int)sh[(1 + 2 * dd) * HPLANE + e];
+                if (l >> LO_BITS) {
+                    sh[(2 + 2 * dd) * HPLANE + e] += (int)(l >> LO_BITS);
+                    sh[(1 + 2 * dd) * HPLANE + e] = (int)(l & ((1u << LO_BITS) - 1u));
+                }
+            }
+        }
+    };
+
+    // Every item is at most HS_ITEM_ROWS = NWARPS * 64 rows: a warp owns two blocks of 32 consecutive positions of it
+    // (block b at k0 + (b * NWARPS + warp) * 32), i.e. exactly four ring stages of 16 rows per item.  The stages of
+    // all the CTA's items form one stream per warp, t = 0 .. 4 * n_my - 1 (item t >> 2, block (t >> 1) & 1, half
+    // t & 1); gathers run NST - 1 stages ahead of the atomics ACROSS item boundaries.
+    const int n_my = i1 - i0, T = 4 * n_my;
+    int rows_i = -1, rows_n = -1;                 // row ids of the block being issued / of the block after it (lane = position)
+    int tile_i = 0, tile_n = 0;
+    unsigned int vbits = 0;                       // bit (t & 31): stage t has at least one valid row
+    auto block_rows = [&](int blk, int &tile) -> int {        // blk = global block index of this warp, = t >> 1
+        if (blk >= 2 * n_my) { tile = 0; return -1; }
+        const Item it = items[i0 + (blk >> 1)];
+        tile = it.tile;
+        const int k = it.k0 + ((blk & 1) * NWARPS + warp) * 32 + lane;
+        return k < it.k1 ? order[k] : -1;
+    };
+    auto issue = [&](int t) {
+        if (t < T) {
+            if ((t & 1) == 0) {                   // first half of a block: rotate the prefetched row ids
+                rows_i = rows_n; tile_i = tile_n;
+                rows_n = block_rows((t >> 1) + 1, tile_n);
+            }
+            const int half = t & 1;
+            const int mine = __shfl_sync(0xffffffffu, rows_i, half * 16 + (lane & 15));
+            if (__any_sync(0xffffffffu, mine >= 0)) {
+                vbits |= 1u << (t & 31);
+                const uint16_t *ctile = codes + ((size_t)tile_i * codes_rows + row_offset) * FT;
+                const unsigned int dst = ring + (unsigned int)((t % NST) * RING_STAGE);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int r = j * 8 + (lane >> 2), q = lane & 3;            // row in stage, 16-byte quarter
+                    const int row = __shfl_sync(0xffffffffu, rows_i, half * 16 + r);
+                    cp_async_16(dst + (unsigned int)(r * 64 + q * 16), ctile + (size_t)(row >= 0 ? row : 0) * FT + q * 8, row >= 0 ? 16 : 0);
+                }
+                if (lane < 16) {
+#pragma unroll
+                    for (int dd = 0; dd < ND; ++dd)
+                        cp_async_4(dst + (unsigned int)(RING_GRAD + (lane * ND + dd) * 4), bg + (size_t)(mine >= 0 ? mine : 0) * D + d0 + dd,
+                                   mine >= 0 ? 4 : 0);
+                }
+            } else vbits &= ~(1u << (t & 31));
+        }
+        cp_async_commit();
+    };
+    rows_n = block_rows(0, tile_n);
+#pragma unroll 1
+    for (int t = 0; t < NST - 1; ++t) issue(t);
+    int since_flush = 0, since_fold = 0;
+    Item prev = items[i0];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        issue(t + NST - 1);
+        cp_async_wait<NST - 1>();
+        __syncwarp();
+        if ((vbits >> (t & 31)) & 1u) {
+            const unsigned int src = ring + (unsigned int)((t % NST) * RING_STAGE);
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) {
+                const int r = ss * 4 + rl;
+                uint2 b;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b.x), "=r"(b.y) : "r"(src + (unsigned int)(r * 64 + g * 8)));
+                int lo[ND], hi[ND];
+#pragma unroll
+                for (int dd = 0; dd < ND; ++dd) {
+                    float gv;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gv) : "r"(src + (unsigned int)(RING_GRAD + (r * ND + dd) * 4)));
+                    const long long q = __float2ll_rn(gv * scale);
+                    lo[dd] = (int)(q & ((1ll << LO_BITS) - 1));
+                    hi[dd] = (int)(q >> LO_BITS);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned int cs = __byte_perm(upper[k] ? b.y : b.x, 0u, psel[k]);   // code * 64, zero-extended
+                    const unsigned int addr = lbase[k] + cs * 2u;
+                    red_shared(addr, 1);
+                    red_shared_off<PB>(addr, lo[0]);
+                    red_shared_off<2 * PB>(addr, hi[0]);
+                    if (ND > 1) { red_shared_off<3 * PB>(addr, lo[ND > 1 ? 1 : 0]); red_shared_off<4 * PB>(addr, hi[ND > 1 ? 1 : 0]); }
+                }
+            }
+        }
+        __syncwarp();                             // the stage buffer is refilled NST - 1 iterations later by other lanes
+        if ((t & 3) == 3) {                       // item boundary (CTA-uniform decisions: they depend on the item list only)
+            ++since_flush; ++since_fold;
+            const int nx = (t >> 2) + 1;
+            bool do_flush = false;
+            Item nxt = prev;
+            if (nx < n_my) {
+                nxt = items[i0 + nx];
+                do_flush = nxt.slot != prev.slot || nxt.tile != prev.tile || since_flush >= HS_FLUSH_ITEMS;
+            }
+            if (do_flush) {
+                __syncthreads();
+                flush(prev);
+                __syncthreads();
+                since_flush = 0; since_fold = 0;
+            } else if (since_fold >= HS_FOLD_ITEMS && nx < n_my) {
+                __syncthreads();
+                fold();
+                __syncthreads();
+                since_fold = 0;
+            }
+            prev = nxt;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    flush(prev);
+}
+
+template <int ND, int NWARPS, int NST>
+static void launch_hist_stream(Model &m, int d0, int write_count, long long *hist, int n_sms, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int) + (size_t)NWARPS * NST * HS_STAGE_ROWS * (64 + 4 * ND);   // planes + rings
+    static bool attr_set = false;
+    if (!attr_set) {
+        GB_CUDA(cudaFuncSetAttribute((hist_stream_kernel<ND, NWARPS, NST>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    GB_LAUNCH((hist_stream_kernel<ND, NWARPS, NST>), n_sms, NWARPS * 32, smem, s, ws.codes.as<uint16_t>(), ws.bg.as<float>(),
+              ws.order[0].as<int>(), ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
+              ws.tile_hi - ws.tile_lo, ws.tile_lo, ws.nT, write_count);
+}
+
 template <int ND>
 static void launch_hist_nd(Model &m, int d0, int write_count, long long *hist, int n_sms, cudaStream_t s) {
     Workspace &ws = m.ws;
@@ -305,6 +539,14 @@ void launch_histogram(Model &m, int level, cudaStream_t s) {
     while (d0 < D) {
         const int nd = (D - d0 >= 3) ? 3 : (D - d0);
         const int wc = (d0 == 0);
+        const bool stream = m.cfg.hist_variant == 0;
+        if (stream) {
+            // two output dimensions per launch at most: the ring needs the shared memory a third pair of planes would take
+            if (nd >= 2) { launch_hist_stream<2, 24, 2>(m, d0, wc, hist, n_sms, s); d0 += 2; }
+            else if (D == 1) { launch_hist_stream<1, 32, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }
+            else { launch_hist_stream<1, 24, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }      // same item size as the ND = 2 launches
+            continue;
+        }
         if (nd == 1) launch_hist_nd<1>(m, d0, wc, hist, n_sms, s);
         else if (nd == 2) launch_hist_nd<2>(m, d0, wc, hist, n_sms, s);
         else launch_hist_nd<3>(m, d0, wc, hist, n_sms, s);

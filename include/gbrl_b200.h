@@ -57,6 +57,7 @@ typedef struct {
                                arg-max only */
     float band_kappa;       /* band = kappa * 2^-24 * sqrt(n_node) * |score|; <=0 -> default 8 */
     int use_subtraction;    /* 1: histogram only the smaller child, derive the sibling from the parent */
+    int hist_variant;       /* 0: streaming histogram kernel (cp.async row ring, carried shared histogram); 1: per-item kernel */
 } gbrl_b200_config;
 
 typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine statistics */
