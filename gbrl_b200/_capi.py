@@ -14,7 +14,7 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "input_dim", "output_dim", "policy_dim", "max_depth", "min_data_in_leaf", "n_bins", "par_th",
         "batch_size", "split_score_func", "generator_type", "grow_policy", "verbose", "device_ordinal",
-        "ref_threads", "tie_replay")] + [("band_kappa", C.c_float), ("use_subtraction", C.c_int), ("hist_variant", C.c_int)]
+        "ref_threads", "tie_replay")] + [("band_kappa", C.c_float), ("use_subtraction", C.c_int), ("hist_variant", C.c_int), ("replay_variant", C.c_int)]
 
 
 class Metadata(C.Structure):

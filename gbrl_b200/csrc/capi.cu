@@ -101,6 +101,11 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
         ws.rbits_words = (long long)((n1 + 255) / 256) * 8 * 64 + 4096;
         ws.rbits.ensure((size_t)ws.rbits_words * sizeof(unsigned int));
         ws.rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
+        if (D <= 2) {
+            ws.rwide_groups = ws.rbits_words / 8 + 1;
+            ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)) + sizeof(int)) +
+                            (size_t)ws.replay_cap * 8 * sizeof(float));
+        }
     }
     // node arrays carved from one allocation
     const size_t MN = ws.MAXN;

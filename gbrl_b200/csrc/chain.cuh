@@ -139,12 +139,45 @@ __device__ __forceinline__ Tab warp_summarize(const float (&x)[KE], float inv_u)
     return tab_of(warp_scan<KE>(x, inv_u));
 }
 
-// Runs the block through the chain starting from the exact running sum acc when its summary was not applicable:
-// the longest valid lane prefix is applied in one step, the lane where the running sum leaves its binade is run as
-// a plain sequential float chain (values broadcast by shuffles), then the rest is re-summarised in the new binade.
-// After MAX_RETRY such steps the remaining lanes are run sequentially.  Lanes whose elements are all +0 are skipped
-// (s + 0 == s).  n_seq counts sequentially run lanes.
-constexpr int MAX_RETRY = 3;
+// Runs the block through the chain starting from the exact running sum acc when its summary was not applicable.
+// Attempt: summarise the remaining lanes in the binade of acc, apply the longest valid lane prefix in one step, run the
+// lanes around the point where the sum leaves its binade as a plain sequential float chain (values broadcast by
+// shuffles; SEQ_RUN lanes, because a sum that has just crossed a power of two tends to cross back), try again.  A sum
+// that hovers around a power of two defeats every summary, and the plain chain (~5 cycles per element) is then the
+// fastest exact evaluation there is: after MAX_RETRY attempts the rest of the block is run sequentially.
+// Lanes whose elements are all +0 are skipped (s + 0 == s).  n_seq counts sequentially run lanes.
+constexpr int MAX_RETRY = 2;
+constexpr int SEQ_RUN = 3;
+
+// sequential chain over the lanes in `lanes` (ascending), shuffles of the next lane overlap the adds of the current one
+template <int KE>
+__device__ __forceinline__ float warp_seq_lanes(float acc, const float (&x)[KE], unsigned int lanes, int &n_seq) {
+    const unsigned int full = 0xffffffffu;
+    if (!lanes) return acc;
+    int l = __ffs(lanes) - 1;
+    lanes &= lanes - 1u;
+    float q[KE];
+#pragma unroll
+    for (int i = 0; i < KE; ++i) q[i] = __shfl_sync(full, x[i], l);
+#pragma unroll 1
+    for (;;) {
+        ++n_seq;
+        float qn[KE];
+        const int ln = lanes ? (__ffs(lanes) - 1) : -1;
+        if (ln >= 0) {
+#pragma unroll
+            for (int i = 0; i < KE; ++i) qn[i] = __shfl_sync(full, x[i], ln);
+        }
+#pragma unroll
+        for (int i = 0; i < KE; ++i) acc = acc + q[i];
+        if (ln < 0) break;
+        lanes &= lanes - 1u;
+#pragma unroll
+        for (int i = 0; i < KE; ++i) q[i] = qn[i];
+    }
+    return acc;
+}
+
 template <int KE>
 __device__ __forceinline__ float warp_advance(float acc, const float (&x)[KE], int &n_seq) {
     const unsigned int full = 0xffffffffu;
@@ -175,23 +208,14 @@ __device__ __forceinline__ float warp_advance(float acc, const float (&x)[KE], i
             todo = lstar < 32 ? (todo & (0xffffffffu << lstar)) : 0u;
             if (!todo) break;
         }
-        const int l = __ffs(todo) - 1;
+        // the next SEQ_RUN pending lanes as a plain chain
+        unsigned int run = 0u, rest = todo;
 #pragma unroll
-        for (int i = 0; i < KE; ++i) acc = acc + __shfl_sync(full, x[i], l);
-        todo &= todo - 1u;
-        ++n_seq;
+        for (int k = 0; k < SEQ_RUN; ++k) { const unsigned int low = rest & (0u - rest); run |= low; rest &= ~low; }
+        acc = warp_seq_lanes<KE>(acc, x, run, n_seq);
+        todo = rest;
     }
-    while (todo) {
-        const int l = __ffs(todo) - 1;
-        float q[KE];
-#pragma unroll
-        for (int i = 0; i < KE; ++i) q[i] = __shfl_sync(full, x[i], l);
-#pragma unroll
-        for (int i = 0; i < KE; ++i) acc = acc + q[i];
-        todo &= todo - 1u;
-        ++n_seq;
-    }
-    return acc;
+    return warp_seq_lanes<KE>(acc, x, todo, n_seq);
 }
 
 // Walks the per-sub-block summaries tab[0..nsub) (nsub <= 32, all computed for the binade inv_a) of one chain in

@@ -1,0 +1,384 @@
+// replay_wide.cu -- near-tie replay with the float chains spread over the WHOLE GPU (output_dim <= 2).
+//
+// replay_stream_kernel (split.cu) gives every (node, candidate) item one CTA; a chain over a million rows is then
+// bounded by what one SM can summarise.  Here the summaries (chain.cuh) of all 256-row groups of all items are
+// produced by all SMs at once, for a PREDICTED binade of the running sum, and one warp per chain only walks them:
+//   wide_bits_kernel    side bits of every (item, row) + per-group sums of every chain (fp64; prediction only)
+//   wide_prefix_kernel  exclusive prefix of the group sums per item and chain = predicted running sum at group start
+//   wide_tabs_kernel    group summaries (Tab) for the binade of that prediction, tagged with the binade
+//   wide_walk_kernel    per chain: composes 32 summaries at a time while their tag equals the binade of the ACTUAL
+//                       running sum and their range check holds; any other group is advanced piecewise from the
+//                       streams (warp_advance).  The prediction never enters the result -- a wrong tag only costs
+//                       time -- so the sums are bit-identical to the reference's sequential chain (node.cpp:336-352).
+// Cosine needs a second round (tabs + walk) for the mat_vec_dot_sum chains once the side means are known.
+#include "replay.cuh"
+#include "chain.cuh"
+
+namespace gb {
+
+constexpr int GROUP_ROWS = 256;
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m); hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return __hiloint2double(hi, lo);
+}
+
+// one warp per 8-word group (256 rows) of a plane
+template <int D>
+__global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (n_items <= 0) return;
+    const int lane = threadIdx.x & 31;
+    const int total_groups = S.woff[n_items] >> 3;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_groups; g += warps) {
+        const int gw = g << 3;
+        int lo = 0, hi = n_items;                 // last item whose offset is <= gw
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (S.woff[mid] <= gw) lo = mid + 1; else hi = mid;
+        }
+        const int it = lo - 1;
+        if (lane == 0) Wd.gitem[g] = S.mode[it] == 0 ? it : -1;
+        if (S.mode[it] != 0) continue;
+        const ReplayItem item = P.items[it];
+        const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
+        const bool is_cand = item.cand >= 0;
+        const int f = is_cand ? item.cand / P.B : 0;
+        const float tv = is_cand ? P.thr[item.cand] : INFINITY;
+        const int k0 = (gw - S.woff[it]) << 5;
+        int cnt = 0;
+        float xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j * 32 + lane;
+            xv[j] = (k < n && is_cand) ? P.X[(size_t)P.order[s0 + k] * P.F + f] : -INFINITY;
+        }
+        double sl[D], sr[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { sl[d] = 0.0; sr[d] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j * 32 + lane;
+            const bool right = xv[j] > tv;                                     // node.cpp:339
+            const unsigned int m = __ballot_sync(0xffffffffu, right);
+            if (lane == j) S.bits[gw + j] = m;
+            cnt += __popc(m);
+            if (k < n) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const double gv = (double)S.G[(size_t)(s0 + k) * D + d];
+                    if (right) sr[d] += gv; else sl[d] += gv;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sl[d] += shfl_xor_d(sl[d], o); sr[d] += shfl_xor_d(sr[d], o); }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) { Wd.bsum[(size_t)g * 2 * D + d] = sl[d]; Wd.bsum[(size_t)g * 2 * D + D + d] = sr[d]; }
+            if (cnt) atomicAdd(&S.nright[it], cnt);
+        }
+    }
+}
+
+// one CTA per item: pred[group][chain] = sum of bsum over the earlier groups of the item
+template <int D>
+__global__ void __launch_bounds__(256) wide_prefix_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+    __shared__ double s_tot[256];
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    const int t = threadIdx.x;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        if (S.mode[it] != 0) continue;
+        const int n = na.seg_len[P.items[it].node];
+        const int ng = (n + GROUP_ROWS - 1) / GROUP_ROWS;
+        const size_t base = (size_t)(S.woff[it] >> 3);
+        const int per = (ng + 255) / 256;
+        const int g0 = min(ng, t * per), g1 = min(ng, g0 + per);
+        for (int c = 0; c < 2 * D; ++c) {
+            double loc = 0.0;
+            for (int g = g0; g < g1; ++g) loc += Wd.bsum[(base + g) * 2 * D + c];
+            s_tot[t] = loc;
+            __syncthreads();
+            for (int o = 1; o < 256; o <<= 1) {
+                const double v = t >= o ? s_tot[t - o] : 0.0;
+                __syncthreads();
+                s_tot[t] += v;
+                __syncthreads();
+            }
+            double acc = s_tot[t] - loc;
+            __syncthreads();
+            for (int g = g0; g < g1; ++g) {
+                Wd.pred[(base + g) * 2 * D + c] = (float)acc;
+                acc += Wd.bsum[(base + g) * 2 * D + c];
+            }
+        }
+    }
+}
+
+// the lane's 8 rows of a group: values (row-major, D per row), side bits, members of chain side `side`
+template <int D>
+__device__ __forceinline__ void group_rows(const float *G, const unsigned int *W, int n, int lg, float (&v)[8 * D], unsigned int &mb) {
+    const int lane = threadIdx.x & 31;
+    const int kb = lg * GROUP_ROWS + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8 * D; ++j) {
+        const int k = kb + j / D;
+        v[j] = k < n ? G[(size_t)kb * D + j] : 0.0f;
+    }
+    mb = (W[lg * 8 + (lane >> 2)] >> ((lane & 3) * 8)) & 0xffu;
+}
+
+template <int D, int PASS>
+__device__ __forceinline__ void chain_elems(const float (&v)[8 * D], unsigned int mb, int c, const float *smean,
+                                            float (&x)[PASS == 0 ? 8 : 8 * D]) {
+    if (PASS == 0) {
+        const int side = c / D, d = c - side * D;
+        const unsigned int sel = side ? mb : ~mb;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float val = v[r * D];
+#pragma unroll
+            for (int dd = 1; dd < D; ++dd) val = (d == dd) ? v[r * D + dd] : val;
+            x[r] = ((sel >> r) & 1u) ? val : 0.0f;
+        }
+    } else {
+        const unsigned int sel = c ? mb : ~mb;
+#pragma unroll
+        for (int j = 0; j < 8 * D; ++j) {
+            const int r = j / D, d = j - r * D;
+            x[j < (PASS == 0 ? 8 : 8 * D) ? j : 0] = ((sel >> r) & 1u) ? v[j] * smean[c * D + d] : 0.0f;   // math_ops.h:432-449
+        }
+    }
+}
+
+// one warp per group: summaries of all chains of the group for the predicted binade
+template <int D, int PASS>
+__global__ void __launch_bounds__(256) wide_tabs_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    constexpr int KE = PASS == 0 ? 8 : 8 * D;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (n_items <= 0) return;
+    if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
+    const int lane = threadIdx.x & 31;
+    const int total_groups = S.woff[n_items] >> 3;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_groups; g += warps) {
+        const int it = Wd.gitem[g];
+        if (it < 0) continue;
+        const ReplayItem item = P.items[it];
+        const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
+        const int lg = g - (S.woff[it] >> 3);
+        float v[8 * D];
+        unsigned int mb;
+        group_rows<D>(S.G + (size_t)s0 * D, S.bits + S.woff[it], n, lg, v, mb);
+        float smean[2 * D];
+        if (PASS == 1) {
+#pragma unroll
+            for (int i = 0; i < 2 * D; ++i) smean[i] = Wd.fin[(size_t)it * 8 + i];
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            float pr;
+            if (PASS == 0) pr = Wd.pred[(size_t)g * 2 * D + c];
+            else {
+                pr = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) pr += smean[c * D + d] * Wd.pred[(size_t)g * 2 * D + c * D + d];
+            }
+            float inv_u, u;
+            const bool ok = seq::epoch_of(pr, inv_u, u);
+            if (ok) {
+                float x[KE];
+                chain_elems<D, PASS>(v, mb, c, smean, x);
+                const seq::Tab tb = seq::warp_summarize<KE>(x, inv_u);
+                if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+            }
+            if (lane == 0) Wd.tag[(size_t)g * 2 * D + c] = ok ? inv_u : 0.0f;
+        }
+    }
+}
+
+// composes the longest applicable prefix of a window of 32 groups (lane = group); returns how many were consumed
+__device__ __forceinline__ int compose_window(float &acc, const int4 q, float tg, bool in_range, int first) {
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float inv_u, u;
+    if (!seq::epoch_of(acc, inv_u, u)) return 0;
+    const bool live = lane >= first;                      // lanes before `first` are consumed already
+    const bool tag_ok = in_range && tg == inv_u;
+    int i0 = (tag_ok && live) ? q.x : 0, i1 = (tag_ok && live) ? q.y : 0;
+    if (!__any_sync(full, i0 != i1)) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int g0 = __shfl_up_sync(full, i0, off);
+            if (lane >= off) i0 += g0;
+        }
+        i1 = i0;
+    } else {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int g0 = __shfl_up_sync(full, i0, off), g1 = __shfl_up_sync(full, i1, off);
+            if (lane >= off) {
+                const int n0 = g0 + ((g0 & 1) ? i1 : i0);
+                const int n1 = g1 + (((g1 + 1) & 1) ? i1 : i0);
+                i0 = n0; i1 = n1;
+            }
+        }
+    }
+    int e0 = __shfl_up_sync(full, i0, 1);
+    if (lane == 0) e0 = 0;
+    const int m = (int)(acc * inv_u);
+    const int lo = (1 << 23) + seq::MARGIN, hi = (1 << 24) - seq::MARGIN;
+    const int b = m + e0;
+    const bool okw = !live || (tag_ok && (m > 0 ? (b + q.z > lo && b + q.w < hi) : (b + q.w < -lo && b + q.z > -hi)));
+    const unsigned int bad = __ballot_sync(full, !okw);
+    const int take = (bad ? (__ffs(bad) - 1) : 32) - first;   // groups first .. first + take - 1 of the window are applied
+    if (take <= 0) return 0;
+    const int inc0 = __shfl_sync(full, i0, first + take - 1), inc1 = __shfl_sync(full, i1, first + take - 1);
+    acc = (float)(m + ((m & 1) ? inc1 : inc0)) * u;
+    return take;
+}
+
+// one CTA per item, warp c walks chain c; then the item's score (L2, or Cosine after PASS 1) / the side means (Cosine, PASS 0)
+template <int D, int PASS>
+__global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd, Ctl *ctl_stats) {
+    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    constexpr int KE = PASS == 0 ? 8 : 8 * D;
+    __shared__ float s_sum[2 * D];
+    __shared__ float s_mean[2 * D];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
+    int n_fast = 0, n_slow = 0, n_seq = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        if (S.mode[it] != 0) continue;
+        const ReplayItem item = P.items[it];
+        const int h = item.node, cand = item.cand;
+        const int s0 = na.seg_start[h], n = na.seg_len[h];
+        const int ng = (n + GROUP_ROWS - 1) / GROUP_ROWS;
+        const size_t base = (size_t)(S.woff[it] >> 3);
+        const float *G = S.G + (size_t)s0 * D;
+        const unsigned int *W = S.bits + S.woff[it];
+        if (PASS == 1) {
+            if (threadIdx.x < 2 * D) s_mean[threadIdx.x] = Wd.fin[(size_t)it * 8 + threadIdx.x];
+            __syncthreads();
+        }
+        if (warp < NCH) {
+            const int c = warp;
+            float acc = 0.0f;
+#pragma unroll 1
+            for (int w0 = 0; w0 < ng; w0 += 32) {          // window of 32 groups, lane = group
+                const bool in_range = w0 + lane < ng;
+                const int wn = min(32, ng - w0);
+                int4 q = make_int4(0, 0, 0, 0);
+                float tg = 0.0f;
+                if (in_range) { q = Wd.tab[(base + w0 + lane) * 2 * D + c]; tg = Wd.tag[(base + w0 + lane) * 2 * D + c]; }
+                int first = 0;
+                float vn[8 * D];                           // rows of the group after a failed one, fetched while that one is advanced
+                unsigned int mbn = 0u;
+                int have = -1;                             // group (window-relative) whose rows vn holds
+#pragma unroll 1
+                while (first < wn) {
+                    const int take = compose_window(acc, q, tg, in_range, first);
+                    n_fast += take;
+                    first += take;
+                    if (first >= wn) break;
+                    // this group is in another binade than predicted, or the sum leaves its binade inside it
+                    float v[8 * D], x[KE];
+                    unsigned int mb;
+                    if (have == first) {
+#pragma unroll
+                        for (int j = 0; j < 8 * D; ++j) v[j] = vn[j];
+                        mb = mbn;
+                    } else group_rows<D>(G, W, n, w0 + first, v, mb);
+                    if (w0 + first + 1 < ng) { group_rows<D>(G, W, n, w0 + first + 1, vn, mbn); have = first + 1; }
+                    chain_elems<D, PASS>(v, mb, c, s_mean, x);
+                    acc = seq::warp_advance<KE>(acc, x, n_seq);
+                    ++n_slow; ++first;
+                }
+            }
+            if (lane == 0) s_sum[c] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nR = S.nright[it], nL = n - nR;
+            const bool invalid = cand >= 0 && (nL < P.min_data || nR < P.min_data);
+            const float lcf = (float)nL, rcf = (float)nR;
+            float result = 0.0f;
+            if (PASS == 0) {
+                float lrec, rrec;
+                if (cand >= 0) { lrec = nL > 0 ? 1.0f / lcf : 0.0f; rrec = nR > 0 ? 1.0f / rcf : 0.0f; }
+                else { lrec = 1.0f / lcf; rrec = 0.0f; }   // parent: n_samples_recip = 1/n (split_candidate_generator.cpp:265,296)
+                float ln = 0.0f, rn = 0.0f, mean[2 * D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) { mean[d] = s_sum[d] * lrec; mean[D + d] = s_sum[D + d] * rrec; }
+#pragma unroll
+                for (int d = 0; d < D; ++d) { ln = ln + mean[d] * mean[d]; rn = rn + mean[D + d] * mean[D + d]; }   // squared_norm
+                if (P.score_func == GBRL_B200_SCORE_L2) {
+                    result = cand >= 0 ? (lcf * ln + rcf * rn) : (ln * lcf);
+                    P.out[it] = invalid ? -INFINITY : result;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 2 * D; ++i) Wd.fin[(size_t)it * 8 + i] = mean[i];
+                    Wd.fin[(size_t)it * 8 + 4] = ln; Wd.fin[(size_t)it * 8 + 5] = rn;
+                }
+            } else {
+                const float ln = Wd.fin[(size_t)it * 8 + 4], rn = Wd.fin[(size_t)it * 8 + 5];
+                const float fnum = s_sum[0], tnum = s_sum[1];
+                if (cand >= 0) {
+                    const float num = tnum + fnum;
+                    const float den = rn * rcf + ln * lcf;
+                    result = (den == 0.0f) ? 0.0f : num / sqrtf(den);
+                } else {
+                    const float den = ln * lcf;
+                    result = (n == 0 || den == 0.0f) ? 0.0f : fnum / sqrtf(den);
+                }
+                P.out[it] = invalid ? -INFINITY : result;
+            }
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && (n_fast | n_slow)) {
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_fast, (unsigned long long)n_fast);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_slow, (unsigned long long)n_slow);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_seq, (unsigned long long)n_seq);
+    }
+}
+
+template <int D>
+static void launch_wide_d(Model &m, const ReplayParams &R, const StreamParams &S, const WideParams &Wd, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    Ctl *ctl = ws.ctl.as<Ctl>();
+    const int grid = ws.n_sms * 8;
+    GB_LAUNCH((wide_bits_kernel<D>), grid, 256, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_prefix_kernel<D>), ws.n_sms * 4, 256, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_tabs_kernel<D, 0>), grid, 256, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_walk_kernel<D, 0>), ws.n_sms * 8, 32 * 2 * D, 0, s, R, ws.na, S, Wd, ctl);
+    if (m.cfg.split_score_func != GBRL_B200_SCORE_L2) {
+        GB_LAUNCH((wide_tabs_kernel<D, 1>), grid, 256, 0, s, R, ws.na, S, Wd);
+        GB_LAUNCH((wide_walk_kernel<D, 1>), ws.n_sms * 8, 32 * 2 * D, 0, s, R, ws.na, S, Wd, ctl);
+    }
+}
+
+void launch_replay_wide(Model &m, const ReplayParams &R, const StreamParams &S, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    WideParams Wd;
+    const size_t ng = (size_t)ws.rwide_groups, D2 = (size_t)2 * ws.D;
+    char *p = ws.rwide.as<char>();
+    Wd.bsum = reinterpret_cast<double *>(p); p += ng * D2 * sizeof(double);
+    Wd.tab = reinterpret_cast<int4 *>(p); p += ng * D2 * sizeof(int4);
+    Wd.pred = reinterpret_cast<float *>(p); p += ng * D2 * sizeof(float);
+    Wd.tag = reinterpret_cast<float *>(p); p += ng * D2 * sizeof(float);
+    Wd.gitem = reinterpret_cast<int *>(p); p += ng * sizeof(int);
+    Wd.fin = reinterpret_cast<float *>(p);
+    Wd.cap_groups = (long long)ng;
+    if (ws.D == 1) launch_wide_d<1>(m, R, S, Wd, s);
+    else launch_wide_d<2>(m, R, S, Wd, s);
+}
+
+}  // namespace gb

@@ -19,6 +19,7 @@
 //      reference's chain of float operations, so the chosen split is the reference's, bit for bit.
 #include "engine.cuh"
 #include "chain.cuh"
+#include "replay.cuh"
 #include <cfloat>
 #include <climits>
 
@@ -438,16 +439,6 @@ __global__ void __launch_bounds__(256) obl_select_kernel(OblParams P, NodeArrays
 }
 
 // ---------------------------------------------------------------- replay: the reference's own arithmetic
-struct ReplayParams {
-    int F, B, D, score_func, min_data;
-    const float *X;            // raw features, row-major
-    const float *bg;           // build_grads
-    const int *order;
-    const float *thr;
-    const ReplayItem *items;
-    float *out;
-    const Ctl *ctl;
-};
 
 // One 128-thread CTA per item.  Rows of the node are visited in ascending sample order (== reference
 // sample_indices).  The chain itself is inherently sequential (every float add depends on the previous one), so
@@ -918,16 +909,6 @@ __global__ void __launch_bounds__(512, 1) replay_par_kernel(ReplayParams P, Node
 //   replay_gather_kernel  order-space copy of build_grads for the rows of every node that has replay items
 //   replay_bits_kernel    side bit (x > threshold, node.cpp:339) of every (item, row), 32 rows per word, + right counts
 //   replay_stream_kernel  the chains (chain.cuh) over the streams; same arithmetic as replay_par_kernel
-struct StreamParams {
-    float *G;                  // [N x D] build_grads in `order` space
-    unsigned int *bits;        // side-bit planes
-    int *woff;                 // [n_items + 1] word offset of the item's plane (prefix; parents / direct items have 0 words)
-    int *mode;                 // [n_items] 0 = streamed, 1 = parent (no plane), 2 = direct (plane did not fit)
-    int *nright;               // [n_items]
-    long long cap_words;
-    int replay_cap, N, oblivious;
-    const int *nid;
-};
 
 __global__ void __launch_bounds__(1024) replay_plan_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
     __shared__ int s_scan[1024];
@@ -940,7 +921,7 @@ __global__ void __launch_bounds__(1024) replay_plan_kernel(ReplayParams P, NodeA
         int words = 0, md = 1;
         if (it < n_items) {
             const ReplayItem item = P.items[it];
-            if (item.cand >= 0) { words = ((na.seg_len[item.node] + 255) >> 8) << 3; md = 0; }   // 8-word groups
+            if (item.cand >= 0 || S.wide) { words = ((na.seg_len[item.node] + 255) >> 8) << 3; md = 0; }   // 8-word groups
         }
         s_scan[threadIdx.x] = words;
         __syncthreads();
@@ -1383,8 +1364,16 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
             S.mode = S.woff + ws.replay_cap + 1; S.nright = S.mode + ws.replay_cap;
             S.cap_words = ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
             S.nid = ws.nid.as<int>();
+            S.wide = (D <= 2 && m.cfg.replay_variant == 0) ? 1 : 0;
             GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
             GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
+            if (S.wide) {
+                // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
+                launch_replay_wide(m, R, S, s);
+                if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                else GB_LAUNCH((replay_par_kernel<2>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                return;
+            }
             GB_LAUNCH(replay_bits_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
             if (D <= 1) {
                 launch_stream<1>(R, ws.na, S, ctl, s);

@@ -83,7 +83,7 @@ class GBRL:
                  par_th=10, cv_beta=0.9, split_score_func="cosine", generator_type="quantile",
                  use_control_variates=False, batch_size=5000, grow_policy="greedy", verbose=0, device="cuda",
                  learner_name="GBRL", ref_threads=None, tie_replay=True, band_kappa=0.0, use_subtraction=True,
-                 device_ordinal=None, hist_variant=0):
+                 device_ordinal=None, hist_variant=0, replay_variant=0):
         if isinstance(input_dim, GBRL):                       # copy constructor, binding.cpp:441
             self._init_from(input_dim)
             return
@@ -105,7 +105,7 @@ class GBRL:
                         verbose=int(verbose), device="cuda", learner_name=learner_name,
                         ref_threads=int(ref_threads if ref_threads else (os.cpu_count() or 1)),
                         tie_replay=bool(tie_replay), band_kappa=float(band_kappa), use_subtraction=bool(use_subtraction),
-                        device_ordinal=int(device_ordinal), hist_variant=int(hist_variant))
+                        device_ordinal=int(device_ordinal), hist_variant=int(hist_variant), replay_variant=int(replay_variant))
         self._create()
 
     # ------------------------------------------------------------------ lifetime
@@ -115,7 +115,7 @@ class GBRL:
                            k["n_bins"], k["par_th"], k["batch_size"], _enum(_SCORE, k["split_score_func"], "split_score_func"),
                            _enum(_GEN, k["generator_type"], "generator_type"), _enum(_GROW, k["grow_policy"], "grow_policy"),
                            k["verbose"], k["device_ordinal"], k["ref_threads"], 1 if k["tie_replay"] else 0,
-                           k["band_kappa"], 1 if k["use_subtraction"] else 0, k.get("hist_variant", 0))
+                           k["band_kappa"], 1 if k["use_subtraction"] else 0, k.get("hist_variant", 0), k.get("replay_variant", 0))
         h = C.c_void_p()
         _capi.check(self._lib.gbrl_b200_create(C.byref(cfg), C.byref(h)))
         self._h = h

@@ -58,6 +58,7 @@ typedef struct {
     float band_kappa;       /* band = kappa * 2^-24 * sqrt(n_node) * |score|; <=0 -> default 8 */
     int use_subtraction;    /* 1: histogram only the smaller child, derive the sibling from the parent */
     int hist_variant;       /* 0: streaming histogram kernel (cp.async row ring, carried shared histogram); 1: per-item kernel */
+    int replay_variant;     /* 0: replay chains spread over the whole GPU where output_dim <= 2; 1: one CTA per replay item */
 } gbrl_b200_config;
 
 typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine statistics */
