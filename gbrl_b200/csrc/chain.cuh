@@ -178,6 +178,35 @@ __device__ __forceinline__ float warp_seq_lanes(float acc, const float (&x)[KE],
     return acc;
 }
 
+// The plain sequential float chain over a whole block (lanes l0 .. 31), staged through a warp-private shared buffer of
+// 32 * KE floats so that every add is fed by broadcast LDS.128 loads issued 16 elements ahead: ~4.5 cycles per element,
+// the speed of the dependent FADD chain itself.  A lone warp cannot do better on a block in which the running sum
+// keeps crossing a power of two (its instruction latency makes every summarise-and-check attempt cost more than that).
+template <int KE>
+__device__ __forceinline__ float warp_seq_block(float acc, const float (&x)[KE], float *wbuf, int &n_seq, int l0 = 0) {
+    static_assert(KE % 8 == 0, "warp_seq_block: 8 elements per step");
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < KE; i += 4)
+        *reinterpret_cast<float4 *>(wbuf + lane * KE + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+    __syncwarp();
+    const float4 *p = reinterpret_cast<const float4 *>(wbuf + l0 * KE);
+    const int n8 = (32 - l0) * (KE / 8);                 // steps of 8 elements
+    float4 a0 = p[0], a1 = p[1];
+#pragma unroll 4
+    for (int j = 0; j < n8; ++j) {
+        float4 b0 = a0, b1 = a1;
+        if (j + 1 < n8) { b0 = p[2 * j + 2]; b1 = p[2 * j + 3]; }
+        acc = acc + a0.x; acc = acc + a0.y; acc = acc + a0.z; acc = acc + a0.w;
+        acc = acc + a1.x; acc = acc + a1.y; acc = acc + a1.z; acc = acc + a1.w;
+        a0 = b0; a1 = b1;
+    }
+    n_seq += 32 - l0;
+    __syncwarp();
+    return acc;
+}
+
 template <int KE>
 __device__ __forceinline__ float warp_advance(float acc, const float (&x)[KE], int &n_seq) {
     const unsigned int full = 0xffffffffu;

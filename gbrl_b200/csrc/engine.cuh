@@ -98,6 +98,7 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
     DevBuf rgrad, rbits, rmeta;          // replay streams: order-space build_grads, side-bit planes, per-item offsets / modes / counts
     long long rbits_words = 0;
+    DevBuf dwide;                        // GPU-wide evaluation of the mean / std chains (preprocess.cu)
     DevBuf rwide;                        // GPU-wide replay: per-group sums / predictions / summaries / tags, per-item hand-over
     long long rwide_groups = 0;
     DevBuf pair_first, pair_nitems, pl_count, pl_ids, partials;   // histogram pairs (node x local tile) and staged partials

@@ -168,6 +168,252 @@ dense_chain_kernel(float *mat, const float *mean, float *partial, long long n_el
     }
 }
 
+// One WARP per (reference thread, column) chain: 256 chain elements per step (8 consecutive per lane), summarised in the
+// binade of the running sum and applied in one integer add, or advanced piecewise where the sum leaves its binade
+// (chain.cuh warp_advance).  No barriers: for chains up to a few hundred thousand elements this beats the CTA pipeline
+// above, in particular when the sum hovers around a power of two (zero-mean gradients).
+template <int MODE>
+__global__ void __launch_bounds__(32)
+warp_chain_kernel(float *mat, const float *mean, float *partial, long long n_elements, int D, int T, long long *stats) {
+    const int t = blockIdx.x / D, col = blockIdx.x - t * D, lane = threadIdx.x;
+    const long long ept = n_elements / T;
+    const long long s = (long long)t * ept, e = (t == T - 1) ? n_elements : s + ept;
+    const long long first = s + ((col - (s % D)) + D) % D;       // first element of column `col` at or after s
+    const long long cnt = first < e ? (e - first + D - 1) / D : 0;
+    const float mu = MODE == 1 ? mean[col] : 0.0f;
+    auto load = [&](long long blk, float (&x)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long j = blk * 256 + lane * 8 + i;
+            float v = 0.0f;
+            if (j < cnt) {
+                const long long idx = first + j * D;
+                const float raw = mat[idx];
+                if (MODE == 1) {
+                    const float c = raw - mu;
+                    mat[idx] = c;
+                    v = c * c;
+                } else v = raw;
+            }
+            x[i] = v;
+        }
+    };
+    float acc = 0.0f;
+    int n_seq = 0;
+    const long long n_blk = (cnt + 255) / 256;
+    // four blocks in flight (a lone warp per SM has nothing else to hide the load latency behind)
+    float xa[8], xb[8], xc[8], xd[8];
+    load(0, xa); load(1, xb); load(2, xc); load(3, xd);
+    for (long long b = 0; b < n_blk; b += 4) {
+        acc = seq::warp_advance<8>(acc, xa, n_seq); load(b + 4, xa);
+        if (b + 1 < n_blk) { acc = seq::warp_advance<8>(acc, xb, n_seq); load(b + 5, xb); }
+        if (b + 2 < n_blk) { acc = seq::warp_advance<8>(acc, xc, n_seq); load(b + 6, xc); }
+        if (b + 3 < n_blk) { acc = seq::warp_advance<8>(acc, xd, n_seq); load(b + 7, xd); }
+    }
+    if (lane == 0) {
+        partial[(size_t)t * D + col] = acc;
+        if (stats) { atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_blk); atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_seq); }
+    }
+}
+
+// ---------------------------------------------------------------- the same chains, summaries by the whole GPU
+// (the scheme of replay_wide.cu for dense chains)  chain = (reference thread t, column), 256 chain elements per group:
+//   wide_dense_sums_kernel  per-group fp64 sums (prediction only); mode 1 also centres the matrix in place
+//   wide_dense_tabs_kernel  (after a per-chain prefix of those sums) group summaries for the predicted binade, tagged
+//   wide_dense_walk_kernel  one warp per chain composes 32 summaries at a time while tag and range check hold for the
+//                           ACTUAL running sum, any other group is advanced piecewise (warp_advance)
+struct DenseWide {
+    float *mat; const float *mean; float *partial;
+    long long n_elements; int D, T, mode;
+    double *bsum; float *pred; int4 *tab; float *tag;      // [chains][gmax]
+    int gmax;
+};
+constexpr float DW_EMPTY = -1.0f;
+
+struct DenseChain { long long first, cnt; int ng; };
+__device__ __forceinline__ DenseChain dense_chain_of(const DenseWide &P, int chain) {
+    const int t = chain / P.D, col = chain - t * P.D;
+    const long long ept = P.n_elements / P.T;
+    const long long s = (long long)t * ept, e = (t == P.T - 1) ? P.n_elements : s + ept;
+    DenseChain c;
+    c.first = s + ((col - (s % P.D)) + P.D) % P.D;
+    c.cnt = c.first < e ? (e - c.first + P.D - 1) / P.D : 0;
+    c.ng = (int)((c.cnt + 255) / 256);
+    return c;
+}
+// the lane's 8 consecutive chain elements of group g (mode 1: squares of the already centred values)
+__device__ __forceinline__ void dense_group(const DenseWide &P, const DenseChain &c, int g, float (&x)[8]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long j = (long long)g * 256 + lane * 8 + i;
+        float v = 0.0f;
+        if (j < c.cnt) { v = P.mat[c.first + j * P.D]; if (P.mode == 1) v = v * v; }
+        x[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) wide_dense_sums_kernel(DenseWide P) {
+    const int lane = threadIdx.x & 31;
+    const int n_chains = P.T * P.D;
+    const long long total = (long long)n_chains * P.gmax;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total; u += warps) {
+        const int chain = (int)(u / P.gmax), g = (int)(u - (long long)chain * P.gmax);
+        const DenseChain c = dense_chain_of(P, chain);
+        if (g >= c.ng) continue;
+        const float mu = P.mode == 1 ? P.mean[chain % P.D] : 0.0f;
+        double sum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long j = (long long)g * 256 + i * 32 + lane;           // coalesced order; only the sum matters here
+            if (j < c.cnt) {
+                const long long idx = c.first + j * P.D;
+                float v = P.mat[idx];
+                if (P.mode == 1) { v = v - mu; P.mat[idx] = v; v = v * v; }    // math_ops.cpp:480-500: centre, then square
+                sum += (double)v;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            int lo = __double2loint(sum), hi = __double2hiint(sum);
+            lo = __shfl_xor_sync(0xffffffffu, lo, o); hi = __shfl_xor_sync(0xffffffffu, hi, o);
+            sum += __hiloint2double(hi, lo);
+        }
+        if (lane == 0) P.bsum[(size_t)chain * P.gmax + g] = sum;
+    }
+}
+
+// one warp per chain: exclusive prefix of the group sums
+__global__ void __launch_bounds__(32) wide_dense_prefix_kernel(DenseWide P) {
+    const int chain = blockIdx.x, lane = threadIdx.x;
+    const DenseChain c = dense_chain_of(P, chain);
+    double carry = 0.0;
+    for (int g0 = 0; g0 < c.ng; g0 += 32) {
+        const int g = g0 + lane;
+        const double v = g < c.ng ? P.bsum[(size_t)chain * P.gmax + g] : 0.0;
+        double inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int lo = __double2loint(inc), hi = __double2hiint(inc);
+            lo = __shfl_up_sync(0xffffffffu, lo, o); hi = __shfl_up_sync(0xffffffffu, hi, o);
+            if (lane >= o) inc += __hiloint2double(hi, lo);
+        }
+        if (g < c.ng) P.pred[(size_t)chain * P.gmax + g] = (float)(carry + inc - v);
+        int lo = __double2loint(inc), hi = __double2hiint(inc);
+        lo = __shfl_sync(0xffffffffu, lo, 31); hi = __shfl_sync(0xffffffffu, hi, 31);
+        carry += __hiloint2double(hi, lo);
+    }
+}
+
+__global__ void __launch_bounds__(256) wide_dense_tabs_kernel(DenseWide P) {
+    const int lane = threadIdx.x & 31;
+    const int n_chains = P.T * P.D;
+    const long long total = (long long)n_chains * P.gmax;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total; u += warps) {
+        const int chain = (int)(u / P.gmax), g = (int)(u - (long long)chain * P.gmax);
+        const DenseChain c = dense_chain_of(P, chain);
+        if (g >= c.ng) continue;
+        float x[8];
+        dense_group(P, c, g, x);
+        bool nz = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nz |= (x[i] != 0.0f) || (x[i] != x[i]);
+        float inv_u, uu;
+        const bool ok = seq::epoch_of(P.pred[(size_t)chain * P.gmax + g], inv_u, uu);
+        float tagv = ok ? inv_u : 0.0f;
+        if (!__any_sync(0xffffffffu, nz)) {
+            tagv = DW_EMPTY;
+            if (lane == 0) P.tab[(size_t)chain * P.gmax + g] = make_int4(0, 0, 0, 0);
+        } else if (ok) {
+            const seq::Tab tb = seq::warp_summarize<8>(x, inv_u);
+            if (lane == 0) P.tab[(size_t)chain * P.gmax + g] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+        }
+        if (lane == 0) P.tag[(size_t)chain * P.gmax + g] = tagv;
+    }
+}
+
+__global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long long *stats) {
+    __shared__ __align__(16) float s_wbuf[256];
+    const unsigned int full = 0xffffffffu;
+    const int chain = blockIdx.x, lane = threadIdx.x;
+    const DenseChain c = dense_chain_of(P, chain);
+    const size_t base = (size_t)chain * P.gmax;
+    float acc = 0.0f;
+    int n_fast = 0, n_slow = 0, n_seq = 0;
+    int4 qnx = make_int4(0, 0, 0, 0);
+    float tgnx = 0.0f;
+    if (lane < c.ng) { qnx = P.tab[base + lane]; tgnx = P.tag[base + lane]; }
+#pragma unroll 1
+    for (int w0 = 0; w0 < c.ng; w0 += 32) {
+        const bool in_range = w0 + lane < c.ng;
+        const int wn = min(32, c.ng - w0);
+        const int4 q = qnx;
+        const float tg = tgnx;
+        if (w0 + 32 + lane < c.ng) { qnx = P.tab[base + w0 + 32 + lane]; tgnx = P.tag[base + w0 + 32 + lane]; }
+        int first = 0, have = -1;
+        float xn[8];
+#pragma unroll 1
+        while (first < wn) {
+            // longest applicable prefix of the window from `first` (same logic as replay_wide.cu compose_window)
+            float inv_u, u;
+            int take = 0;
+            const bool live = lane >= first;
+            if (!seq::epoch_of(acc, inv_u, u)) {
+                const unsigned int stop = __ballot_sync(full, live && !(in_range && tg == DW_EMPTY));
+                take = (stop ? (__ffs(stop) - 1) : 32) - first;
+            } else {
+                const bool empty = in_range && tg == DW_EMPTY;
+                const bool tag_ok = in_range && (tg == inv_u || empty);
+                int i0 = (tag_ok && live) ? q.x : 0, i1 = (tag_ok && live) ? q.y : 0;
+                if (!__any_sync(full, i0 != i1)) {
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) { const int g0 = __shfl_up_sync(full, i0, off); if (lane >= off) i0 += g0; }
+                    i1 = i0;
+                } else {
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int g0 = __shfl_up_sync(full, i0, off), g1 = __shfl_up_sync(full, i1, off);
+                        if (lane >= off) {
+                            const int n0 = g0 + ((g0 & 1) ? i1 : i0), n1 = g1 + (((g1 + 1) & 1) ? i1 : i0);
+                            i0 = n0; i1 = n1;
+                        }
+                    }
+                }
+                int e0 = __shfl_up_sync(full, i0, 1);
+                if (lane == 0) e0 = 0;
+                const int m = (int)(acc * inv_u);
+                const int lo = (1 << 23) + seq::MARGIN, hi = (1 << 24) - seq::MARGIN;
+                const int b = m + e0;
+                const bool okw = !live || empty || (tag_ok && (m > 0 ? (b + q.z > lo && b + q.w < hi) : (b + q.w < -lo && b + q.z > -hi)));
+                const unsigned int bad = __ballot_sync(full, !okw);
+                take = (bad ? (__ffs(bad) - 1) : 32) - first;
+                if (take > 0) {
+                    const int inc0 = __shfl_sync(full, i0, first + take - 1), inc1 = __shfl_sync(full, i1, first + take - 1);
+                    acc = (float)(m + ((m & 1) ? inc1 : inc0)) * u;
+                }
+            }
+            if (take > 0) { n_fast += take; first += take; }
+            if (first >= wn) break;
+            float x[8];
+            if (have == first) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = xn[i];
+            } else dense_group(P, c, w0 + first, x);
+            if (w0 + first + 1 < c.ng) { dense_group(P, c, w0 + first + 1, xn); have = first + 1; }
+            acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
+            ++n_slow; ++first;
+        }
+    }
+    if (lane == 0) {
+        P.partial[chain] = acc;
+        if (stats) {
+            atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_fast);
+            atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_slow);
+            atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_seq);
+        }
+    }
+}
+
 constexpr size_t DC_SMEM = (size_t)3 * DC_THREADS * 8 * sizeof(float);
 
 template <int D>
@@ -177,13 +423,32 @@ static void launch_dense(float *mat, const float *mean, float *partial, long lon
     GB_LAUNCH(dense_chain_kernel<D>, T, DC_THREADS, DC_SMEM, s, mat, mean, partial, ne, T, mode, stats);
 }
 
-static void launch_ref_chain(float *mat, const float *mean, float *partial, long long ne, int D, int T, int mode, cudaStream_t s,
-                             long long *stats = nullptr) {
-    if (D == 1) launch_dense<1>(mat, mean, partial, ne, T, mode, s, stats);
-    else if (D == 2) launch_dense<2>(mat, mean, partial, ne, T, mode, s, stats);
-    else if (D == 3) launch_dense<3>(mat, mean, partial, ne, T, mode, s, stats);
-    else if (D == 4) launch_dense<4>(mat, mean, partial, ne, T, mode, s, stats);
-    else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, s, mat, mean, partial, ne, D, T, mode);
+static void launch_ref_chain(Model *m, float *mat, const float *mean, float *partial, long long ne, int D, int T, int mode,
+                             cudaStream_t s, long long *stats = nullptr) {
+    if (ne <= 0) { GB_CUDA(cudaMemsetAsync(partial, 0, (size_t)T * D * sizeof(float), s)); return; }
+    // GPU-wide summaries + one walking warp per chain
+    static DevBuf fallback_scratch;                        // diag path (no model workspace)
+    DevBuf &scratch = m ? m->ws.dwide : fallback_scratch;
+    DenseWide P;
+    P.mat = mat; P.mean = mean; P.partial = partial; P.n_elements = ne; P.D = D; P.T = T; P.mode = mode;
+    const long long ept = ne / T;
+    const long long longest = (ne - (long long)(T - 1) * ept + D - 1) / D + 1;      // the last thread takes the remainder
+    P.gmax = (int)((longest + 255) / 256) + 1;
+    const size_t per = (size_t)T * D * P.gmax;
+    scratch.ensure(per * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)));
+    char *p = scratch.as<char>();
+    P.tab = reinterpret_cast<int4 *>(p); p += per * sizeof(int4);       // 16-byte entries first (alignment)
+    P.bsum = reinterpret_cast<double *>(p); p += per * sizeof(double);
+    P.pred = reinterpret_cast<float *>(p); p += per * sizeof(float);
+    P.tag = reinterpret_cast<float *>(p);
+    long long units = (long long)per;
+    int grid = (int)((units + 7) / 8);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    GB_LAUNCH(wide_dense_sums_kernel, grid, 256, 0, s, P);
+    GB_LAUNCH(wide_dense_prefix_kernel, T * D, 32, 0, s, P);
+    GB_LAUNCH(wide_dense_tabs_kernel, grid, 256, 0, s, P);
+    GB_LAUNCH(wide_dense_walk_kernel, T * D, 32, 0, s, P, stats);
 }
 
 // test hook: thread-partitioned chain sums of a host matrix through launch_ref_chain (impl 0) or the one-thread-per-
@@ -200,7 +465,17 @@ void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode
     GB_CUDA(cudaEventCreate(&e0)); GB_CUDA(cudaEventCreate(&e1));
     GB_CUDA(cudaDeviceSynchronize());
     GB_CUDA(cudaEventRecord(e0, 0));
-    if (impl == 0) launch_ref_chain(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode, 0, stats.as<long long>());
+    if (impl == 0) launch_ref_chain(nullptr, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode, 0, stats.as<long long>());
+    else if (impl == 2) {                                  // the one-CTA-per-chain pipeline (chains of output_dim <= 4)
+        if (D == 1) launch_dense<1>(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, T, mode, 0, stats.as<long long>());
+        else if (D == 2) launch_dense<2>(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, T, mode, 0, stats.as<long long>());
+        else if (D == 3) launch_dense<3>(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, T, mode, 0, stats.as<long long>());
+        else if (D == 4) launch_dense<4>(mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, T, mode, 0, stats.as<long long>());
+        else throw Error("diag_chain_sums: impl 2 needs D <= 4");
+    } else if (impl == 3) {                                // one warp per chain, no summaries
+        if (mode == 0) GB_LAUNCH(warp_chain_kernel<0>, T * D, 32, 0, 0, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, stats.as<long long>());
+        else GB_LAUNCH(warp_chain_kernel<1>, T * D, 32, 0, 0, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, stats.as<long long>());
+    }
     else GB_LAUNCH(ref_chain_kernel, ceil_div(T, 4), 128, 0, 0, mat.as<float>(), mean.as<float>(), partial.as<float>(), ne, D, T, mode);
     GB_CUDA(cudaEventRecord(e1, 0));
     GB_CUDA(cudaDeviceSynchronize());
@@ -281,7 +556,7 @@ void column_mean_ref(Model &m, const float *mat, int N, int D, float *out_dev, c
     const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
     ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
     float *partial = ws.lrs.as<float>();
-    launch_ref_chain(const_cast<float *>(mat), nullptr, partial, ne, D, T, 0, s);
+    launch_ref_chain(&m, const_cast<float *>(mat), nullptr, partial, ne, D, T, 0, s);
     GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, out_dev, D, T, N, 0);
 }
 
@@ -300,9 +575,9 @@ void build_grads(Model &m, const float *grads, int N, cudaStream_t s) {
         const int T = calc_threads(ne, m.cfg.par_th, m.cfg.ref_threads);
         ws.lrs.ensure((size_t)(T * D + 2 * D) * sizeof(float));
         float *partial = ws.lrs.as<float>(), *mean = partial + (size_t)T * D, *stdv = mean + D;
-        launch_ref_chain(ws.bg.as<float>(), nullptr, partial, ne, D, T, 0, s);
+        launch_ref_chain(&m, ws.bg.as<float>(), nullptr, partial, ne, D, T, 0, s);
         GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, mean, D, T, N, 0);
-        launch_ref_chain(ws.bg.as<float>(), mean, partial, ne, D, T, 1, s);
+        launch_ref_chain(&m, ws.bg.as<float>(), mean, partial, ne, D, T, 1, s);
         GB_LAUNCH(ref_merge_kernel, ceil_div(D, 64), 64, 0, s, partial, stdv, D, T, N, 1);
         GB_LAUNCH(divide_and_max_kernel, grid, 256, 0, s, ws.bg.as<float>(), stdv, ctl, ne, D, 1, 0);
     } else if (ne > 0) {

@@ -17,6 +17,7 @@
 namespace gb {
 
 constexpr int GROUP_ROWS = 256;
+constexpr float TAG_EMPTY = -1.0f;     // tag of a group in which the chain has no element: applicable to any running sum
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -192,13 +193,21 @@ __global__ void __launch_bounds__(256) wide_tabs_kernel(ReplayParams P, NodeArra
             }
             float inv_u, u;
             const bool ok = seq::epoch_of(pr, inv_u, u);
-            if (ok) {
-                float x[KE];
-                chain_elems<D, PASS>(v, mb, c, smean, x);
+            float x[KE];
+            chain_elems<D, PASS>(v, mb, c, smean, x);
+            bool nz = false;
+#pragma unroll
+            for (int i = 0; i < KE; ++i) nz |= (x[i] != 0.0f) || (x[i] != x[i]);
+            const bool empty = !__any_sync(0xffffffffu, nz);          // the chain has no (non-zero) element in this group
+            float tagv = ok ? inv_u : 0.0f;
+            if (empty) {
+                tagv = TAG_EMPTY;
+                if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(0, 0, 0, 0);
+            } else if (ok) {
                 const seq::Tab tb = seq::warp_summarize<KE>(x, inv_u);
                 if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
             }
-            if (lane == 0) Wd.tag[(size_t)g * 2 * D + c] = ok ? inv_u : 0.0f;
+            if (lane == 0) Wd.tag[(size_t)g * 2 * D + c] = tagv;
         }
     }
 }
@@ -208,9 +217,14 @@ __device__ __forceinline__ int compose_window(float &acc, const int4 q, float tg
     const unsigned int full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     float inv_u, u;
-    if (!seq::epoch_of(acc, inv_u, u)) return 0;
     const bool live = lane >= first;                      // lanes before `first` are consumed already
-    const bool tag_ok = in_range && tg == inv_u;
+    if (!seq::epoch_of(acc, inv_u, u)) {
+        // no binade yet (acc == 0): only groups without elements can be skipped
+        const unsigned int stop = __ballot_sync(full, live && !(in_range && tg == TAG_EMPTY));
+        return (stop ? (__ffs(stop) - 1) : 32) - first;
+    }
+    const bool empty = in_range && tg == TAG_EMPTY;
+    const bool tag_ok = in_range && (tg == inv_u || empty);
     int i0 = (tag_ok && live) ? q.x : 0, i1 = (tag_ok && live) ? q.y : 0;
     if (!__any_sync(full, i0 != i1)) {
 #pragma unroll
@@ -235,7 +249,7 @@ __device__ __forceinline__ int compose_window(float &acc, const int4 q, float tg
     const int m = (int)(acc * inv_u);
     const int lo = (1 << 23) + seq::MARGIN, hi = (1 << 24) - seq::MARGIN;
     const int b = m + e0;
-    const bool okw = !live || (tag_ok && (m > 0 ? (b + q.z > lo && b + q.w < hi) : (b + q.w < -lo && b + q.z > -hi)));
+    const bool okw = !live || empty || (tag_ok && (m > 0 ? (b + q.z > lo && b + q.w < hi) : (b + q.w < -lo && b + q.z > -hi)));
     const unsigned int bad = __ballot_sync(full, !okw);
     const int take = (bad ? (__ffs(bad) - 1) : 32) - first;   // groups first .. first + take - 1 of the window are applied
     if (take <= 0) return 0;
@@ -251,6 +265,7 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
     constexpr int KE = PASS == 0 ? 8 : 8 * D;
     __shared__ float s_sum[2 * D];
     __shared__ float s_mean[2 * D];
+    __shared__ __align__(16) float s_wbuf[NCH][32 * KE];       // per chain warp: staging of a block that is run sequentially
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
     if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
@@ -271,13 +286,16 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
         if (warp < NCH) {
             const int c = warp;
             float acc = 0.0f;
+            int4 qnx = make_int4(0, 0, 0, 0);              // the next window's summaries / tags, loaded a window ahead
+            float tgnx = 0.0f;
+            if (lane < ng) { qnx = Wd.tab[(base + lane) * 2 * D + c]; tgnx = Wd.tag[(base + lane) * 2 * D + c]; }
 #pragma unroll 1
             for (int w0 = 0; w0 < ng; w0 += 32) {          // window of 32 groups, lane = group
                 const bool in_range = w0 + lane < ng;
                 const int wn = min(32, ng - w0);
-                int4 q = make_int4(0, 0, 0, 0);
-                float tg = 0.0f;
-                if (in_range) { q = Wd.tab[(base + w0 + lane) * 2 * D + c]; tg = Wd.tag[(base + w0 + lane) * 2 * D + c]; }
+                const int4 q = qnx;
+                const float tg = tgnx;
+                if (w0 + 32 + lane < ng) { qnx = Wd.tab[(base + w0 + 32 + lane) * 2 * D + c]; tgnx = Wd.tag[(base + w0 + 32 + lane) * 2 * D + c]; }
                 int first = 0;
                 float vn[8 * D];                           // rows of the group after a failed one, fetched while that one is advanced
                 unsigned int mbn = 0u;
@@ -298,7 +316,7 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
                     } else group_rows<D>(G, W, n, w0 + first, v, mb);
                     if (w0 + first + 1 < ng) { group_rows<D>(G, W, n, w0 + first + 1, vn, mbn); have = first + 1; }
                     chain_elems<D, PASS>(v, mb, c, s_mean, x);
-                    acc = seq::warp_advance<KE>(acc, x, n_seq);
+                    acc = seq::warp_seq_block<KE>(acc, x, s_wbuf[c], n_seq);
                     ++n_slow; ++first;
                 }
             }

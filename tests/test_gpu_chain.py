@@ -74,10 +74,15 @@ def test_parallel_chain_is_bit_identical_to_sequential(kind, D, T, n):
     for mode in (0, 1):
         mean = mat.mean(axis=0).astype(np.float32) if mode == 1 else None
         want, want_c = _seq_partials(mat, D, T, mode, mean)
-        got, got_c = _gpu_partials(mat, D, T, mode, mean)
-        assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (kind, D, T, mode, want, got)
-        if mode == 1:
-            assert np.array_equal(want_c.view(np.uint32), got_c.view(np.uint32))
+        # impl 0: summaries by the whole GPU + one walking warp per chain (the product path); 2: one CTA per chain
+        # (D <= 4); 3: one warp per chain
+        for impl in (0, 2, 3):
+            if impl == 2 and D > 4:
+                continue
+            got, got_c = _gpu_partials(mat, D, T, mode, mean, impl=impl)
+            assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), (kind, D, T, mode, impl, want, got)
+            if mode == 1:
+                assert np.array_equal(want_c.view(np.uint32), got_c.view(np.uint32))
 
 
 def test_parallel_chain_nonfinite_and_short():

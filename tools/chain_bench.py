@@ -16,7 +16,7 @@ for kind in ("walk", "drift", "sparse", "squares", "grad"):
         else:
             mat = _data(kind, n, D, rng)
         info = np.zeros(4)
-        for impl in (0, 1):
+        for impl in (0, 2, 3, 1):
             _gpu_partials(mat, D, T, 0, None, impl=impl, info=info)      # warm
             _gpu_partials(mat, D, T, 0, None, impl=impl, info=info)
             print("%-8s n=%d D=%d T=%d impl=%d: %.3f ms  fast %d adv %d seq_lanes %d" % (kind, n, D, T, impl, info[0], info[1], info[2], info[3]), flush=True)

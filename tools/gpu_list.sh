@@ -3,5 +3,5 @@
 mkdir -p gpurun_out
 W=${WORKLOAD:-c2}
 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:gb:: -c 2400 --csv \
-    --log-file gpurun_out/launches_$W.csv python bench.py --workload $W --steps 2 --warmup 1 --no-e2e --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/ncu_list.log 2>&1
+    --log-file gpurun_out/launches_$W.csv python bench.py --workload $W --steps ${LIST_STEPS:-2} --warmup 1 --no-e2e --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"; tail -1 gpurun_out/ncu_list.log | cut -c1-1500
