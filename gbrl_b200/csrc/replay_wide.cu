@@ -25,7 +25,8 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     return __hiloint2double(hi, lo);
 }
 
-// one warp per 8-word group (256 rows) of a plane
+// A warp owns a contiguous range of 8-word groups (256 rows each) of the planes: the item of the first group is
+// found by one binary search, after that the item index only moves forward.
 template <int D>
 __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
@@ -33,22 +34,38 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
     const int lane = threadIdx.x & 31;
     const int total_groups = S.woff[n_items] >> 3;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_groups; g += warps) {
-        const int gw = g << 3;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int per = (total_groups + warps - 1) / warps;
+    const int g_begin = min(total_groups, wid * per), g_end = min(total_groups, g_begin + per);
+    if (g_begin >= g_end) return;
+    int it;
+    {
+        const int gw = g_begin << 3;
         int lo = 0, hi = n_items;                 // last item whose offset is <= gw
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (S.woff[mid] <= gw) lo = mid + 1; else hi = mid;
         }
-        const int it = lo - 1;
-        if (lane == 0) Wd.gitem[g] = S.mode[it] == 0 ? it : -1;
-        if (S.mode[it] != 0) continue;
-        const ReplayItem item = P.items[it];
-        const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
-        const bool is_cand = item.cand >= 0;
-        const int f = is_cand ? item.cand / P.B : 0;
-        const float tv = is_cand ? P.thr[item.cand] : INFINITY;
-        const int k0 = (gw - S.woff[it]) << 5;
+        it = lo - 1;
+    }
+    int it_loaded = -1, s0 = 0, n = 0, f = 0, woff_it = 0, md = 1;
+    bool is_cand = false;
+    float tv = INFINITY;
+    for (int g = g_begin; g < g_end; ++g) {
+        const int gw = g << 3;
+        while (it + 1 < n_items && S.woff[it + 1] <= gw) ++it;      // items without words share the offset of their successor
+        if (it != it_loaded) {
+            const ReplayItem item = P.items[it];
+            s0 = na.seg_start[item.node]; n = na.seg_len[item.node];
+            is_cand = item.cand >= 0;
+            f = is_cand ? item.cand / P.B : 0;
+            tv = is_cand ? P.thr[item.cand] : INFINITY;
+            woff_it = S.woff[it]; md = S.mode[it];
+            it_loaded = it;
+        }
+        if (lane == 0) Wd.gitem[g] = md == 0 ? it : -1;
+        if (md != 0) continue;
+        const int k0 = (gw - woff_it) << 5;
         int cnt = 0;
         float xv[8];
 #pragma unroll
@@ -56,9 +73,10 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
             const int k = k0 + j * 32 + lane;
             xv[j] = (k < n && is_cand) ? P.X[(size_t)P.order[s0 + k] * P.F + f] : -INFINITY;
         }
-        double sl[D], sr[D];
+        // group sums in fp32 (tree order); they only steer the binade prediction
+        float sl[D], sr[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) { sl[d] = 0.0; sr[d] = 0.0; }
+        for (int d = 0; d < D; ++d) { sl[d] = 0.0f; sr[d] = 0.0f; }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = k0 + j * 32 + lane;
@@ -69,7 +87,7 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
             if (k < n) {
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
-                    const double gv = (double)S.G[(size_t)(s0 + k) * D + d];
+                    const float gv = S.G[(size_t)(s0 + k) * D + d];
                     if (right) sr[d] += gv; else sl[d] += gv;
                 }
             }
@@ -77,11 +95,11 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
 #pragma unroll
         for (int d = 0; d < D; ++d) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { sl[d] += shfl_xor_d(sl[d], o); sr[d] += shfl_xor_d(sr[d], o); }
+            for (int o = 16; o > 0; o >>= 1) { sl[d] += __shfl_xor_sync(0xffffffffu, sl[d], o); sr[d] += __shfl_xor_sync(0xffffffffu, sr[d], o); }
         }
         if (lane == 0) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) { Wd.bsum[(size_t)g * 2 * D + d] = sl[d]; Wd.bsum[(size_t)g * 2 * D + D + d] = sr[d]; }
+            for (int d = 0; d < D; ++d) { Wd.bsum[(size_t)g * 2 * D + d] = (double)sl[d]; Wd.bsum[(size_t)g * 2 * D + D + d] = (double)sr[d]; }
             if (cnt) atomicAdd(&S.nright[it], cnt);
         }
     }
