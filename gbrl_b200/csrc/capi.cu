@@ -258,7 +258,12 @@ static void fit_iterate(Model &m, int iterations, cudaStream_t s) {
           multirmse_grads(m, preds, bT, grads, fs.batch_n, s);      // fitter.cpp:193-195
           build_grads(m, grads, fs.batch_n, s); }                   // fitter.cpp:203-214
         grow_tree(m, bX, grads, fs.batch_n, F, s);                  // fitter.cpp:220-225
-        if (fs.incremental) { ProfScope ps(m, P_PRED, s); launch_update_preds_last_tree(m, fs.X, N, F, ws.preds_full.as<float>(), s); }
+        if (fs.incremental) {
+            ProfScope ps(m, P_PRED, s);
+            // full batch: the rows still know the node they ended in; mini-batch: walk the new tree for all N rows
+            if (fs.batch_n == N) launch_update_preds_from_nodes(m, N, ws.preds_full.as<float>(), s);
+            else launch_update_preds_last_tree(m, fs.X, N, F, ws.preds_full.as<float>(), s);
+        }
         fs.batch_start += fs.batch_n;                               // fitter.cpp:227-230
         if (fs.batch_start >= N) fs.batch_start = 0;
         fs.batch_n = fs.batch_start + bs < N ? bs : N - fs.batch_start;

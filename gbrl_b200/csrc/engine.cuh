@@ -188,6 +188,7 @@ void ensure_ensemble_capacity(Model &m, int extra_trees, cudaStream_t s);
 void launch_predict(Model &m, const float *X, int N, int F, int start_tree, int stop_tree, float *preds, bool add_bias,
                     cudaStream_t s);
 void launch_update_preds_last_tree(Model &m, const float *X, int N, int F, float *preds, cudaStream_t s);
+void launch_update_preds_from_nodes(Model &m, int N, float *preds, cudaStream_t s);
 void upload_optimizers(Model &m, cudaStream_t s);
 void rebuild_heap_topology(Model &m, cudaStream_t s);
 // dist.cu

@@ -233,6 +233,42 @@ void launch_update_preds_last_tree(Model &m, const float *X, int N, int F, float
     launch_predict(m, X, N, F, m.ens.n_trees - 1, m.ens.n_trees, preds, false, s);
 }
 
+// Same update for the rows the newest tree was just grown on: every row still carries the heap id of the node it ended
+// in (`nid`, the same x > threshold comparisons the walk would repeat) and tree.cu numbered that node's leaf, so the
+// tree does not have to be walked again: theta -= lr * value[leaf]  (optimizer.cpp:110-118), one coalesced pass.
+__global__ void __launch_bounds__(256)
+update_preds_from_nodes_kernel(float *__restrict__ preds, const int *__restrict__ nid, const int *__restrict__ leaf_index,
+                               const int *__restrict__ tree_indices, const float *__restrict__ values, const int *__restrict__ heap_feat_t,
+                               const DevOpt *__restrict__ opts, int n_opts, int N, int D, int t, int oblivious) {
+    if (!oblivious && heap_feat_t[0] < 0) return;          // depth-0 tree: never matches in the reference (predictor.cpp:211-217)
+    const int first_leaf = tree_indices[t];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)N * D; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / D), d = (int)(e - (long long)i * D);
+        const int li = leaf_index[nid[i]];
+        if (li < 0) continue;
+        const float v = values[(size_t)(first_leaf + li) * D + d];
+        float th = preds[e];
+        for (int o = 0; o < n_opts; ++o) {
+            const DevOpt op = opts[o];
+            if (d >= op.start_idx && d < op.stop_idx) th = th - sched_lr(op, t) * v;
+        }
+        preds[e] = th;
+    }
+}
+
+void launch_update_preds_from_nodes(Model &m, int N, float *preds, cudaStream_t s) {
+    if (N <= 0) return;
+    Ensemble &e = m.ens;
+    const int t = e.n_trees - 1, D = m.cfg.output_dim, md = m.cfg.max_depth;
+    const bool obl = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
+    long long ne = (long long)N * D;
+    int grid = (int)((ne + 1023) / 1024);
+    if (grid > 148 * 16) grid = 148 * 16;
+    GB_LAUNCH(update_preds_from_nodes_kernel, grid, 256, 0, s, preds, m.ws.nid.as<int>(), m.ws.na.leaf_index, e.tree_indices.as<int>(),
+              e.values.as<float>(), obl ? nullptr : e.heap_feat.as<int>() + (size_t)t * (1 << md), m.d_opts.as<DevOpt>(),
+              (int)m.opts.size(), N, D, t, obl ? 1 : 0);
+}
+
 // ---------------------------------------------------------------- rebuild heap topology from leaf paths
 // (ensembles loaded in the reference layout: gbrl_b200_set_ensemble)
 __global__ void rebuild_heap_kernel(const int *tree_indices, const int *depths, const int *feature_indices,
