@@ -13,6 +13,7 @@
 // The exact per-column order statistics use cub::DeviceRadixSort per column (library call on a row that
 // SURVEY 8f lists as "next"); everything else here is hand-written.
 #include "engine.cuh"
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 #include <cfloat>
@@ -192,6 +193,63 @@ bin_kernel(const float *__restrict__ X, const float *__restrict__ thrT, uint16_t
     }
 }
 
+// Feature-major copy of the codes for ALL features (every rank), codesT[f][row] = code (not pre-scaled), row stride
+// codesT_stride: the consumers that need ONE feature of many rows -- the stable partition (node.cpp:86-96) and the
+// side bits of the near-tie replay (node.cpp:339) -- read 2 coalesced bytes per row instead of a 32-byte sector of
+// the row-major fp32 matrix.  x > thr[f][j]  <=>  code(x) > j, so the comparisons are the reference's.
+__global__ void __launch_bounds__(256)
+bin_featmajor_kernel(const float *__restrict__ X, const float *__restrict__ thrT, uint16_t *__restrict__ codesT, int N, int F,
+                     long long stride, int rows_per_cta) {
+    __shared__ float sthr[NB * FT];
+    __shared__ uint16_t s_c[FT][36];
+    const int tile = blockIdx.y;
+    const float *tt = thrT + (size_t)tile * NB * FT;
+    for (int i = threadIdx.x; i < NB * FT; i += blockDim.x) sthr[i] = tt[i];
+    __syncthreads();
+    const int r = threadIdx.x >> 3, g = threadIdx.x & 7, rl = r & 3;
+    const int fbase = tile * FT + g * 4;
+    const bool vec = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int row1 = min(N, row0 + rows_per_cta);
+    for (int rb = row0; rb < row1; rb += 32) {
+        const int row = rb + r;
+        unsigned int c[4] = {0u, 0u, 0u, 0u};
+        if (row < row1) {
+            float x[4];
+            if (vec && fbase + 3 < F) {
+                float4 v = *reinterpret_cast<const float4 *>(X + (size_t)row * F + fbase);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = (fbase + k < F) ? X[(size_t)row * F + fbase + k] : -INFINITY;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int mslot = (k + rl) & 3;
+                const float xv = mslot == 0 ? x[0] : mslot == 1 ? x[1] : mslot == 2 ? x[2] : x[3];
+                const int fs = g * 4 + mslot;
+                int pos = 0;
+#pragma unroll
+                for (int st = 128; st >= 1; st >>= 1)
+                    if (sthr[(pos + st - 1) * FT + fs] < xv) pos += st;
+                if (sthr[pos * FT + fs] < xv) pos += 1;   // only possible when pos == 255
+                if (mslot == 0) c[0] = pos; else if (mslot == 1) c[1] = pos; else if (mslot == 2) c[2] = pos; else c[3] = pos;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_c[g * 4 + k][r] = (uint16_t)c[k];
+        __syncthreads();
+        {   // thread -> (feature, 4 consecutive rows): one 8-byte store
+            const int ft = threadIdx.x >> 3, rg = (threadIdx.x & 7) * 4;
+            if (tile * FT + ft < F && rb + rg < row1) {
+                const uint2 w = *reinterpret_cast<const uint2 *>(&s_c[ft][rg]);
+                *reinterpret_cast<uint2 *>(codesT + (size_t)(tile * FT + ft) * stride + rb + rg) = w;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 void bin_features(Model &m, const float *X, int N, int F, cudaStream_t s) {
     Workspace &ws = m.ws;
     int ntl = ws.tile_hi - ws.tile_lo;
@@ -200,6 +258,16 @@ void bin_features(Model &m, const float *X, int N, int F, cudaStream_t s) {
     int rows_per_cta = 1024;
     dim3 grid(ceil_div(N, rows_per_cta), ntl);
     GB_LAUNCH(bin_kernel, grid, 256, 0, s, X, ws.thrT.as<float>(), ws.codes.as<uint16_t>(), N, F, ws.tile_lo, rows_per_cta);
+    // the feature-major copy pays off once the fp32 matrix no longer sits in L2 (a PPO minibatch does)
+    // (GBRL_B200_FEATMAJOR=1 / 0 forces it on / off: the parity tests run both paths on the same small inputs)
+    const char *force = getenv("GBRL_B200_FEATMAJOR");
+    ws.use_codesT = force ? (force[0] == '1') : ((size_t)N * F * sizeof(float) > ((size_t)48 << 20));
+    if (ws.use_codesT) {
+        ws.codesT_stride = ((long long)N + 7) & ~7ll;
+        ws.codesT.ensure((size_t)F * ws.codesT_stride * sizeof(uint16_t) + 64);
+        dim3 grid_t(ceil_div(N, rows_per_cta), ws.nT);
+        GB_LAUNCH(bin_featmajor_kernel, grid_t, 256, 0, s, X, ws.thrT.as<float>(), ws.codesT.as<uint16_t>(), N, F, ws.codesT_stride, rows_per_cta);
+    }
 }
 
 }  // namespace gb

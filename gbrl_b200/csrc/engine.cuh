@@ -92,6 +92,9 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     int N = 0, F = 0, nT = 0, D = 0, depth = 0, MAXN = 0, B = 0;
     int tile_lo = 0, tile_hi = 0;   // feature tiles owned by this rank [tile_lo, tile_hi)
     int row_groups = 1, row_group = 0;   // 2-D sharding: ranks beyond the tile count split each node's row chunks round-robin
+    DevBuf codesT;                  // feature-major copy of the codes, all features: [F][codesT_stride] u16
+    long long codesT_stride = 0;
+    bool use_codesT = false;
     int codes_rows = 0;             // rows of the code matrix (tile stride); >= N when a tree is grown on a mini-batch
     int row_offset = 0;             // first row of the current mini-batch inside the code matrix
     DevBuf codes, thr, thrT, bg, order[2], nid, rflag, rscan, chunk_sums, hist[2], scores, cand_flags;

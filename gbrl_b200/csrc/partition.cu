@@ -15,8 +15,9 @@ namespace gb {
 constexpr int PART_CHUNK = 2048;   // rows per CTA (256 threads x 8)
 
 __global__ void __launch_bounds__(256)
-part_flag_kernel(const float *__restrict__ X, const int *__restrict__ order, const int *__restrict__ nid, NodeArrays na,
-                 uint8_t *__restrict__ flag, int *__restrict__ chunk_sums, int N, int F) {
+part_flag_kernel(const float *__restrict__ X, int F, const uint16_t *__restrict__ codesT, long long stride, int row_offset,
+                 const int *__restrict__ order, const int *__restrict__ nid, NodeArrays na, uint8_t *__restrict__ flag,
+                 int *__restrict__ chunk_sums, int N) {
     __shared__ int s_sum;
     if (threadIdx.x == 0) s_sum = 0;
     __syncthreads();
@@ -26,7 +27,11 @@ part_flag_kernel(const float *__restrict__ X, const int *__restrict__ order, con
         const int i = order[k];
         const int h = nid[i];
         uint8_t fl = 0;
-        if (na.state[h] == NODE_SPLIT) fl = X[(size_t)i * F + na.split_f[h]] > na.split_thr[h] ? 1 : 0;
+        // x > thr[f][j]  <=>  code(x) > j  (candidates.cu): 2 coalesced-ish bytes of the feature-major codes per row
+        if (na.state[h] == NODE_SPLIT) {
+            if (codesT != nullptr) fl = (int)codesT[(size_t)na.split_f[h] * stride + row_offset + i] > na.split_j[h] ? 1 : 0;
+            else fl = X[(size_t)i * F + na.split_f[h]] > na.split_thr[h] ? 1 : 0;
+        }
         flag[k] = fl;
         mine += fl;
     }
@@ -113,8 +118,9 @@ void launch_partition(Model &m, const float *X, int level, int cur, cudaStream_t
     const int N = ws.N;
     if (N == 0) return;
     const int n_chunks = ceil_div(N, PART_CHUNK);
-    GB_LAUNCH(part_flag_kernel, n_chunks, 256, 0, s, X, ws.order[0].as<int>(), ws.nid.as<int>(), ws.na, ws.rflag.as<uint8_t>(),
-              ws.chunk_sums.as<int>(), N, ws.F);
+    GB_LAUNCH(part_flag_kernel, n_chunks, 256, 0, s, X, ws.F, ws.use_codesT ? ws.codesT.as<uint16_t>() : nullptr, ws.codesT_stride,
+              ws.row_offset, ws.order[0].as<int>(),
+              ws.nid.as<int>(), ws.na, ws.rflag.as<uint8_t>(), ws.chunk_sums.as<int>(), N);
     GB_LAUNCH(part_scan_chunks_kernel, 1, 1024, 0, s, ws.chunk_sums.as<int>(), n_chunks);
     GB_LAUNCH(part_rscan_kernel, n_chunks, 256, 0, s, ws.rflag.as<uint8_t>(), ws.chunk_sums.as<int>(), ws.rscan.as<int>(), N);
     GB_LAUNCH(part_scatter_kernel, ceil_div(N, 256), 256, 0, s, ws.order[0].as<int>(), ws.order[1].as<int>(), ws.nid.as<int>(),

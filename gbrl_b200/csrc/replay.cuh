@@ -7,6 +7,9 @@ namespace gb {
 struct ReplayParams {
     int F, B, D, score_func, min_data;
     const float *X;            // raw features, row-major
+    const uint16_t *codesT;    // feature-major codes [F][codesT_stride] (x > thr[f][j] <=> code > j), rows offset by row_offset
+    long long codesT_stride;
+    int row_offset;
     const float *bg;           // build_grads
     const int *order;
     const float *thr;

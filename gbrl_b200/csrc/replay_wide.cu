@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
         }
         it = lo - 1;
     }
-    int it_loaded = -1, s0 = 0, n = 0, f = 0, woff_it = 0, md = 1;
+    int it_loaded = -1, s0 = 0, n = 0, jb = 0, f = 0, woff_it = 0, md = 1;
     bool is_cand = false;
     float tv = INFINITY;
+    const uint16_t *col = P.codesT;
     for (int g = g_begin; g < g_end; ++g) {
         const int gw = g << 3;
         while (it + 1 < n_items && S.woff[it + 1] <= gw) ++it;      // items without words share the offset of their successor
@@ -59,7 +60,9 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
             s0 = na.seg_start[item.node]; n = na.seg_len[item.node];
             is_cand = item.cand >= 0;
             f = is_cand ? item.cand / P.B : 0;
+            jb = is_cand ? item.cand - f * P.B : 0;
             tv = is_cand ? P.thr[item.cand] : INFINITY;
+            if (P.codesT != nullptr) col = P.codesT + (size_t)f * P.codesT_stride + P.row_offset;
             woff_it = S.woff[it]; md = S.mode[it];
             it_loaded = it;
         }
@@ -67,11 +70,19 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
         if (md != 0) continue;
         const int k0 = (gw - woff_it) << 5;
         int cnt = 0;
-        float xv[8];
+        bool rt[8];
+        if (P.codesT != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = k0 + j * 32 + lane;
-            xv[j] = (k < n && is_cand) ? P.X[(size_t)P.order[s0 + k] * P.F + f] : -INFINITY;
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j * 32 + lane;
+                rt[j] = (k < n && is_cand) && (int)col[P.order[s0 + k]] > jb;           // x > thr[f][jb] <=> code > jb
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j * 32 + lane;
+                rt[j] = (k < n && is_cand) && P.X[(size_t)P.order[s0 + k] * P.F + f] > tv;
+            }
         }
         // group sums in fp32 (tree order); they only steer the binade prediction
         float sl[D], sr[D];
@@ -80,7 +91,7 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = k0 + j * 32 + lane;
-            const bool right = xv[j] > tv;                                     // node.cpp:339
+            const bool right = rt[j];                                          // node.cpp:339
             const unsigned int m = __ballot_sync(0xffffffffu, right);
             if (lane == j) S.bits[gw + j] = m;
             cnt += __popc(m);

@@ -977,19 +977,28 @@ __global__ void __launch_bounds__(256) replay_bits_kernel(ReplayParams P, NodeAr
         if (S.mode[it] != 0) continue;
         const ReplayItem item = P.items[it];
         const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
-        const int f = item.cand / P.B;
+        const int f = item.cand / P.B, jb = item.cand - f * P.B;
         const float tv = P.thr[item.cand];
         const int k0 = (gw - S.woff[it]) << 5;
         int cnt = 0;
-        float xv[8];
+        bool rt[8];
+        if (P.codesT != nullptr) {
+            const uint16_t *col = P.codesT + (size_t)f * P.codesT_stride + P.row_offset;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = k0 + j * 32 + lane;
-            xv[j] = k < n ? P.X[(size_t)P.order[s0 + k] * P.F + f] : -INFINITY;
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j * 32 + lane;
+                rt[j] = k < n && (int)col[P.order[s0 + k]] > jb;              // x > thr[f][jb] <=> code > jb
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j * 32 + lane;
+                rt[j] = k < n && P.X[(size_t)P.order[s0 + k] * P.F + f] > tv;
+            }
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const unsigned int m = __ballot_sync(0xffffffffu, xv[j] > tv);      // node.cpp:339
+            const unsigned int m = __ballot_sync(0xffffffffu, rt[j]);           // node.cpp:339
             if (lane == j) S.bits[gw + j] = m;
             cnt += __popc(m);
         }
@@ -1352,7 +1361,8 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
     if (m.cfg.tie_replay) {
         ReplayParams R;
         R.F = ws.F; R.B = ws.B; R.D = ws.D; R.score_func = m.cfg.split_score_func; R.min_data = m.cfg.min_data_in_leaf;
-        R.X = X; R.bg = ws.bg.as<float>(); R.order = ws.order[0].as<int>(); R.thr = ws.thr.as<float>();
+        R.X = X; R.codesT = ws.use_codesT ? ws.codesT.as<uint16_t>() : nullptr; R.codesT_stride = ws.codesT_stride; R.row_offset = ws.row_offset;
+        R.bg = ws.bg.as<float>(); R.order = ws.order[0].as<int>(); R.thr = ws.thr.as<float>();
         R.items = ws.replay.as<ReplayItem>(); R.out = ws.replay_scores.as<float>(); R.ctl = ctl;
         // rows per thread per stage: 8 (1024-row stages) for D == 1 down to 1 for wide outputs, so that a stage's
         // gradients fit in registers while they are in flight and two stages fit in shared memory

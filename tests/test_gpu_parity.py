@@ -62,6 +62,26 @@ def test_step_parity_vs_oracle(n, f, d, depth, bins, score, grow, gen, iters, T)
     _log_stats("step n=%d f=%d d=%d depth=%d %s %s T=%d" % (n, f, d, depth, score, grow, T), st)
 
 
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[7]])
+def test_step_parity_feature_major_codes(case, monkeypatch):
+    """Large matrices take the side of a split from the feature-major u16 code copy (x > thr[f][j] <=> code > j) instead
+    of the fp32 value; force that path on small inputs and check it against the oracle like any other."""
+    monkeypatch.setenv("GBRL_B200_FEATMAJOR", "1")
+    n, f, d, depth, bins, score, grow, gen, iters, T = case
+    X, y = synth(n, f, d, seed=n + f + 1)
+    kw = dict(input_dim=f, output_dim=d, max_depth=depth, n_bins=bins, par_th=10, split_score_func=score,
+              generator_type=gen, batch_size=n, grow_policy=grow)
+    o, g = _pair(ref_threads=T, **kw)
+    boosting_loop([o, g], X, y, iters)
+    assert g.m.get_stats()["replay_overflow"] == 0
+
+
+@pytest.mark.parametrize("grow,score", [("greedy", "L2"), ("oblivious", "cosine")])
+def test_fit_parity_minibatch_feature_major(grow, score, monkeypatch):
+    monkeypatch.setenv("GBRL_B200_FEATMAJOR", "1")
+    test_fit_parity_minibatch(grow, score)
+
+
 @pytest.mark.parametrize("grow,score", [("greedy", "L2"), ("oblivious", "cosine")])
 def test_fit_parity_minibatch(grow, score):
     n, f, d = 3100, 10, 2
