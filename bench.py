@@ -116,12 +116,12 @@ def synth_numpy(n, f, d, seed):
     return X, y
 
 
-def make_engine(c, device_index, ref_threads, tie_replay=True, hist_variant=0, replay_variant=0):
+def make_engine(c, device_index, ref_threads, tie_replay=True, hist_variant=0, replay_variant=0, band_kappa=0.0):
     import numpy as np
     from gbrl_b200 import GBRL
     m = GBRL(input_dim=c["f"], output_dim=c["d"], policy_dim=c["d"], max_depth=c["depth"], n_bins=256, par_th=10,
              split_score_func=c["score"], generator_type="quantile", batch_size=c["n"], grow_policy=c["grow"],
-             device="cuda:%d" % device_index, ref_threads=ref_threads, tie_replay=tie_replay, hist_variant=hist_variant, replay_variant=replay_variant)
+             device="cuda:%d" % device_index, ref_threads=ref_threads, tie_replay=tie_replay, hist_variant=hist_variant, replay_variant=replay_variant, band_kappa=band_kappa)
     m.set_bias(np.zeros(c["d"], np.float32))
     m.set_feature_weights(np.ones(c["f"], np.float32))
     m.set_feature_mapping(np.arange(c["f"], dtype=np.int32), np.ones(c["f"], dtype=bool))
@@ -277,6 +277,7 @@ def main():
     ap.add_argument("--no-replay", action="store_true", help="exact-arithmetic arg-max only (see DESIGN.md, near-tie replay)")
     ap.add_argument("--hist-variant", type=int, default=0, help="0 streaming histogram kernel (default), 1 per-item kernel")
     ap.add_argument("--replay-variant", type=int, default=0, help="0 GPU-wide replay chains where output_dim <= 2 (default), 1 one CTA per replay item")
+    ap.add_argument("--kappa", type=float, default=0.0, help="near-tie band width in noise units (0 = engine default)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
     args = ap.parse_args()
@@ -313,7 +314,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl")
     X, y = synth_torch(c["n"], c["f"], c["d"], 0, dev)
-    m = make_engine(c, local, ref_threads=cores, tie_replay=not args.no_replay, hist_variant=args.hist_variant, replay_variant=args.replay_variant)
+    m = make_engine(c, local, ref_threads=cores, tie_replay=not args.no_replay, hist_variant=args.hist_variant, replay_variant=args.replay_variant, band_kappa=args.kappa)
     if world > 1:
         m.init_distributed()
     m.fit_begin(X, y, shuffle=False)              # bias, candidates, binning: once per fit (fitter.cpp:134-151)
@@ -386,7 +387,7 @@ def main():
     if not args.no_e2e:
         Xh = torch.empty((c["n"], c["f"]), dtype=torch.float32, pin_memory=True); Xh.copy_(X)
         yh = torch.empty((c["n"], c["d"]), dtype=torch.float32, pin_memory=True); yh.copy_(y)
-        m2 = make_engine(c, local, ref_threads=cores, tie_replay=not args.no_replay, hist_variant=args.hist_variant, replay_variant=args.replay_variant)
+        m2 = make_engine(c, local, ref_threads=cores, tie_replay=not args.no_replay, hist_variant=args.hist_variant, replay_variant=args.replay_variant, band_kappa=args.kappa)
         if world > 1:
             pass   # e2e is reported for rank 0's single-GPU call only when world > 1
         hx = (Xh.data_ptr(), tuple(Xh.shape), "torch.float32", "cpu")
@@ -407,7 +408,7 @@ def main():
     # ---- the same K iterations with the exact-arithmetic tier only (no reference-order replay of near-ties)
     exact_only = None
     if not args.no_replay and world == 1:
-        m3 = make_engine(c, local, ref_threads=cores, tie_replay=False, hist_variant=args.hist_variant, replay_variant=args.replay_variant)
+        m3 = make_engine(c, local, ref_threads=cores, tie_replay=False, hist_variant=args.hist_variant, replay_variant=args.replay_variant, band_kappa=args.kappa)
         m3.fit_begin(X, y, shuffle=False)
         m3.fit_iterate(W, sync=True)
         torch.cuda.synchronize()

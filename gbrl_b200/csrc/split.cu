@@ -340,7 +340,7 @@ struct OblParams {
     const float *fw;
     const int *rev_map;
     float *obl_tot;            // [C]
-    float *obl_nb;             // [C] rounding-noise scale of the total: w * sum_nodes sqrt(n_node) * |score|
+    float *obl_nb;             // [C] rounding-noise scale of the total: w * sqrt(sum_nodes n_node * score^2)
     float2 *blk_best;          // [nblocks]
     ReplayItem *replay;
     int *obl_cands;            // candidate list of replay (stored after the items, see launcher)
@@ -359,13 +359,15 @@ __global__ void __launch_bounds__(256) obl_reduce_kernel(OblParams P, NodeArrays
         for (int p = 0; p < P.nn; ++p) {
             const float sp = P.scores[(size_t)p * P.C + c];
             s += sp;                                                         // fitter.cpp:427-430, node order
-            if (sp > -INFINITY) nb += sqrtf((float)na.seg_len[base + p]) * fabsf(sp);
+            // rounding noise of the node's sequential sums: independent from node to node (disjoint samples), so the
+            // noise scale of the total is the root of the sum of squares of the per-node scales 2^-24 sqrt(n) |score|
+            if (sp > -INFINITY) nb += (float)na.seg_len[base + p] * sp * sp;
         }
         const int f = c / P.B;
         const float wf = P.fw[P.rev_map[f]];
         s = s * wf;                                                          // fitter.cpp:432-435
         P.obl_tot[c] = s;
-        P.obl_nb[c] = nb * fabsf(wf);
+        P.obl_nb[c] = sqrtf(nb) * fabsf(wf);
         if (s > -INFINITY) { tot = s; idx = c; }
     }
     s_gain[threadIdx.x] = tot; s_idx[threadIdx.x] = idx;
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(256) obl_select_kernel(OblParams P, NodeArrays
         s_best = g; s_besti = (bi == INT_MAX) ? -1 : bi; s_count = 0; s_w = 0; s_ok = 0;
         P.ctl->obl_best = g; P.ctl->obl_best_idx = s_besti; P.ctl->obl_has_replay = 0;
         atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, (unsigned long long)P.nn);
-        // per-node sequential sums carry noise ~ 2^-24 sqrt(n_node) |score|; the total's noise scale is their sum
+        // per-node sequential sums carry noise ~ 2^-24 sqrt(n_node) |score|; the total's noise scale is their quadrature sum
         s_band = 0.5f * P.kappa * U24 * (s_besti >= 0 ? P.obl_nb[s_besti] : 0.0f) + FLT_MIN;
     }
     __syncthreads();
@@ -1339,7 +1341,9 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
     const int C = ws.F * ws.B, nn = 1 << level;
     Ctl *ctl = ws.ctl.as<Ctl>();
     GB_CUDA(cudaMemsetAsync(&ctl->n_replay, 0, sizeof(int), s));
-    const float kappa = m.cfg.band_kappa > 0 ? m.cfg.band_kappa : 8.0f;
+    // default band: 6 noise units.  The largest noise ever observed on a replayed candidate is 1.35 units (max_noise_ratio), so two
+    // candidates can swap when they are <= 2.7 units apart; the observed spread (sigma ~ 0.35 units) puts 6 units at > 12 sigma.
+    const float kappa = m.cfg.band_kappa > 0 ? m.cfg.band_kappa : 6.0f;
     int *obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap);
     if (!obl) {
         SelectParams P;

@@ -55,7 +55,7 @@ typedef struct {
                                the best are re-scored in the reference's sequential fp32 order so that
                                the chosen split is bit-identical to the reference's; 0: exact-arithmetic
                                arg-max only */
-    float band_kappa;       /* band = kappa * 2^-24 * sqrt(n_node) * |score|; <=0 -> default 8 */
+    float band_kappa;       /* band = kappa * 2^-24 * sqrt(n_node) * |score|; <=0 -> default 6 */
     int use_subtraction;    /* 1: histogram only the smaller child, derive the sibling from the parent */
     int hist_variant;       /* 0: streaming histogram kernel (cp.async row ring, carried shared histogram); 1: per-item kernel */
     int replay_variant;     /* 0: replay chains spread over the whole GPU where output_dim <= 2; 1: one CTA per replay item */
