@@ -62,6 +62,28 @@ def test_step_parity_vs_oracle(n, f, d, depth, bins, score, grow, gen, iters, T)
     _log_stats("step n=%d f=%d d=%d depth=%d %s %s T=%d" % (n, f, d, depth, score, grow, T), st)
 
 
+MEDIUM = [
+    # large enough for long float chains (many binade changes, near-ties inside the replay band), small enough for the oracle
+    (60000, 12, 1, 5, 256, "L2", "greedy", "quantile", 3, 4),
+    (40000, 10, 2, 4, 256, "cosine", "oblivious", "quantile", 3, 4),
+    (50000, 8, 1, 6, 256, "cosine", "greedy", "quantile", 2, 1),
+    (30000, 6, 3, 4, 128, "L2", "greedy", "quantile", 2, 2),          # output_dim 3: one CTA per replay item
+]
+
+
+@pytest.mark.parametrize("n,f,d,depth,bins,score,grow,gen,iters,T", MEDIUM)
+def test_step_parity_medium(n, f, d, depth, bins, score, grow, gen, iters, T):
+    X, y = synth(n, f, d, seed=n + f)
+    kw = dict(input_dim=f, output_dim=d, max_depth=depth, n_bins=bins, par_th=10, split_score_func=score,
+              generator_type=gen, batch_size=n, grow_policy=grow)
+    o, g = _pair(ref_threads=T, **kw)
+    boosting_loop([o, g], X, y, iters)
+    st = g.m.get_stats()
+    assert st["replay_overflow"] == 0
+    _log_stats("medium n=%d f=%d d=%d depth=%d %s %s T=%d chain fast/slow %d/%d" % (
+        n, f, d, depth, score, grow, T, st["chain_blocks_fast"], st["chain_blocks_slow"]), st)
+
+
 @pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[7]])
 def test_step_parity_feature_major_codes(case, monkeypatch):
     """Large matrices take the side of a split from the feature-major u16 code copy (x > thr[f][j] <=> code > j) instead
