@@ -81,14 +81,6 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
         GB_CUDA(cudaGetDeviceProperties(&prop, m.device));
         ws.n_sms = prop.multiProcessorCount;
     }
-    // histogram pairs (node slot x local tile) of the widest level, and the pool of staged partials: a CTA shares at
-    // most the first and the last pair of its run of items with other CTAs
-    const size_t pairs_max = ((size_t)1 << lv) * nTl;
-    ws.pair_first.ensure(pairs_max * sizeof(int)); ws.pair_nitems.ensure(pairs_max * sizeof(int)); ws.pl_count.ensure(pairs_max * sizeof(int));
-    ws.pl_stride = ws.n_sms + 2;
-    ws.pl_ids.ensure(pairs_max * ws.pl_stride * sizeof(int));
-    ws.max_partials = 2 * ws.n_sms + 2;
-    ws.partials.ensure((size_t)ws.max_partials * NB * FT * 3 * sizeof(int));
     ws.items.ensure((size_t)ws.items_cap * sizeof(Item));
     ws.replay_cap = 1 << 18;
     if ((size_t)ws.replay_cap < 4 * ((size_t)1 << md)) ws.replay_cap = 4 << md;

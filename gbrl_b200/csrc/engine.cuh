@@ -104,8 +104,7 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     DevBuf dwide;                        // GPU-wide evaluation of the mean / std chains (preprocess.cu)
     DevBuf rwide;                        // GPU-wide replay: per-group sums / predictions / summaries / tags, per-item hand-over
     long long rwide_groups = 0;
-    DevBuf pair_first, pair_nitems, pl_count, pl_ids, partials;   // histogram pairs (node x local tile) and staged partials
-    int max_partials = 0, pl_stride = 0, n_sms = 0;
+    int n_sms = 0;
     DevBuf sort_offsets;
     DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage, pred_partials;
     NodeArrays na{};
