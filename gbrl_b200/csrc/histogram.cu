@@ -5,19 +5,20 @@
 // sample is right of candidate (f, j) iff code(x_f) > j, the per-side (count, sum g) of ALL n_bins
 // candidates of a feature follow from one histogram over codes: right(j) = sum_{c > j} H[f][c].
 //
-// Kernel shape (sm_100a):
-//   * work item = (node, 32-feature tile, <= 8192 consecutive rows of the node's segment of `order`)
+// Kernel shape (sm_100a), common to both variants:
 //   * lane <-> feature: a warp handles 4 rows x 8 lanes x 4 features; in each of its 4 rounds the 32
 //     lanes address 32 different features, and the shared-memory histogram is laid out
 //     plane[w][code-1][feature], so bank == feature: every ATOMS.ADD is bank-conflict free by
 //     construction, whatever the codes are.
 //   * integer accumulation (north_star: "int32 atomics into shared-memory histograms"): build_grads
-//     are converted to 36-bit fixed point q = hi*2^18 + lo; count, lo and hi are accumulated in three
-//     int32 planes (8192 rows * 2^18 < 2^31), then flushed once per item to the global int64 histogram
-//     with REDG.ADD.64.  Integer sums are associative, so the histogram (and everything derived from
-//     it, including the parent - sibling subtraction and the multi-GPU all-reduce) is bit-reproducible.
-//   * rows are gathered through `order` (64 B per row and tile, one DRAM burst), 32 rows in flight per
-//     warp before the atomics start.
+//     are converted to 34-bit fixed point q = hi*2^18 + lo; count, lo and hi are accumulated in three
+//     int32 planes, then flushed to the global int64 histogram with REDG.ADD.64.  Integer sums are
+//     associative, so the histogram (and everything derived from it, including the parent - sibling
+//     subtraction and the multi-GPU all-reduce) is bit-reproducible.
+//   * hist_stream_kernel (default): one CTA per SM, rows reach the atomics through a per-warp cp.async ring,
+//     the shared histogram is carried across the items of a (node, tile) pair -- see the comment above it.
+//   * hist_kernel (hist_variant = 1): one work item = (node, tile, <= 8192 rows) per CTA visit, 2 CTAs per SM,
+//     rows prefetched into registers, one flush per item.
 // Algorithmic bytes per level: N * (4F + 4D + 4)  (SURVEY 8d); DRAM traffic is lower because the
 // fp32 feature matrix was quantised to u16 codes once per tree.
 #include "engine.cuh"

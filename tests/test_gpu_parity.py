@@ -84,6 +84,19 @@ def test_step_parity_medium(n, f, d, depth, bins, score, grow, gen, iters, T):
         n, f, d, depth, score, grow, T, st["chain_blocks_fast"], st["chain_blocks_slow"]), st)
 
 
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], MEDIUM[0], MEDIUM[1]])
+def test_step_parity_kernel_variants(case):
+    """The comparison variants stay correct: per-item histogram kernel (hist_variant=1) and one CTA per replay item
+    (replay_variant=1) against the oracle, like the default kernels."""
+    n, f, d, depth, bins, score, grow, gen, iters, T = case
+    X, y = synth(n, f, d, seed=n + f + 2)
+    kw = dict(input_dim=f, output_dim=d, max_depth=depth, n_bins=bins, par_th=10, split_score_func=score,
+              generator_type=gen, batch_size=n, grow_policy=grow)
+    o = configure(make_oracle(ref_threads=T, **kw), f, d)
+    g = configure(make_gpu(ref_threads=T, hist_variant=1, replay_variant=1, **kw), f, d)
+    boosting_loop([OracleAdaptor(o), GpuAdaptor(g)], X, y, min(iters, 2))
+
+
 @pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[7]])
 def test_step_parity_feature_major_codes(case, monkeypatch):
     """Large matrices take the side of a split from the feature-major u16 code copy (x > thr[f][j] <=> code > j) instead
