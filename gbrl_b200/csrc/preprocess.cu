@@ -244,6 +244,22 @@ __device__ __forceinline__ DenseChain dense_chain_of(const DenseWide &P, int cha
 // the lane's 8 consecutive chain elements of group g (mode 1: squares of the already centred values)
 __device__ __forceinline__ void dense_group(const DenseWide &P, const DenseChain &c, int g, float (&x)[8]) {
     const int lane = threadIdx.x & 31;
+    if (P.D == 1 && (long long)(g + 1) * 256 <= c.cnt) {
+        // interior group of a contiguous chain: one address, eight loads (two LDG.128 when the chain start allows it)
+        const float *p = P.mat + c.first + (long long)g * 256 + lane * 8;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = p[i];
+        }
+        if (P.mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = x[i] * x[i];
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long j = (long long)g * 256 + lane * 8 + i;
@@ -343,6 +359,8 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
     int4 qnx = make_int4(0, 0, 0, 0);
     float tgnx = 0.0f;
     if (lane < c.ng) { qnx = P.tab[base + lane]; tgnx = P.tag[base + lane]; }
+    float pa[8], pb[8];                                   // rows of two groups fetched ahead of need
+    int ha = -1, hb = -1;                                 // which groups they are
 #pragma unroll 1
     for (int w0 = 0; w0 < c.ng; w0 += 32) {
         const bool in_range = w0 + lane < c.ng;
@@ -350,8 +368,7 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
         const int4 q = qnx;
         const float tg = tgnx;
         if (w0 + 32 + lane < c.ng) { qnx = P.tab[base + w0 + 32 + lane]; tgnx = P.tag[base + w0 + 32 + lane]; }
-        int first = 0, have = -1;
-        float xn[8];
+        int first = 0;
 #pragma unroll 1
         while (first < wn) {
             // longest applicable prefix of the window from `first` (same logic as replay_wide.cu compose_window)
@@ -394,12 +411,23 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
             }
             if (take > 0) { n_fast += take; first += take; }
             if (first >= wn) break;
+            // rows of the failed group; the two groups after it are fetched now (a sum that hovers around a power of two
+            // fails group after group, and a lone warp has nothing else to hide the load latency behind)
+            const int gq = w0 + first;
             float x[8];
-            if (have == first) {
+            if (ha == gq) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = xn[i];
-            } else dense_group(P, c, w0 + first, x);
-            if (w0 + first + 1 < c.ng) { dense_group(P, c, w0 + first + 1, xn); have = first + 1; }
+                for (int i = 0; i < 8; ++i) x[i] = pa[i];
+            } else if (hb == gq) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = pb[i];
+            } else dense_group(P, c, gq, x);
+            if (hb == gq + 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pa[i] = pb[i];
+                ha = gq + 1;
+            } else if (ha != gq + 1 && gq + 1 < c.ng) { dense_group(P, c, gq + 1, pa); ha = gq + 1; }
+            if (gq + 2 < c.ng) { dense_group(P, c, gq + 2, pb); hb = gq + 2; }
             acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
             ++n_slow; ++first;
         }

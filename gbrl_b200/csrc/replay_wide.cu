@@ -155,10 +155,25 @@ template <int D>
 __device__ __forceinline__ void group_rows(const float *G, const unsigned int *W, int n, int lg, float (&v)[8 * D], unsigned int &mb) {
     const int lane = threadIdx.x & 31;
     const int kb = lg * GROUP_ROWS + lane * 8;
+    const float *p = G + (size_t)kb * D;
+    if ((lg + 1) * GROUP_ROWS <= n) {
+        // interior group: one address, 8 * D loads (LDG.128 when the node's first row allows it)
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
-    for (int j = 0; j < 8 * D; ++j) {
-        const int k = kb + j / D;
-        v[j] = k < n ? G[(size_t)kb * D + j] : 0.0f;
+            for (int j = 0; j < 8 * D; j += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(p + j);
+                v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8 * D; ++j) v[j] = p[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8 * D; ++j) {
+            const int k = kb + j / D;
+            v[j] = k < n ? p[j] : 0.0f;
+        }
     }
     mb = (W[lg * 8 + (lane >> 2)] >> ((lane & 3) * 8)) & 0xffu;
 }
