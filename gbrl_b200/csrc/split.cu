@@ -21,6 +21,7 @@
 #include "chain.cuh"
 #include "replay.cuh"
 #include <cfloat>
+#include <cstdlib>
 #include <climits>
 
 namespace gb {
@@ -1376,7 +1377,9 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
             StreamParams S;
             S.G = ws.rgrad.as<float>(); S.bits = ws.rbits.as<unsigned int>(); S.woff = ws.rmeta.as<int>();
             S.mode = S.woff + ws.replay_cap + 1; S.nright = S.mode + ws.replay_cap;
-            S.cap_words = ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
+            // GBRL_B200_REPLAY_DIRECT=1 (tests): no plane fits, every item takes the direct-gather kernel
+            static const bool force_direct = getenv("GBRL_B200_REPLAY_DIRECT") != nullptr && getenv("GBRL_B200_REPLAY_DIRECT")[0] == '1';
+            S.cap_words = force_direct ? 0 : ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
             S.nid = ws.nid.as<int>();
             S.wide = (D <= 2 && m.cfg.replay_variant == 0) ? 1 : 0;
             GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);

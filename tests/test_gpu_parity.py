@@ -97,6 +97,30 @@ def test_step_parity_kernel_variants(case):
     boosting_loop([OracleAdaptor(o), GpuAdaptor(g)], X, y, min(iters, 2))
 
 
+def test_step_parity_direct_replay_items():
+    """Replay items whose side-bit plane does not fit the stream buffer are gathered by their own CTA
+    (replay_par_kernel); GBRL_B200_REPLAY_DIRECT=1 sends every item down that path.  Runs in a subprocess because the
+    switch is latched when the library first replays."""
+    import subprocess, sys, os
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from helpers import *\n"
+        "import test_gpu_parity as t\n"
+        "for case in (t.MEDIUM[0], t.MEDIUM[2], t.CASES[7]):\n"
+        "    n, f, d, depth, bins, score, grow, gen, iters, T = case\n"
+        "    X, y = synth(n, f, d, seed=n + f)\n"
+        "    kw = dict(input_dim=f, output_dim=d, max_depth=depth, n_bins=bins, par_th=10, split_score_func=score,\n"
+        "              generator_type=gen, batch_size=n, grow_policy=grow)\n"
+        "    o, g = t._pair(ref_threads=T, **kw)\n"
+        "    boosting_loop([o, g], X, y, 2)\n"
+        "    assert g.m.get_stats()['replay_items'] > 0\n"
+        "print('DIRECT_REPLAY_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GBRL_B200_REPLAY_DIRECT="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "DIRECT_REPLAY_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[7]])
 def test_step_parity_feature_major_codes(case, monkeypatch):
     """Large matrices take the side of a split from the feature-major u16 code copy (x > thr[f][j] <=> code > j) instead
