@@ -15,8 +15,14 @@
 //      reference on every exact tie (duplicate thresholds, small nodes).
 //   2. replay tier -- the reference's own sums are sequential fp32 accumulations in ascending sample
 //      order, i.e. they carry O(u*sqrt(n)) rounding noise.  Whenever another (non-identical) candidate is
-//      within that noise band of the exact best, both are re-scored by replay_kernel with exactly the
-//      reference's chain of float operations, so the chosen split is the reference's, bit for bit.
+//      within that noise band of the exact best, both are re-scored with exactly the reference's chain of
+//      float operations, so the chosen split is the reference's, bit for bit.  The chains are evaluated by the
+//      bit-exact parallel evaluator of chain.cuh:
+//        output_dim <= 2   replay_plan / replay_gather here, then replay_wide.cu (summaries by the whole GPU,
+//                          one walking warp per chain)
+//        output_dim 3..4   replay_stream_kernel (one CTA per item over the gathered streams)
+//        output_dim  > 4   replay_kernel (one lane per output dimension runs its chain sequentially)
+//        items whose side-bit plane does not fit the stream buffer: replay_par_kernel (gathers its rows itself)
 #include "engine.cuh"
 #include "chain.cuh"
 #include "replay.cuh"
