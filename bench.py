@@ -35,6 +35,11 @@ WORKLOADS = {
 }
 # predict-only workload (BASELINE config 4): 100k oblivious trees d6, D=2, batch 8192 x 128 (PPO rollout shape)
 PREDICT = dict(n=8192, f=128, d=2, depth=6, n_trees=100_000, lrs=[(0.1, 0, 1), (0.01, 1, 2)])
+# dram__bytes_read.sum + dram__bytes_write.sum of the histogram kernel, bytes per launch averaged over the six levels of a C2
+# tree, from the committed `ncu --set full` capture (a number measured under a profiler cannot be taken live here)
+NCU_TRAFFIC = {"c2": {"bytes_per_launch": 2.06e8,
+                      "source": "profiles/r01_hist_full_c2.md: root level 269.2 MB, level 1 176.3 MB, level 2 197.6 MB "
+                                "(levels 3-5 taken as level 2); algorithmic bytes of the same launches average 245 MB"}}
 METRIC = "boosting-iters/sec (fit)"
 UNIT = "iters/s"
 
@@ -375,7 +380,10 @@ def main():
     alg_bytes = rows_scanned * (4 * f_local + 4 * c["d"] + 4)
     achieved = alg_bytes / (hist_ms * 1e-3) / 1e9 if hist_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "hist_kernel", "launches": hist_launches, "avg_launch_ms": hist_ms / hist_launches,
+                "traffic": NCU_TRAFFIC.get(args.workload, {}).get("bytes_per_launch") if (world == 1 and args.hist_variant == 0) else None,
+                "traffic_source": NCU_TRAFFIC.get(args.workload, {}).get("source") if (world == 1 and args.hist_variant == 0) else None,
+                "kernel": "hist_stream_kernel" if args.hist_variant == 0 else "hist_kernel", "launches": hist_launches,
+                "avg_launch_ms": hist_ms / hist_launches,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": alg_bytes / hist_launches,
                 "note": "algorithmic bytes count the fp32 row-major matrix (SURVEY 8d) for the rows the launch scans; the kernel "
