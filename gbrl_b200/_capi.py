@@ -34,7 +34,7 @@ EXPORTS = [
     "gbrl_b200_n_optimizers", "gbrl_b200_get_optimizer", "gbrl_b200_get_scheduler_lrs", "gbrl_b200_step",
     "gbrl_b200_fit", "gbrl_b200_fit_begin", "gbrl_b200_fit_iterate", "gbrl_b200_fit_end", "gbrl_b200_profile",
     "gbrl_b200_get_profile", "gbrl_b200_predict", "gbrl_b200_get_metadata", "gbrl_b200_get_ensemble",
-    "gbrl_b200_set_ensemble", "gbrl_b200_get_candidates", "gbrl_b200_get_root_scores", "gbrl_b200_dist_unique_id",
+    "gbrl_b200_set_ensemble", "gbrl_b200_set_iteration", "gbrl_b200_get_candidates", "gbrl_b200_get_root_scores", "gbrl_b200_dist_unique_id",
     "gbrl_b200_dist_init", "gbrl_b200_dist_shutdown", "gbrl_b200_microbench", "gbrl_b200_diag_chain_sums",
 ]
 
@@ -77,6 +77,7 @@ def lib():
     L.gbrl_b200_get_metadata.argtypes = [vp, C.POINTER(Metadata)]
     L.gbrl_b200_get_ensemble.argtypes = [vp, ip, ip, fp, ip, fp, fp, u8p]
     L.gbrl_b200_set_ensemble.argtypes = [vp, C.c_int, C.c_int, ip, ip, fp, ip, fp, fp, u8p, C.c_int]
+    L.gbrl_b200_set_iteration.argtypes = [vp, C.c_int]
     L.gbrl_b200_get_candidates.argtypes = [vp, fp, ip]
     L.gbrl_b200_get_root_scores.argtypes = [vp, fp, ip]
     L.gbrl_b200_dist_unique_id.argtypes = [u8p]

@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <numeric>
 #include <random>
+#include <map>
+#include <mutex>
 
 namespace gb {
 
@@ -20,6 +22,19 @@ void dist_shutdown(Model &m);
 double microbench(int which, int iters);
 void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode, const float *host_mean, float *host_partial,
                      float *host_centered, int impl, double *info);
+
+void ensure_dyn_smem_impl(const void *func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    int dev = 0;
+    GB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(func, dev);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return;
+    GB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done[key] = bytes;
+}
 
 // ---------------------------------------------------------------- DevBuf
 void DevBuf::ensure(size_t n, bool keep, cudaStream_t s) {
@@ -188,7 +203,21 @@ static void fit_begin(Model &m, const float *obs, int obs_dev, const float *targ
         // gbrl.cpp:1017-1026: the reference shuffles with std::random_device (not reproducible); we do the same
         std::vector<int> perm(N);
         std::iota(perm.begin(), perm.end(), 0);
-        std::random_device rd; std::mt19937 g(rd());
+        // every rank of a multi-GPU job must see the same row order (the histogram items and the replay chains are
+        // defined on positions of `order`): rank 0 draws the seed, an integer all-reduce hands it to the others
+        unsigned long long seed = 0;
+        if (m.rank == 0) { std::random_device rd; seed = ((unsigned long long)rd() << 32) | rd(); }
+        if (m.world > 1) {
+            DevBuf sb;
+            sb.ensure(sizeof(long long));
+            long long hs = (long long)(seed >> 1);
+            GB_CUDA(cudaMemcpyAsync(sb.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, s));
+            dist_allreduce_hist(m, sb.as<long long>(), 1, s);
+            GB_CUDA(cudaMemcpyAsync(&hs, sb.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+            GB_CUDA(cudaStreamSynchronize(s));
+            seed = (unsigned long long)hs;
+        }
+        std::mt19937_64 g(seed);
         std::shuffle(perm.begin(), perm.end(), g);
         DevBuf permbuf;
         permbuf.ensure((size_t)N * sizeof(int)); m.fit_x.ensure((size_t)N * F * sizeof(float)); m.fit_t.ensure((size_t)N * D * sizeof(float));
@@ -626,6 +655,30 @@ int gbrl_b200_set_ensemble(gbrl_b200_model *h, int n_trees, int n_leaves, const 
     e.n_trees = 0; e.n_leaves = 0;
     // make room (capacity is computed from tree counts; leaves may exceed trees * 2^md only if inconsistent)
     GB_CHECK((long long)n_leaves <= (long long)n_trees * (1 << md), "inconsistent ensemble: too many leaves");
+    // a truncated or corrupt .gbrl_model must not turn into out-of-bounds device accesses in predict / rebuild_heap
+    const bool obl_ = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
+    if (n_trees > 0) {
+        GB_CHECK(tree_indices && depths && values, "inconsistent ensemble: missing arrays");
+        GB_CHECK(md == 0 || (feature_indices && feature_values && edge_weights && inequality_directions),
+                 "inconsistent ensemble: missing split arrays");
+        GB_CHECK(n_num_features == m.cfg.input_dim, "inconsistent ensemble: feature count differs from input_dim");
+        GB_CHECK(tree_indices[0] == 0, "inconsistent ensemble: tree_indices[0] != 0");
+        for (int t = 0; t < n_trees; ++t) {
+            const int l0 = tree_indices[t], l1 = t + 1 < n_trees ? tree_indices[t + 1] : n_leaves;
+            GB_CHECK(l0 >= 0 && l0 < l1 && l1 <= n_leaves, "inconsistent ensemble: tree_indices not increasing / out of range");
+            GB_CHECK(l1 - l0 <= (1 << md), "inconsistent ensemble: a tree has more than 2^max_depth leaves");
+            if (obl_) GB_CHECK(depths[t] >= 0 && depths[t] <= md && (l1 - l0) == (1 << depths[t]), "inconsistent ensemble: oblivious depth / leaf count");
+        }
+        const size_t S_ = obl_ ? (size_t)n_trees : (size_t)n_leaves;
+        for (size_t r = 0; r < S_; ++r) {
+            const int dep = depths[r];
+            GB_CHECK(dep >= 0 && dep <= md, "inconsistent ensemble: depth out of range");
+            for (int k = 0; k < dep; ++k) {
+                const int f = feature_indices[r * md + k];
+                GB_CHECK(f >= 0 && f < m.cfg.input_dim, "inconsistent ensemble: feature index out of range");
+            }
+        }
+    }
     ensure_ensemble_capacity(m, n_trees > 0 ? n_trees : 1, 0);
     const size_t S = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? n_trees : n_leaves;
     if (n_trees > 0) {
@@ -645,6 +698,13 @@ int gbrl_b200_set_ensemble(gbrl_b200_model *h, int n_trees, int n_leaves, const 
     GB_CUDA(cudaDeviceSynchronize());
     m.n_num_features = n_num_features; m.n_cat_features = 0;
     if (n_trees > 0 && m.iteration == 0) m.iteration = n_trees;
+    API_END
+}
+
+int gbrl_b200_set_iteration(gbrl_b200_model *h, int iteration) {
+    API_BEGIN
+    GB_CHECK(iteration >= 0, "negative iteration");
+    h->m.iteration = iteration;
     API_END
 }
 

@@ -49,6 +49,11 @@ extern std::atomic<long long> g_kernel_launches;
         GB_CUDA(cudaGetLastError());                                      \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device attribute: remembered per (kernel, device), so a
+// second model on another GPU of the same process gets its opt-in too (capi.cu)
+void ensure_dyn_smem_impl(const void *func, size_t bytes);
+template <typename K> inline void ensure_dyn_smem(K kernel, size_t bytes) { ensure_dyn_smem_impl(reinterpret_cast<const void *>(kernel), bytes); }
+
 // ---------------------------------------------------------------- device helpers
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div64(long long a, long long b) { return (a + b - 1) / b; }

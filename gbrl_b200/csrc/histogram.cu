@@ -500,11 +500,7 @@ template <int ND, int NWARPS, int NST>
 static void launch_hist_stream(Model &m, int d0, int write_count, long long *hist, int n_sms, cudaStream_t s) {
     Workspace &ws = m.ws;
     const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int) + (size_t)NWARPS * NST * HS_STAGE_ROWS * (64 + 4 * ND);   // planes + rings
-    static bool attr_set = false;
-    if (!attr_set) {
-        GB_CUDA(cudaFuncSetAttribute((hist_stream_kernel<ND, NWARPS, NST>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    ensure_dyn_smem(hist_stream_kernel<ND, NWARPS, NST>, smem);
     GB_LAUNCH((hist_stream_kernel<ND, NWARPS, NST>), n_sms, NWARPS * 32, smem, s, ws.codes.as<uint16_t>(), ws.bg.as<float>(),
               ws.order[0].as<int>(), ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
               ws.tile_hi - ws.tile_lo, ws.tile_lo, ws.nT, write_count);
@@ -514,11 +510,7 @@ template <int ND>
 static void launch_hist_nd(Model &m, int d0, int write_count, long long *hist, int n_sms, cudaStream_t s) {
     Workspace &ws = m.ws;
     const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int);
-    static bool attr_set[4] = {false, false, false, false};
-    if (!attr_set[ND]) {
-        GB_CUDA(cudaFuncSetAttribute(hist_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[ND] = true;
-    }
+    ensure_dyn_smem(hist_kernel<ND>, smem);
     const int ctas_per_sm = ND == 1 ? 2 : 1;
     GB_LAUNCH(hist_kernel<ND>, n_sms * ctas_per_sm, HIST_THREADS, smem, s, ws.codes.as<uint16_t>(), ws.bg.as<float>(),
               ws.order[0].as<int>(), ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
@@ -528,12 +520,7 @@ static void launch_hist_nd(Model &m, int d0, int write_count, long long *hist, i
 // `order` ping-pong: launch_partition swaps the two DevBufs, so ws.order[0] is always the current one.
 void launch_histogram(Model &m, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
-    static int n_sms = 0;
-    if (!n_sms) {
-        cudaDeviceProp p;
-        GB_CUDA(cudaGetDeviceProperties(&p, m.device));
-        n_sms = p.multiProcessorCount;
-    }
+    const int n_sms = ws.n_sms;
     long long *hist = ws.hist[level & 1].as<long long>();
     const int D = ws.D;
     int d0 = 0;

@@ -165,7 +165,7 @@ __global__ void predict_combine_kernel(const float *__restrict__ partials, const
 template <int DM>
 static void launch_predict_chunked(Model &m, const PredictParams &P, int n_chunks, int tpc, cudaStream_t s) {
     const size_t smem = (size_t)P.F * 33 * sizeof(float);
-    if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(predict_chunk_kernel<DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) ensure_dyn_smem(predict_chunk_kernel<DM>, smem);
     m.ws.pred_partials.ensure((size_t)n_chunks * P.N * P.D * sizeof(float));
     dim3 grid(ceil_div(P.N, 32), n_chunks);
     GB_LAUNCH(predict_chunk_kernel<DM>, grid, 128, smem, s, P, m.ws.pred_partials.as<float>(), tpc);

@@ -446,8 +446,7 @@ constexpr size_t DC_SMEM = (size_t)3 * DC_THREADS * 8 * sizeof(float);
 
 template <int D>
 static void launch_dense(float *mat, const float *mean, float *partial, long long ne, int T, int mode, cudaStream_t s, long long *stats) {
-    static bool attr = false;
-    if (!attr) { GB_CUDA(cudaFuncSetAttribute(dense_chain_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM)); attr = true; }
+    ensure_dyn_smem(dense_chain_kernel<D>, DC_SMEM);
     GB_LAUNCH(dense_chain_kernel<D>, T, DC_THREADS, DC_SMEM, s, mat, mean, partial, ne, T, mode, stats);
 }
 

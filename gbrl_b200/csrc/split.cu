@@ -1330,16 +1330,16 @@ void launch_scan(Model &m, int level, cudaStream_t s) {
     else if (D <= 4) launch_scan_dm<4>(P, ws.na, grid, s);
     else if (D <= 8) launch_scan_dm<8>(P, ws.na, grid, s);
     else if (D <= 16) launch_scan_dm<16>(P, ws.na, grid, s);
-    else launch_scan_dm<32>(P, ws.na, grid, s);
+    else if (D <= 32) launch_scan_dm<32>(P, ws.na, grid, s);
+    else launch_scan_dm<64>(P, ws.na, grid, s);      // gbrl_b200_create caps output_dim at 64
 }
 
 template <int DCT>
-static void launch_stream(const ReplayParams &R, const NodeArrays &na, const StreamParams &S, Ctl *ctl, cudaStream_t s) {
+static void launch_stream(const ReplayParams &R, const NodeArrays &na, const StreamParams &S, Ctl *ctl, int n_sms, cudaStream_t s) {
     using C = ParCfg<DCT>;
     const size_t smem = (size_t)3 * C::STAGE * DCT * sizeof(float) + (size_t)3 * (C::STAGE / 32) * sizeof(unsigned int);
-    static bool attr = false;
-    if (!attr) { GB_CUDA(cudaFuncSetAttribute(replay_stream_kernel<DCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    GB_LAUNCH((replay_stream_kernel<DCT>), 148 * 2, 512, smem, s, R, na, S, ctl);
+    ensure_dyn_smem(replay_stream_kernel<DCT>, smem);
+    GB_LAUNCH((replay_stream_kernel<DCT>), n_sms * 2, 512, smem, s, R, na, S, ctl);
 }
 
 void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s) {
@@ -1393,30 +1393,30 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
             if (S.wide) {
                 // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
                 launch_replay_wide(m, R, S, s);
-                if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-                else GB_LAUNCH((replay_par_kernel<2>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                else GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
                 return;
             }
             GB_LAUNCH(replay_bits_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
             if (D <= 1) {
-                launch_stream<1>(R, ws.na, S, ctl, s);
-                GB_LAUNCH((replay_par_kernel<1>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                launch_stream<1>(R, ws.na, S, ctl, ws.n_sms, s);
+                GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
             } else if (D == 2) {
-                launch_stream<2>(R, ws.na, S, ctl, s);
-                GB_LAUNCH((replay_par_kernel<2>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                launch_stream<2>(R, ws.na, S, ctl, ws.n_sms, s);
+                GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
             } else if (D == 3) {
-                launch_stream<3>(R, ws.na, S, ctl, s);
-                GB_LAUNCH((replay_par_kernel<3>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                launch_stream<3>(R, ws.na, S, ctl, ws.n_sms, s);
+                GB_LAUNCH((replay_par_kernel<3>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
             } else {
-                launch_stream<4>(R, ws.na, S, ctl, s);
-                GB_LAUNCH((replay_par_kernel<4>), 148 * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
+                launch_stream<4>(R, ws.na, S, ctl, ws.n_sms, s);
+                GB_LAUNCH((replay_par_kernel<4>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
             }
         } else {
             // wide outputs: one lane per output dimension runs its chain sequentially (parallel over D instead of over rows)
             const int T = 128;
             const size_t smem = ((size_t)2 * T * D + 2 * D) * sizeof(float) + (size_t)2 * (T / 32) * sizeof(unsigned int);
-            if (smem > 48 * 1024) GB_CUDA(cudaFuncSetAttribute(replay_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GB_LAUNCH((replay_kernel<1, 128>), 148 * 4, 128, smem, s, R, ws.na);
+            if (smem > 48 * 1024) ensure_dyn_smem(replay_kernel<1, 128>, smem);
+            GB_LAUNCH((replay_kernel<1, 128>), ws.n_sms * 4, 128, smem, s, R, ws.na);
         }
     }
 }

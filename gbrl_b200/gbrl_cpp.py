@@ -130,7 +130,7 @@ class GBRL:
         self.set_bias(other.get_bias())
         self.set_feature_weights(other.get_feature_weights())
         fm, num = other.get_feature_mapping()
-        self.set_feature_mapping(fm, num)
+        self.set_feature_mapping(fm, num, _restore=True)
         for o in other.get_optimizers():
             self.set_optimizer(o["algo"], o["scheduler_func"], o["init_lr"], o["start_idx"], o["stop_idx"], o["stop_lr"], o["T"])
         md = other._meta()
@@ -300,12 +300,15 @@ class GBRL:
         n = int(np.prod(a.shape)) if a.shape else 1
         _capi.check(self._lib.gbrl_b200_set_feature_weights(self._h, a.ptr, n, a.dev))
 
-    def set_feature_mapping(self, feature_mapping, mapping_numerics):
+    def set_feature_mapping(self, feature_mapping, mapping_numerics, _restore=False):
+        """gbrl.cpp:271-316.  `_restore` (load / copy-constructor): the arrays are put back verbatim -- a model that was only
+        ever driven through fit() carries the reference's zero-initialised mapping (all `mapping_numerics` False although
+        it has no categorical feature), which is not a request for categorical splits."""
         m = np.ascontiguousarray(feature_mapping, dtype=np.int32)
         n = np.ascontiguousarray(mapping_numerics).astype(np.uint8)
         if m.size != n.size:
             raise RuntimeError("feature_mapping and mapping_numerics must have the same length")
-        if not np.all(n):
+        if not np.all(n) and not _restore:
             raise NotImplementedError("categorical features are out of scope of the B200 engine (SURVEY 2.1 #19)")
         _capi.check(self._lib.gbrl_b200_set_feature_mapping(self._h, m.ctypes.data_as(C.POINTER(C.c_int)),
                                                             n.ctypes.data_as(C.POINTER(C.c_uint8)), int(m.size)))
@@ -485,7 +488,19 @@ class GBRL:
         """GBRL::loadFromFile (gbrl.cpp:1175-1252) for numerical-feature SGD models; the model lands on the GPU."""
         from . import model_io
         meta, e, opts, name = model_io.read_model(path)
-        if meta["n_cat_features"] != 0 or (e["is_numerics"] is not None and not np.all(e["is_numerics"])):
+        for k in ("bias", "feature_weights", "feature_mapping", "mapping_numerics"):
+            if e[k] is None:
+                raise RuntimeError("corrupt model file: section %s is absent" % k)
+        if meta["n_trees"] > 0:
+            for k in ("tree_indices", "depths", "values", "feature_indices", "feature_values", "edge_weights", "inequality_directions"):
+                if e[k] is None:
+                    raise RuntimeError("corrupt model file: section %s is absent" % k)
+        categorical = meta["n_cat_features"] != 0
+        if not categorical and meta["n_trees"] > 0 and e["is_numerics"] is not None and meta["max_depth"] > 0:
+            # only the first depths[r] entries of a row are splits; the unused tail is zero-initialised (types.cpp:232-260)
+            used = np.arange(meta["max_depth"])[None, :] < np.asarray(e["depths"])[:, None]
+            categorical = bool(np.any(used & ~e["is_numerics"]))
+        if categorical:
             raise NotImplementedError("categorical features are out of scope of the B200 engine (SURVEY 2.1 #19)")
         m = GBRL(input_dim=meta["input_dim"], output_dim=meta["output_dim"], policy_dim=meta["policy_dim"],
                  max_depth=meta["max_depth"], min_data_in_leaf=meta["min_data_in_leaf"], n_bins=meta["n_bins"],
@@ -495,9 +510,10 @@ class GBRL:
                  **engine_kwargs)
         m.set_bias(e["bias"])
         m.set_feature_weights(e["feature_weights"])
-        m.set_feature_mapping(e["feature_mapping"], e["mapping_numerics"])
+        m.set_feature_mapping(e["feature_mapping"], e["mapping_numerics"], _restore=True)
         for o in opts:
             m.set_optimizer(o["algo"], o["scheduler_func"], o["init_lr"], o["start_idx"], o["stop_idx"], o["stop_lr"], o["T"])
         if meta["n_trees"] > 0:
             m._set_ensemble(e, meta["n_num_features"])
+        _capi.check(m._lib.gbrl_b200_set_iteration(m._h, int(meta["iteration"])))
         return m

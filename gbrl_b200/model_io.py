@@ -98,9 +98,14 @@ def read_model(path):
 
     def arr(count, dtype, shape=None):
         nonlocal off
+        if off >= len(buf):
+            raise RuntimeError("truncated .gbrl_model file (offset %d of %d bytes)" % (off, len(buf)))
         present = buf[off]; off += 1
         if not present:
             return None
+        if off + count * np.dtype(dtype).itemsize > len(buf):
+            raise RuntimeError("truncated .gbrl_model file: section of %d x %s at offset %d exceeds %d bytes" % (
+                count, np.dtype(dtype).name, off, len(buf)))
         a = np.frombuffer(buf, dtype=dtype, count=count, offset=off).copy()
         off += a.nbytes
         return a.reshape(shape) if shape is not None else a

@@ -125,6 +125,8 @@ int gbrl_b200_get_ensemble(gbrl_b200_model *m, int *tree_indices, int *depths, f
 int gbrl_b200_set_ensemble(gbrl_b200_model *m, int n_trees, int n_leaves, const int *tree_indices, const int *depths,
                            const float *values, const int *feature_indices, const float *feature_values,
                            const float *edge_weights, const uint8_t *inequality_directions, int n_num_features);
+/* restores ensembleMetaData::iteration of a loaded model (GBRL::loadFromFile, gbrl.cpp:1175-1252) */
+int gbrl_b200_set_iteration(gbrl_b200_model *m, int iteration);
 
 /* ---- building blocks exposed for tests / profiling (same kernels the calls above use) ---- */
 /* thresholds[f*n_bins + b] of the last step/fit (fitter.cpp:77-90 candidates), host copy */
