@@ -31,6 +31,16 @@ def _enum(table, s, what):
     return table[k]
 
 
+def _default_ref_threads():
+    """omp_get_max_threads() of the reference on this host (utils.h:64-81 partitions its float reductions by it):
+    OMP_NUM_THREADS when set, else the core count.  GBRL_B200_REF_THREADS overrides both."""
+    for k in ("GBRL_B200_REF_THREADS", "OMP_NUM_THREADS"):
+        v = os.environ.get(k, "").split(",")[0].strip()
+        if v.isdigit() and int(v) >= 1:
+            return int(v)
+    return os.cpu_count() or 1
+
+
 def _torch():
     import torch
     return torch
@@ -103,7 +113,7 @@ class GBRL:
                         cv_beta=float(cv_beta), split_score_func=split_score_func, generator_type=generator_type,
                         use_control_variates=False, batch_size=int(batch_size), grow_policy=grow_policy,
                         verbose=int(verbose), device="cuda", learner_name=learner_name,
-                        ref_threads=int(ref_threads if ref_threads else (os.cpu_count() or 1)),
+                        ref_threads=int(ref_threads if ref_threads else _default_ref_threads()),
                         tie_replay=bool(tie_replay), band_kappa=float(band_kappa), use_subtraction=bool(use_subtraction),
                         device_ordinal=int(device_ordinal), hist_variant=int(hist_variant), replay_variant=int(replay_variant))
         self._create()

@@ -1,0 +1,153 @@
+"""GPU suite: parity pinned at the sizes of BASELINE.json's configs.
+
+ * full-size known-answer vectors generated from the reference itself (tests/golden/full_*.npz, made by
+   tests/golden/make_golden_full.py in the build container: C1 at its true 10 000 x 16, one C2 / C3 / C5 / 1M x 128
+   oblivious fit each at FULL size) -- only the seed and the resulting ensemble are stored, the inputs are regenerated;
+ * the C2 / C3 / C5 families at full F, depth and n_bins on 65 536 - 131 072 rows against oracle/_ref run HERE (the GPU
+   box's host cores, one subprocess per case), >= 2 boosting iterations;
+ * C4: the 100 000-tree ensemble is written in the reference's wire format, loaded by the reference, and the 8192 x 128
+   predictions of both engines are compared.
+
+Bar: bit-exact split features / thresholds / directions / leaf assignment, <= 1e-5 on leaf values, predictions and loss.
+The near-tie replay band is statistical, so every case also asserts the calibration statistic
+max_noise_ratio < kappa / 2 (= 3) and replay_overflow == 0.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_DIR, compare_ensembles, make_gpu, TOL
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = ("tree_indices", "depths", "feature_indices", "feature_values", "inequality_directions", "edge_weights", "values")
+
+
+def _data(n, f, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, f), dtype=np.float32)
+    W = rng.standard_normal((f, d), dtype=np.float32)
+    y = (np.tanh(X @ W / np.sqrt(f)) + 0.1 * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+    return X, y
+
+
+def _engine(f, d, depth, grow, score, n, lrs, T):
+    m = make_gpu(ref_threads=T, input_dim=f, output_dim=d, max_depth=depth, n_bins=256, par_th=10, split_score_func=score,
+                 generator_type="quantile", batch_size=n, grow_policy=grow)
+    m.set_bias(np.zeros(d, np.float32))
+    m.set_feature_weights(np.ones(f, np.float32))
+    m.set_feature_mapping(np.arange(f, dtype=np.int32), np.ones(f, dtype=bool))
+    for (lr, a, b) in lrs:
+        m.set_optimizer("SGD", "const", float(lr), int(a), int(b))
+    return m
+
+
+def _check_stats(m, tag):
+    st = m.get_stats()
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/noise_stats.txt", "a") as fh:
+        fh.write("%s | replay_nodes %d / %d evaluated, items %d, max_noise_ratio %.3f, overflow %d\n" % (
+            tag, st["replay_nodes"], st["nodes_evaluated"], st["replay_items"], st["max_noise_ratio"], st["replay_overflow"]))
+    assert st["replay_overflow"] == 0, tag
+    assert st["max_noise_ratio"] < 3.0, "%s: observed rounding noise %.2f units is not covered twice by the band (6)" % (tag, st["max_noise_ratio"])
+
+
+@pytest.mark.parametrize("name", ["c1", "c1_l2", "c2", "j3", "c3", "c5"])
+def test_full_size_golden_from_reference(name):
+    path = os.path.join(GOLDEN_DIR, "full_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/full_%s.npz not generated (tests/golden/make_golden_full.py %s)" % (name, name))
+    z = np.load(path, allow_pickle=False)
+    n, f, d, depth, bins, iters, batch, seed, T = [int(v) for v in z["cfg"]]
+    lrs = [(float(a), int(b), int(c)) for a, b, c in z["lrs"]]
+    X, y = _data(n, f, d, seed)
+    m = _engine(f, d, depth, str(z["grow"]), str(z["score"]), n, lrs, T)
+    loss = m.fit(X, None, y, iters, False, "MultiRMSE")
+    exp = {k: z["fit_" + k] for k in KEYS}
+    compare_ensembles(exp, m.get_ensemble_data(), "full-size %s" % name)
+    assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
+    head = z["fit_pred_head"]
+    got = m.predict_numpy(X[:head.shape[0]]).reshape(head.shape)
+    assert np.abs(got.astype(np.float64) - head).max() <= TOL
+    assert np.abs(m.get_bias().astype(np.float64) - z["fit_bias"]).max() <= 1e-6
+    _check_stats(m, "golden full_%s n=%d" % (name, n))
+
+
+FAMILIES = [
+    # name, n, f, d, depth, grow, score, iterations     (full F / depth / n_bins of the BASELINE config, reduced N)
+    ("c2-family", 131072, 128, 1, 6, "greedy", "L2", 3),
+    ("c3-family", 65536, 64, 2, 8, "oblivious", "cosine", 3),
+    ("c5-family", 65536, 256, 1, 6, "greedy", "L2", 2),
+    ("j3-family", 131072, 128, 1, 6, "oblivious", "cosine", 2),
+]
+
+
+@pytest.mark.parametrize("name,n,f,d,depth,grow,score,iters", FAMILIES)
+def test_baseline_family_vs_compiled_reference(name, n, f, d, depth, grow, score, iters, tmp_path):
+    from oracle.oracle import load_reference
+    if load_reference() is None:
+        pytest.skip("oracle/_ref not built")
+    cores = os.cpu_count() or 1
+    seed = 4242 + n % 89 + f
+    out = str(tmp_path / "ref.npz")
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_fit_worker.py"), "fit", str(n), str(f), str(d), str(depth),
+                        grow, score, str(iters), str(seed), out], capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0 and "REF_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    z = np.load(out)
+    X, y = _data(n, f, d, seed)
+    lrs = [(0.1, 0, 1)] if d == 1 else [(0.1, 0, d - 1), (0.01, d - 1, d)]
+    m = _engine(f, d, depth, grow, score, n, lrs, cores)
+    loss = m.fit(X, None, y, iters, False, "MultiRMSE")
+    compare_ensembles({k: z["fit_" + k] for k in KEYS}, m.get_ensemble_data(), name)
+    assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
+    head = z["fit_pred_head"]
+    assert np.abs(m.predict_numpy(X[:head.shape[0]]).reshape(head.shape).astype(np.float64) - head).max() <= TOL
+    _check_stats(m, "%s n=%d T=%d (reference: %.1f s)" % (name, n, cores, float(z["seconds"])))
+
+
+def test_c4_predict_100k_trees_vs_compiled_reference(tmp_path):
+    """BASELINE config 4 at its true size: 100 000 oblivious trees (depth 6, D = 2), 8192 x 128 observations."""
+    from oracle.oracle import load_reference
+    if load_reference() is None:
+        pytest.skip("oracle/_ref not built")
+    from gbrl_b200 import GBRL, model_io
+    nt, dep, f, d = 100_000, 6, 128, 2
+    rng = np.random.default_rng(0)
+    nl = nt << dep
+    li = np.arange(1 << dep)
+    iq = ((li[:, None] >> (dep - 1 - np.arange(dep))[None, :]) & 1).astype(bool)      # fitter.cpp:517-542 leaf bit order
+    e = {"tree_indices": (np.arange(nt, dtype=np.int64) << dep).astype(np.int32), "depths": np.full(nt, dep, np.int32),
+         "values": (0.01 * rng.standard_normal((nl, d), dtype=np.float32)),
+         "feature_indices": rng.integers(0, f, (nt, dep)).astype(np.int32),
+         "feature_values": rng.standard_normal((nt, dep), dtype=np.float32),
+         "edge_weights": np.zeros((nl, dep), np.float32), "inequality_directions": np.tile(iq, (nt, 1)),
+         "bias": np.array([0.25, -0.5], np.float32), "feature_weights": np.ones(f, np.float32),
+         "reverse_num_feature_mapping": np.arange(f, dtype=np.int32), "reverse_cat_feature_mapping": np.full(f, -1, np.int32),
+         "feature_mapping": np.arange(f, dtype=np.int32), "mapping_numerics": np.ones(f, bool)}
+    meta = {"n_leaves": nl, "n_trees": nt, "input_dim": f, "output_dim": d, "policy_dim": d, "max_depth": dep, "min_data_in_leaf": 0,
+            "n_bins": 256, "par_th": 10, "cv_beta": 0.9, "verbose": 0, "batch_size": 8192, "use_cv": 0, "split_score_func": 1,
+            "generator_type": 1, "grow_policy": 1, "n_num_features": f, "n_cat_features": 0, "iteration": nt}
+    opts = [{"algo": "SGD", "scheduler_func": "Const", "init_lr": 0.1, "start_idx": 0, "stop_idx": 1, "stop_lr": 1e-8, "T": 10000},
+            {"algo": "SGD", "scheduler_func": "Const", "init_lr": 0.01, "start_idx": 1, "stop_idx": 2, "stop_lr": 1e-8, "T": 10000}]
+    path = str(tmp_path / "c4.gbrl_model")
+    model_io.write_model(path, meta, e, opts, "GBRL")
+    X = rng.standard_normal((8192, f), dtype=np.float32)
+    np.save(str(tmp_path / "obs.npy"), X)
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_fit_worker.py"), "load", path, str(tmp_path / "obs.npy"),
+                        str(tmp_path / "ref_pred.npy")], capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0 and "REF_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    exp = np.load(str(tmp_path / "ref_pred.npy")).reshape(8192, d)
+    m = GBRL.load(path)                                        # the same file, read by gbrl_b200/model_io.py
+    assert m.get_num_trees() == nt and m.get_iteration() == nt
+    got = m.predict_numpy(X).reshape(8192, d)                  # chunked rollout-shape kernel
+    err = np.abs(got.astype(np.float64) - exp).max()
+    assert err <= TOL, "100k-tree predict: max abs err %.3e" % err
+    sub = m.predict_numpy(X, 1000, 99000).reshape(8192, d)     # tree sub-range == difference of prefix sums (+ bias)
+    full_minus = got.astype(np.float64) - (m.predict_numpy(X, 0, 1000).astype(np.float64).reshape(8192, d) - e["bias"]) \
+        - (m.predict_numpy(X, 99000, nt).astype(np.float64).reshape(8192, d) - e["bias"])
+    assert np.abs(sub - full_minus).max() <= 3e-5
