@@ -11,9 +11,13 @@ generation and binning happen once per fit() call (fitter.cpp:134-151) and are o
 region; they are inside `e2e`, which times the reference-facing call GBRL.fit(host arrays).
 
 Workloads (BASELINE.json configs): c2 greedy d6 L2 1Mx128 (default, the config the metric is quoted on),
-c3 oblivious d8 cosine 4Mx64 D=2, c5 greedy d6 L2 8Mx256, c1 oblivious d4 10kx16.
+c3 oblivious d8 cosine 4Mx64 D=2, c5 greedy d6 L2 8Mx256, c1 oblivious d4 10kx16, j3 = north_star's "1M x 128
+oblivious fit", c4 = predict-only (100k trees x 8192 obs), rl = PPO-minibatch shape through the step() API.
+The default single-GPU run also measures c3 / c5 / j3 / c4 (each with its own roofline and bounded-sample CPU baseline)
+and reports them under "extra_workloads"; a multi-GPU run adds c5 (the config the sharded histogram exists for).
 """
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -30,24 +34,45 @@ WORKLOADS = {
     "c2": dict(n=1_000_000, f=128, d=1, depth=6, grow="greedy", score="L2", lrs=[(0.1, 0, 1)]),
     "c3": dict(n=4_000_000, f=64, d=2, depth=8, grow="oblivious", score="cosine", lrs=[(0.1, 0, 1), (0.01, 1, 2)]),
     "c5": dict(n=8_000_000, f=256, d=1, depth=6, grow="greedy", score="L2", lrs=[(0.1, 0, 1)]),
+    # north_star's target workload: "1M x 128 oblivious fit"
+    "j3": dict(n=1_000_000, f=128, d=1, depth=6, grow="oblivious", score="cosine", lrs=[(0.1, 0, 1)]),
     # PPO-minibatch shape driven through GBRL.step (shared actor-critic tree: 3 policy outputs + value), gbrl defaults
     "rl": dict(n=32_768, f=64, d=4, depth=4, grow="greedy", score="cosine", lrs=[(0.1, 0, 3), (0.01, 3, 4)]),
 }
 # predict-only workload (BASELINE config 4): 100k oblivious trees d6, D=2, batch 8192 x 128 (PPO rollout shape)
 PREDICT = dict(n=8192, f=128, d=2, depth=6, n_trees=100_000, lrs=[(0.1, 0, 1), (0.01, 1, 2)])
-# dram__bytes_read.sum + dram__bytes_write.sum of the histogram kernel, bytes per launch averaged over the six levels of a C2
-# tree, from the committed `ncu --set full` capture (a number measured under a profiler cannot be taken live here)
-NCU_TRAFFIC = {"c2": {"bytes_per_launch": 2.06e8,
-                      "source": "profiles/r01_hist_full_c2.md: root level 269.2 MB, level 1 176.3 MB, level 2 197.6 MB "
-                                "(levels 3-5 taken as level 2); algorithmic bytes of the same launches average 245 MB"}}
 METRIC = "boosting-iters/sec (fit)"
 UNIT = "iters/s"
+KEYS = ("tree_indices", "depths", "feature_indices", "feature_values", "inequality_directions", "edge_weights", "values")
+
+
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this round (a number measured under a profiler cannot be taken live inside a timed run)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t.get(workload)
+    except Exception:
+        return None
 
 
 def workload_name(w):
     c = WORKLOADS[w]
     return "%s: %s tree depth=%d %s score, %dx%d fp32, D=%d, quantile candidates, n_bins=256" % (
         w, c["grow"], c["depth"], c["score"], c["n"], c["f"], c["d"])
+
+
+def predict_name():
+    p = PREDICT
+    return "c4: predict-only, %d oblivious trees depth %d, D=%d, batch %d obs x %d features" % (p["n_trees"], p["depth"], p["d"], p["n"], p["f"])
+
+
+def peak_hbm():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -135,7 +160,22 @@ def make_engine(c, device_index, ref_threads, tie_replay=True, hist_variant=0, r
     return m
 
 
-# ------------------------------------------------------------------------------------------------ CPU reference
+def predict_ensemble(rng):
+    """The synthetic C4 ensemble: random feature in [0,128), threshold ~ N(0,1), values ~ N(0, 0.01)."""
+    import numpy as np
+    p = PREDICT
+    nt, dep, f, d = p["n_trees"], p["depth"], p["f"], p["d"]
+    nl = nt << dep
+    li = np.arange(1 << dep)
+    iq = ((li[:, None] >> (dep - 1 - np.arange(dep))[None, :]) & 1).astype(bool)
+    return {"tree_indices": (np.arange(nt, dtype=np.int64) << dep).astype(np.int32), "depths": np.full(nt, dep, np.int32),
+            "values": (0.01 * rng.standard_normal((nl, d), dtype=np.float32)),
+            "feature_indices": rng.integers(0, f, (nt, dep)).astype(np.int32),
+            "feature_values": rng.standard_normal((nt, dep), dtype=np.float32),
+            "edge_weights": np.zeros((nl, dep), np.float32), "inequality_directions": np.tile(iq, (nt, 1))}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference (child process)
 def cpu_reference_model(c, n_rows):
     """The reference's own CPU path (oracle/_ref, compiled from the reference sources) or, if that is not
     present, the plain-C oracle port.  Returns (kind, fit_callable)."""
@@ -155,46 +195,105 @@ def cpu_reference_model(c, n_rows):
     return "port", (lambda X, y, it: o.fit(X, y, it))
 
 
-def cpu_probe_rows(c, budget_s, steps):
-    """Pick the sample size (rows) so that `steps` reference iterations take about budget_s seconds: the
-    reference's cost is linear in N (O(d*B*F*N*D)), so probe a small N and scale."""
-    n0 = 1024
-    X, y = synth_numpy(n0, c["f"], c["d"], 0)
-    kind, fit = cpu_reference_model(c, n0)
-    t = time.perf_counter(); fit(X, y, 1); t = time.perf_counter() - t
-    per_row = max(t, 1e-4) / n0
-    rows = int(budget_s / max(steps, 1) / per_row)
-    rows = max(512, min(rows, c["n"]))
-    rows = 1 << int(math.log2(rows))
-    return min(rows, c["n"]), kind
-
-
-def run_cpu_sample(c, rows, warmup, steps):
+def cpu_child(args):
+    """Runs in a CHILD process whose OMP_NUM_THREADS was set explicitly by the parent (torchrun exports OMP_NUM_THREADS=1
+    to its workers, and the reference's thread count is latched when libgomp loads): probes the cost per row, picks the
+    sample size for the budget (the reference's cost is linear in N), times `steps` boosting iterations (fit
+    workloads) or predict calls (c4) and prints one JSON object."""
+    import numpy as np
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    if args.workload == "c4":
+        from oracle.oracle import load_reference
+        from gbrl_b200 import model_io
+        ref = load_reference()
+        p = PREDICT
+        rng = np.random.default_rng(0)
+        e = predict_ensemble(rng)
+        nt, dep, f, d = p["n_trees"], p["depth"], p["f"], p["d"]
+        e.update({"bias": np.zeros(d, np.float32), "feature_weights": np.ones(f, np.float32),
+                  "reverse_num_feature_mapping": np.arange(f, dtype=np.int32), "reverse_cat_feature_mapping": np.full(f, -1, np.int32),
+                  "feature_mapping": np.arange(f, dtype=np.int32), "mapping_numerics": np.ones(f, bool)})
+        meta = {"n_leaves": nt << dep, "n_trees": nt, "input_dim": f, "output_dim": d, "policy_dim": d, "max_depth": dep,
+                "min_data_in_leaf": 0, "n_bins": 256, "par_th": 10, "cv_beta": 0.9, "verbose": 0, "batch_size": p["n"], "use_cv": 0,
+                "split_score_func": 1, "generator_type": 1, "grow_policy": 1, "n_num_features": f, "n_cat_features": 0, "iteration": nt}
+        opts = [{"algo": "SGD", "scheduler_func": "Const", "init_lr": lr, "start_idx": a, "stop_idx": b, "stop_lr": 1e-8, "T": 10000}
+                for (lr, a, b) in p["lrs"]]
+        path = "/tmp/bench_c4_%d.gbrl_model" % os.getpid()
+        model_io.write_model(path, meta, e, opts, "GBRL")
+        m = ref.GBRL.load(path)
+        os.unlink(path)
+        rows = args.rows if args.rows > 0 else 1024
+        X = rng.standard_normal((rows, f), dtype=np.float32)
+        m.predict(X[:64], None)
+        t = time.perf_counter()
+        for _ in range(K):
+            m.predict(X, None)
+        t = time.perf_counter() - t
+        print(json.dumps({"kind": "reference", "rows": rows, "seconds": t, "steps": K, "obs_per_s": rows * K / t}), flush=True)
+        os._exit(0)
+    c = WORKLOADS[args.workload]
+    rows = args.rows
+    if rows <= 0:
+        n0 = 1024
+        X, y = synth_numpy(n0, c["f"], c["d"], 0)
+        kind, fit = cpu_reference_model(c, n0)
+        t = time.perf_counter(); fit(X, y, 1); t = time.perf_counter() - t
+        per_row = max(t, 1e-4) / n0
+        rows = int(args.budget / max(K + W, 1) / per_row)
+        rows = max(512, min(rows, c["n"]))
+        rows = min(1 << int(math.log2(rows)), c["n"])
     X, y = synth_numpy(rows, c["f"], c["d"], 0)
     kind, fit = cpu_reference_model(c, rows)
-    if warmup > 0:
-        fit(X, y, warmup)
-    t = time.perf_counter(); fit(X, y, steps); t = time.perf_counter() - t
-    its = steps / t
-    return kind, its, its * rows / c["n"], t
+    if W > 0:
+        fit(X, y, W)
+    t = time.perf_counter(); fit(X, y, K); t = time.perf_counter() - t
+    print(json.dumps({"kind": kind, "rows": rows, "seconds": t, "steps": K, "its_sample": K / t}), flush=True)
+    os._exit(0)      # the reference module's teardown is not worth waiting for
+
+
+def run_cpu_sample(workload, budget_s, steps, warmup, rows=0):
+    """Spawns cpu_child with every host core.  Returns dict(kind, rows, seconds, value [metric unit at full size], cores)."""
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    for k in ("OMP_PROC_BIND", "OMP_PLACES", "GOMP_CPU_AFFINITY", "KMP_AFFINITY"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-child", "--workload", workload, "--budget", str(budget_s), "--steps", str(steps),
+           "--warmup", str(warmup), "--rows", str(rows)]
+    try:
+        os.sched_setaffinity(0, range(cores))      # torchrun may have pinned this rank; the child inherits the mask
+    except Exception:
+        pass
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=3600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("cpu sample failed: " + (r.stderr or r.stdout)[-400:])
+    d = json.loads(lines[-1])
+    d["cores"] = cores
+    if workload == "c4":
+        d["value"] = d["obs_per_s"]
+        d["sample"] = "%d of %d observations x all %d trees, %d predict calls in %.1f s (reference predict is linear in observations)" % (
+            d["rows"], PREDICT["n"], PREDICT["n_trees"], d["steps"], d["seconds"])
+    else:
+        n = WORKLOADS[workload]["n"]
+        d["value"] = d["its_sample"] * d["rows"] / n
+        full = d["rows"] >= n
+        d["sample"] = ("%d of %d rows (full F=%d, depth, n_bins), %d timed boosting iterations in %.1f s%s" % (
+            d["rows"], n, WORKLOADS[workload]["f"], d["steps"], d["seconds"],
+            "" if full else "; value scaled by rows/N (cost is linear in N)"))
+    return d
 
 
 # ------------------------------------------------------------------------------------------------ predict (config 4)
-def bench_predict(args):
+def bench_predict(args, K, W, with_cpu=True):
     """obs/s of the batched ensemble predict: 100k-tree oblivious ensemble, 8192 x 128 observations per call."""
     import numpy as np
     import torch
     from gbrl_b200 import GBRL
     p = PREDICT
-    K, W = max(args.steps, 1), max(args.warmup, 0)
     rng = np.random.default_rng(0)
     nt, dep, f, d = p["n_trees"], p["depth"], p["f"], p["d"]
     nl = nt << dep
-    e = {"tree_indices": (np.arange(nt, dtype=np.int64) << dep).astype(np.int32), "depths": np.full(nt, dep, np.int32),
-         "values": (0.01 * rng.standard_normal((nl, d), dtype=np.float32)),
-         "feature_indices": rng.integers(0, f, (nt, dep)).astype(np.int32),
-         "feature_values": rng.standard_normal((nt, dep), dtype=np.float32),
-         "edge_weights": np.zeros((nl, dep), np.float32), "inequality_directions": np.zeros((nl, dep), bool)}
+    e = predict_ensemble(rng)
     m = GBRL(input_dim=f, output_dim=d, policy_dim=d, max_depth=dep, n_bins=256, split_score_func="cosine",
              generator_type="quantile", batch_size=p["n"], grow_policy="oblivious", device="cuda:0")
     m.set_bias(np.zeros(d, np.float32)); m.set_feature_weights(np.ones(f, np.float32))
@@ -215,30 +314,49 @@ def bench_predict(args):
     ms = ev0.elapsed_time(ev1) / K
     launches = m.get_stats()["kernel_launches"] - l0
     Xh = torch.empty((p["n"], f), dtype=torch.float32, pin_memory=True); Xh.copy_(X)
-    oh = np.empty((p["n"], d), np.float32)
     t = time.perf_counter()
     for _ in range(K):
-        oh = m.predict_numpy(Xh.numpy())
+        m.predict_numpy(Xh.numpy())
     te = (time.perf_counter() - t) / K
     walks = p["n"] * nt
+    peak, peak_src = peak_hbm()
+    ens_bytes = nl * d * 4 + nt * dep * 8
+    alg = ens_bytes + p["n"] * f * 4 + p["n"] * d * 4
+    # honest bound: the work unit is the tree walk -- depth x (shared-memory feature read + compare) + one value
+    # gather of D floats + D multiply-subtracts, ~ (4 * depth + 2 * D + 6) issue slots per 32 walks; the ensemble is
+    # L2-resident, so the HBM figure only says how little of the time is DRAM
+    slots = 4 * dep + 2 * d + 6
+    issue_peak = 148 * 4 * 1.965e9 / slots * 32
     out = {"metric": "obs/sec (predict)", "value": p["n"] / (ms * 1e-3), "unit": "obs/s", "n_gpus": 1, "steps": K, "warmup": W,
            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "c4: predict-only, %d oblivious trees depth %d, D=%d, batch %d obs x %d features" % (nt, dep, d, p["n"], f),
-                      "l2": "ensemble arrays (%.0f MB) cycle through L2 every call" % ((nl * d * 4 + nt * dep * 8) / 1e6)},
+           "config": {"workload": predict_name(), "l2": "ensemble arrays (%.0f MB) cycle through L2 every call" % (ens_bytes / 1e6)},
            "tree_walks_per_s": walks / (ms * 1e-3),
            "e2e": {"value": p["n"] / te, "unit": "obs/s", "h2d_bytes_per_step": p["n"] * f * 4, "d2h_bytes_per_step": p["n"] * d * 4},
-           "gpu_launches": int(launches)}
-    print(json.dumps(out))
-    return 0
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                        "traffic": (ncu_traffic("c4") or {}).get("bytes_per_launch"), "peak_source": peak_src, "kernel": "predict_tiles_kernel",
+                        "algorithmic_bytes_per_launch": alg,
+                        "note": "predict is not HBM-bound (ensemble + observations sit in L2, SURVEY 8d); the bound that matters is the "
+                                "issue rate of the tree walk, reported under issue_bound"},
+           "issue_bound": {"walks_per_s": walks / (ms * 1e-3), "peak_walks_per_s": issue_peak, "frac": walks / (ms * 1e-3) / issue_peak,
+                           "model": "%d issue slots per warp-walk (32 observations x 1 tree), 148 SMs x 4 schedulers x 1.965 GHz" % slots}}
+    if with_cpu:
+        try:
+            cpu = run_cpu_sample("c4", 0, 2, 0, rows=1024)
+            out["cpu_baseline"] = {"value": cpu["value"], "unit": "obs/s", "cores": cpu["cores"], "kind": cpu["kind"], "sample": cpu["sample"]}
+        except Exception as ex:   # pragma: no cover
+            out["cpu_baseline"] = {"value": None, "unit": "obs/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)[:200]}
+    del m, X
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ step() API (RL path)
-def bench_step_api(args):
+def bench_step_api(args, K, W, workload="rl"):
     """GBRL_SB3's call pattern: every update calls predict(obs) then step(obs, grads) with device tensors; step()
     recomputes the quantile candidates from the batch (fitter.cpp:72-90), bins it and grows one tree."""
     import torch
-    c = WORKLOADS["rl"]
-    K, W = max(args.steps, 1), max(args.warmup, 0)
+    c = WORKLOADS[workload]
     dev = torch.device("cuda", 0)
     X, y = synth_torch(c["n"], c["f"], c["d"], 0, dev)
     m = make_engine(c, 0, ref_threads=os.cpu_count() or 1, tie_replay=not args.no_replay)
@@ -262,62 +380,30 @@ def bench_step_api(args):
     prof = m.get_profile()
     out = {"metric": "boosting-iters/sec (step API: predict + step per call)", "value": 1000.0 / ms, "unit": UNIT, "n_gpus": 1,
            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": {"workload": workload_name("rl") + ", device tensors, predict(all trees) + step per iteration"},
+           "data": "synthetic", "config": {"workload": workload_name(workload) + ", device tensors, predict(all trees) + step per iteration"},
            "kernel_ms_per_step": {k: round(v["ms"] / K, 4) for k, v in prof.items() if isinstance(v, dict) and v["ms"] > 0},
            "gpu_launches": int(m.get_stats()["kernel_launches"] - l0), "replay": {k: m.get_stats()[k] for k in ("replay_nodes", "replay_items", "nodes_evaluated")}}
-    print(json.dumps(out))
-    return 0
+    return out
 
 
-# ------------------------------------------------------------------------------------------------ main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])   # "rl" is part of WORKLOADS
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-replay", action="store_true", help="exact-arithmetic arg-max only (see DESIGN.md, near-tie replay)")
-    ap.add_argument("--hist-variant", type=int, default=0, help="0 streaming histogram kernel (default), 1 per-item kernel")
-    ap.add_argument("--replay-variant", type=int, default=0, help="0 GPU-wide replay chains where output_dim <= 2 (default), 1 one CTA per replay item")
-    ap.add_argument("--kappa", type=float, default=0.0, help="near-tie band width in noise units (0 = engine default)")
-    ap.add_argument("--cpu-budget", type=float, default=20.0)
-    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
-    args = ap.parse_args()
-    if args.workload == "c4":
-        return bench_predict(args)
-    if args.workload == "rl":
-        return bench_step_api(args)
-    c = WORKLOADS[args.workload]
-    K, W = max(args.steps, 1), max(args.warmup, 0)
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
+# ------------------------------------------------------------------------------------------------ fit workloads
+def ensemble_sha(m):
+    import numpy as np
+    e = m.get_ensemble_data()
+    h = hashlib.sha256()
+    for k in KEYS:
+        h.update(np.ascontiguousarray(e[k]).tobytes())
+    return h.hexdigest()[:16]
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        rows, _ = cpu_probe_rows(c, args.ref_budget, K + W)
-        kind, its_sample, its_full, t = run_cpu_sample(c, rows, W, K)
-        sample = "%d of %d rows (full F=%d, depth, n_bins), %d timed boosting iterations in %.1f s; value scaled by rows/N (cost is linear in N)" % (
-            rows, c["n"], c["f"], K, t)
-        out = {"impl": "reference", "metric": METRIC, "value": its_full, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-               "ms_per_step": 1000.0 / its_full, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-               "data": "synthetic", "config": {"workload": workload_name(args.workload)},
-               "cpu_baseline": {"value": its_full, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
-               "e2e": {"value": its_full, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(out))
-        return 0
 
+def bench_fit(wl, args, K, W, rank, world, local, with_e2e=True, with_exact=True, with_cpu=True, cpu_budget=20.0):
+    """One fit workload on `world` ranks.  Returns the JSON dict on rank 0, None elsewhere."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the engine has no CPU fallback)"
-    torch.cuda.set_device(local)
+    c = WORKLOADS[wl]
+    cores = os.cpu_count() or 1
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl")
     X, y = synth_torch(c["n"], c["f"], c["d"], 0, dev)
     m = make_engine(c, local, ref_threads=cores, tie_replay=not args.no_replay, hist_variant=args.hist_variant, replay_variant=args.replay_variant, band_kappa=args.kappa)
     if world > 1:
@@ -354,68 +440,48 @@ def main():
     m.profile(False)
     loss = m.fit_end()
     stats = m.get_stats()
+    sha = ensemble_sha(m)
+    if world > 1:      # every rank must hold the same ensemble (integer histograms: bit-identical by construction)
+        shas = [None] * world
+        dist.all_gather_object(shas, sha)
+        assert all(s == shas[0] for s in shas), "ranks disagree on the ensemble: %s" % shas
     value = K / (ms * 1e-3)
+    del m
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel (histogram): algorithmic bytes = rows scanned * (4F + 4D + 4), SURVEY 8d
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    hist_ms = prof["histogram"]["ms"]; hist_launches = max(prof["histogram"]["launches"], 1)
-    rows_scanned = prof["hist_rows"] - rows0
-    n_tiles = (c["f"] + 31) // 32
-    gt = min(world, n_tiles)                      # same 2-D sharding arithmetic as prepare_workspace() in capi.cu
-    while gt > 1 and world % gt != 0:
-        gt -= 1
-    tg = rank % gt
-    own_tiles = (n_tiles * (tg + 1)) // gt - (n_tiles * tg) // gt      # feature tiles this rank histograms
-    f_local = min(c["f"], own_tiles * 32)
-    alg_bytes = rows_scanned * (4 * f_local + 4 * c["d"] + 4)
-    achieved = alg_bytes / (hist_ms * 1e-3) / 1e9 if hist_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC.get(args.workload, {}).get("bytes_per_launch") if (world == 1 and args.hist_variant == 0) else None,
-                "traffic_source": NCU_TRAFFIC.get(args.workload, {}).get("source") if (world == 1 and args.hist_variant == 0) else None,
-                "kernel": "hist_stream_kernel" if args.hist_variant == 0 else "hist_kernel", "launches": hist_launches,
-                "avg_launch_ms": hist_ms / hist_launches,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                "algorithmic_bytes_per_launch": alg_bytes / hist_launches,
-                "note": "algorithmic bytes count the fp32 row-major matrix (SURVEY 8d) for the rows the launch scans; the kernel "
-                        "reads u16 codes (2 B/feature), so DRAM traffic is about half of that (see profiles/)"}
-    breakdown = {k: round(v["ms"] / K, 4) for k, v in prof.items() if isinstance(v, dict) and v["ms"] > 0}
-
-    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies + candidates + binning inside
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), copies + candidates + binning inside; on N ranks the
+    #      same call on every rank (each holds all rows; histograms sharded), timed between barriers, max over ranks
     e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         Xh = torch.empty((c["n"], c["f"]), dtype=torch.float32, pin_memory=True); Xh.copy_(X)
         yh = torch.empty((c["n"], c["d"]), dtype=torch.float32, pin_memory=True); yh.copy_(y)
         m2 = make_engine(c, local, ref_threads=cores, tie_replay=not args.no_replay, hist_variant=args.hist_variant, replay_variant=args.replay_variant, band_kappa=args.kappa)
         if world > 1:
-            pass   # e2e is reported for rank 0's single-GPU call only when world > 1
+            m2.init_distributed()
         hx = (Xh.data_ptr(), tuple(Xh.shape), "torch.float32", "cpu")
         hy = (yh.data_ptr(), tuple(yh.shape), "torch.float32", "cpu")
         # untimed warm-up call (W boosting iterations): first-use allocation of the workspace, lazy module loading
         m2.fit(hx, None, hy, max(W, 1), False, "MultiRMSE")
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         te = time.perf_counter()
         loss2 = m2.fit(hx, None, hy, K, False, "MultiRMSE")
         torch.cuda.synchronize()
         te = time.perf_counter() - te
+        if world > 1:
+            t = torch.tensor([te], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
         e2e = {"value": K / te, "unit": UNIT, "h2d_bytes_per_step": (Xh.numel() + yh.numel()) * 4 // K,
                "d2h_bytes_per_step": (4 + 4 * c["d"] + 256) // K + 1, "seconds": te, "loss": loss2,
-               "call": "GBRL.fit(pinned host obs, pinned host targets, iterations=%d, shuffle=False) after one untimed warm-up call; "
-                       "H2D copies, candidate generation, binning, bias and the final loss read-back are inside" % K}
+               "call": "GBRL.fit(pinned host obs, pinned host targets, iterations=%d, shuffle=False) after one untimed warm-up call%s; "
+                       "H2D copies, candidate generation, binning, bias and the final loss read-back are inside" % (
+                           K, "" if world == 1 else ", on every one of the %d ranks (max over ranks)" % world)}
         del m2, Xh, yh
 
     # ---- the same K iterations with the exact-arithmetic tier only (no reference-order replay of near-ties)
     exact_only = None
-    if not args.no_replay and world == 1:
+    if with_exact and not args.no_replay and world == 1:
         m3 = make_engine(c, local, ref_threads=cores, tie_replay=False, hist_variant=args.hist_variant, replay_variant=args.replay_variant, band_kappa=args.kappa)
         m3.fit_begin(X, y, shuffle=False)
         m3.fit_iterate(W, sync=True)
@@ -428,32 +494,161 @@ def main():
                       "note": "tie_replay=0: arg-max on exact integer-histogram sums only; differs from the reference only where "
                               "the reference's own sequential-fp32 rounding noise decides between near-tied candidates"}
         del m3
+    del X, y
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel (histogram): algorithmic bytes = rows scanned * (4F + 4D + 4), SURVEY 8d
+    peak, peak_src = peak_hbm()
+    hist_ms = prof["histogram"]["ms"]; hist_launches = max(prof["histogram"]["launches"], 1)
+    rows_scanned = prof["hist_rows"] - rows0
+    n_tiles = (c["f"] + 31) // 32
+    gt = min(world, n_tiles)                      # same 2-D sharding arithmetic as prepare_workspace() in capi.cu
+    while gt > 1 and world % gt != 0:
+        gt -= 1
+    tg = rank % gt
+    own_tiles = (n_tiles * (tg + 1)) // gt - (n_tiles * tg) // gt      # feature tiles this rank histograms
+    f_local = min(c["f"], own_tiles * 32)
+    alg_bytes = rows_scanned * (4 * f_local + 4 * c["d"] + 4)
+    dram_bytes = rows_scanned * (2 * f_local + 4 * c["d"] + 4)         # what the kernel really streams: u16 codes, gradient, row id
+    achieved = alg_bytes / (hist_ms * 1e-3) / 1e9 if hist_ms > 0 else 0.0
+    tr = ncu_traffic(wl) if (world == 1 and args.hist_variant == 0) else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "frac_dram": (dram_bytes / (hist_ms * 1e-3) / 1e9 / peak) if hist_ms > 0 else 0.0,
+                "traffic": (tr or {}).get("bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                "kernel": "hist_stream_kernel" if args.hist_variant == 0 else "hist_kernel", "launches": hist_launches,
+                "avg_launch_ms": hist_ms / hist_launches, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes / hist_launches,
+                "note": "frac counts the fp32 row-major matrix (SURVEY 8d: rows scanned x (4F + 4D + 4)); frac_dram counts the bytes the "
+                        "kernel really streams (u16 codes: rows x (2F + 4D + 4))"}
+    breakdown = {k: round(v["ms"] / K, 4) for k, v in prof.items() if isinstance(v, dict) and v["ms"] > 0}
 
     # ---- CPU baseline on this box's host cores: bounded sample, scaled to the metric's unit
     cpu = None
-    if not args.no_cpu_baseline and args.gpus == 1:
+    if with_cpu:
         try:
-            rows, _ = cpu_probe_rows(c, args.cpu_budget, 2)
-            kind, its_sample, its_full, t = run_cpu_sample(c, rows, 0, 2)
-            cpu = {"value": its_full, "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": "%d of %d rows (full F, depth, n_bins), 2 boosting iterations in %.1f s; scaled by rows/N" % (rows, c["n"], t)}
+            s = run_cpu_sample(wl, cpu_budget, 2, 0)
+            cpu = {"value": s["value"], "unit": UNIT, "cores": s["cores"], "kind": s["kind"], "sample": s["sample"]}
         except Exception as ex:   # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "unavailable", "sample": repr(ex)[:200]}
 
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms / K,
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scores / int64 fixed-point sums",
-           "data": "synthetic",
-           "config": {"workload": workload_name(args.workload), "parallelism": "histogram sharded over %d rank(s): feature tiles x row chunks, one int64 all-reduce per level" % world,
-                      "l2": "inputs larger than L2 (code matrix %.0f MB + fp32 matrix %.0f MB per level pass)" % (
-                          c["n"] * c["f"] * 2 / 1e6, c["n"] * c["f"] * 4 / 1e6),
-                      "tie_replay": not args.no_replay, "ref_threads": cores},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-           "kernel_ms_per_step": breakdown, "final_loss": loss, "exact_tier_only": exact_only,
-           "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
-                      "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"],
-                      "chain_blocks_fast": stats["chain_blocks_fast"], "chain_blocks_slow": stats["chain_blocks_slow"],
-                      "chain_lanes_seq": stats["chain_lanes_seq"]}}
-    print(json.dumps(out))
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scores / int64 fixed-point sums",
+            "data": "synthetic",
+            "config": {"workload": workload_name(wl), "parallelism": "histogram sharded over %d rank(s): feature tiles x row chunks, one exchange of the owned int64 slices per level" % world,
+                       "l2": "inputs larger than L2 (code matrix %.0f MB + fp32 matrix %.0f MB per level pass)" % (
+                           c["n"] * c["f"] * 2 / 1e6, c["n"] * c["f"] * 4 / 1e6),
+                       "tie_replay": not args.no_replay, "ref_threads": cores},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_ms_per_step": breakdown, "final_loss": loss, "ensemble_sha": sha, "exact_tier_only": exact_only,
+            "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
+                       "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"],
+                       "chain_blocks_fast": stats["chain_blocks_fast"], "chain_blocks_slow": stats["chain_blocks_slow"],
+                       "chain_lanes_seq": stats["chain_lanes_seq"]}}
+
+
+def compact(d):
+    """The part of a workload's line that is kept under extra_workloads."""
+    keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches",
+            "kernel_ms_per_step", "ensemble_sha", "tree_walks_per_s", "issue_bound", "exact_tier_only")
+    return {k: d[k] for k in keep if k in d and d[k] is not None}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no extra_workloads)")
+    ap.add_argument("--no-replay", action="store_true", help="exact-arithmetic arg-max only (see DESIGN.md, near-tie replay)")
+    ap.add_argument("--hist-variant", type=int, default=0, help="0 streaming histogram kernel (default), 1 per-item kernel")
+    ap.add_argument("--replay-variant", type=int, default=0, help="0 GPU-wide replay chains where output_dim <= 2 (default), 1 one CTA per replay item")
+    ap.add_argument("--kappa", type=float, default=0.0, help="near-tie band width in noise units (0 = engine default)")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--ref-rows", type=int, default=0, help="--impl reference: force the sample size (e.g. the full N for a directly timed iteration)")
+    ap.add_argument("--extras-budget", type=float, default=170.0, help="wall-clock seconds after which remaining extra workloads are skipped")
+    # internal: the CPU sample runs in a child process with an explicit OMP_NUM_THREADS (see cpu_child)
+    ap.add_argument("--cpu-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--budget", type=float, default=20.0, help=argparse.SUPPRESS)
+    ap.add_argument("--rows", type=int, default=0, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.cpu_child:
+        return cpu_child(args)
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    t_start = time.time()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = args.workload
+        s = run_cpu_sample(wl, args.ref_budget, K, W, rows=args.ref_rows)
+        unit = "obs/s" if wl == "c4" else UNIT
+        out = {"impl": "reference", "metric": "obs/sec (predict)" if wl == "c4" else METRIC, "value": s["value"], "unit": unit, "n_gpus": args.gpus,
+               "steps": K, "warmup": W, "ms_per_step": 1000.0 / s["value"] if wl != "c4" else 1000.0 * PREDICT["n"] / s["value"],
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "config": {"workload": predict_name() if wl == "c4" else workload_name(wl)},
+               "cpu_baseline": {"value": s["value"], "unit": unit, "cores": s["cores"], "kind": s["kind"], "sample": s["sample"]},
+               "e2e": {"value": s["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the engine has no CPU fallback)"
+    torch.cuda.set_device(local)
+    if args.workload == "c4":
+        print(json.dumps(bench_predict(args, K, W, with_cpu=not args.no_cpu_baseline)))
+        return 0
+    if args.workload == "rl":
+        print(json.dumps(bench_step_api(args, K, W)))
+        return 0
+    if world > 1:
+        dist.init_process_group("nccl")
+    out = bench_fit(args.workload, args, K, W, rank, world, local, with_e2e=not args.no_e2e, with_exact=True,
+                    with_cpu=(not args.no_cpu_baseline) and args.gpus == 1, cpu_budget=args.cpu_budget)
+    if rank == 0:
+        out["n_gpus"] = args.gpus
+
+    # ---- the other BASELINE configs (driver-visible: extra keys of the same line)
+    extras = {}
+    if not args.no_extras and args.workload == "c2":
+        if world > 1:
+            # the config the sharded histogram exists for (BASELINE config 5): every rank takes part
+            Kx = min(K, 10)
+            try:
+                r = bench_fit("c5", args, Kx, min(W, 3), rank, world, local, with_e2e=False, with_exact=False, with_cpu=False)
+                if rank == 0:
+                    extras["c5"] = compact(r)
+            except Exception as ex:   # pragma: no cover
+                if rank == 0:
+                    extras["c5"] = {"error": repr(ex)[:300]}
+        else:
+            for wl in ("j3", "c3", "c4", "c5"):
+                if time.time() - t_start > args.extras_budget:
+                    extras[wl] = {"skipped": "extras budget of %.0f s spent" % args.extras_budget}
+                    continue
+                try:
+                    if wl == "c4":
+                        r = bench_predict(args, min(K, 20), min(W, 3), with_cpu=not args.no_cpu_baseline)
+                    else:
+                        r = bench_fit(wl, args, min(K, 10), min(W, 3), 0, 1, local, with_e2e=(wl == "j3") and not args.no_e2e, with_exact=False,
+                                      with_cpu=not args.no_cpu_baseline, cpu_budget=8.0)
+                    extras[wl] = compact(r)
+                except Exception as ex:   # pragma: no cover
+                    extras[wl] = {"error": repr(ex)[:300]}
+    if rank == 0:
+        if extras:
+            out["extra_workloads"] = extras
+        out["bench_seconds"] = round(time.time() - t_start, 1)
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     return 0
