@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgbrl_b200.so")
+LIB_PATH = os.environ.get("GBRL_B200_LIB") or os.path.join(_HERE, "lib", "libgbrl_b200.so")   # override: A/B runs of two builds
 
 
 class Config(C.Structure):
@@ -23,7 +23,7 @@ class Metadata(C.Structure):
         "batch_size", "split_score_func", "generator_type", "grow_policy", "verbose", "n_num_features",
         "n_cat_features", "n_trees", "n_leaves", "iteration")] + [(n, C.c_longlong) for n in (
             "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")] + [("max_noise_ratio", C.c_float)] + [
-                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow", "chain_lanes_seq")]
+                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow", "chain_lanes_seq", "chain_errors")]
 
 
 # every symbol include/gbrl_b200.h declares (tests check that the library exports all of them)

@@ -110,8 +110,8 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
         ws.rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
         if (D <= 2) {
             ws.rwide_groups = ws.rbits_words / 8 + 1;
-            ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)) + sizeof(int)) +
-                            (size_t)ws.replay_cap * 8 * sizeof(float));
+            ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(float) + 16 + 8 * 8) + sizeof(int)) +
+                            (size_t)ws.replay_cap * 8 * sizeof(float) + 64);      // bsum, pred, spec::Head, J x spec::Cand per (group, chain)
         }
     }
     // node arrays carved from one allocation
@@ -145,7 +145,7 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
     m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
     m.hist_rows = h.stat_hist_rows;
-    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow; m.chain_seq = h.stat_chain_seq;
+    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow; m.chain_seq = h.stat_chain_seq; m.chain_err = h.stat_chain_err;
     m.max_noise = __builtin_bit_cast(float, h.stat_max_noise);
 }
 
@@ -616,7 +616,7 @@ int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
     o->n_leaves = m.ens.n_leaves; o->iteration = m.iteration;
     o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
     o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated; o->max_noise_ratio = m.max_noise;
-    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow; o->chain_lanes_seq = m.chain_seq;
+    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow; o->chain_lanes_seq = m.chain_seq; o->chain_errors = m.chain_err;
     API_END
 }
 

@@ -151,3 +151,43 @@ def run_golden(name, factory, adaptor):
         assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
         assert np.abs(np.asarray(e.predict(X)).reshape(n, d).astype(np.float64) - z["fit_pred"]).max() <= TOL
     return e
+
+
+def numpy_predict(e, X, bias, lrs, n_trees, oblivious):
+    """The reference's sample-parallel predict restated in numpy float32 (predictor.cpp:167-265, optimizer.cpp:110-118):
+    theta = bias, then for every tree in ascending order theta[d] = fl(theta[d] - fl(lr_d * value[leaf, d])).  Bit-identical to
+    the reference's predictions (asserted when the full-size fixtures are generated), so a test can rebuild the exact
+    gradient stream of a boosting run from the stored ensemble alone."""
+    X = np.asarray(X, np.float32)
+    n, D = X.shape[0], len(bias)
+    lr_d = np.zeros(D, np.float32)
+    for (lr, a, b) in lrs:
+        lr_d[int(a):int(b)] = np.float32(lr)
+    out = np.tile(np.asarray(bias, np.float32), (n, 1))
+    ti, nl = np.asarray(e["tree_indices"]), np.asarray(e["values"]).shape[0]
+    vals = np.asarray(e["values"], np.float32).reshape(nl, D)
+    fi, fv, iq, dp = (np.asarray(e[k]) for k in ("feature_indices", "feature_values", "inequality_directions", "depths"))
+    for t in range(n_trees):
+        l0, l1 = int(ti[t]), (int(ti[t + 1]) if t + 1 < len(ti) else nl)
+        if oblivious:
+            dep = int(dp[t])
+            if dep == 0:
+                continue                                   # a depth-0 tree never matches (predictor.cpp:211-217)
+            li = np.zeros(n, np.int64)
+            for k in range(dep):
+                li |= (X[:, int(fi[t, k])] > fv[t, k]).astype(np.int64) << (dep - 1 - k)
+            leaf = l0 + li
+        else:
+            leaf = np.full(n, -1, np.int64)
+            for L in range(l0, l1):
+                dep = int(dp[L])
+                if dep == 0:
+                    continue
+                ok = np.ones(n, bool)
+                for k in range(dep):
+                    ok &= (X[:, int(fi[L, k])] > fv[L, k]) == bool(iq[L, k])
+                leaf[ok] = L
+        hit = leaf >= 0
+        upd = (lr_d[None, :] * vals[np.where(hit, leaf, 0)]).astype(np.float32)
+        out = np.where(hit[:, None], (out - upd).astype(np.float32), out)
+    return out

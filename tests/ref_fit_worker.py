@@ -4,6 +4,7 @@ separate process, because the reference's thread count (which fixes the partitio
 from the environment when libgomp loads.  TEST INFRASTRUCTURE ONLY.
 
     OMP_NUM_THREADS=16 python tests/ref_fit_worker.py fit  n f d depth grow score iters seed out.npz
+    OMP_NUM_THREADS=16 python tests/ref_fit_worker.py step n f d depth grow score iters seed out.npz
     OMP_NUM_THREADS=16 python tests/ref_fit_worker.py load model.gbrl_model obs.npy out.npy
 """
 import os
@@ -41,17 +42,30 @@ def main():
         np.save(sys.argv[4], p)
         print("REF_WORKER_OK predict %.2f s" % (time.time() - t), flush=True)
         os._exit(0)
+    mode = sys.argv[1]
     n, f, d, depth = [int(v) for v in sys.argv[2:6]]
     grow, score, iters, seed, out = sys.argv[6], sys.argv[7], int(sys.argv[8]), int(sys.argv[9]), sys.argv[10]
     X, y = data(n, f, d, seed)
     m = make_reference(ref, input_dim=f, output_dim=d, max_depth=depth, n_bins=256, par_th=10, split_score_func=score,
                        generator_type="quantile", batch_size=n, grow_policy=grow, lrs=lrs_of(d))
     t = time.time()
-    loss = m.fit(X, None, y, iters, False, "MultiRMSE")
+    if mode == "fit":
+        loss = m.fit(X, None, y, iters, False, "MultiRMSE")
+        bias = np.array(m.get_bias(), copy=True)
+    else:
+        # GBRL.step boosting loop, gradients computed OUTSIDE the reference: its fit() path races on a shared temporary in
+        # MultiRMSE::get_loss_and_gradients (loss.cpp:42-57) when it runs on many threads (tests/golden/make_golden_full.py)
+        bias = y.astype(np.float64).mean(0).astype(np.float32)
+        m.set_bias(bias)
+        loss = 0.0
+        for it in range(iters):
+            p = np.array(m.predict(X, None), copy=True).reshape(n, d)
+            m.step(X, None, (p - y).astype(np.float32))
     dt = time.time() - t
     e = m.get_ensemble_data()
     o = {"fit_%s" % k: np.array(e[k], copy=True) for k in KEYS}
     o["fit_loss"] = np.float32(loss)
+    o["fit_bias"] = bias
     o["fit_pred_head"] = np.array(m.predict(X[:8192], None), copy=True).reshape(-1, d)
     o["seconds"] = np.float64(dt)
     np.savez(out, **o)

@@ -4,7 +4,8 @@
    tests/golden/make_golden_full.py in the build container: C1 at its true 10 000 x 16, one C2 / C3 / C5 / 1M x 128
    oblivious fit each at FULL size) -- only the seed and the resulting ensemble are stored, the inputs are regenerated;
  * the C2 / C3 / C5 families at full F, depth and n_bins on 65 536 - 131 072 rows against oracle/_ref run HERE (the GPU
-   box's host cores, one subprocess per case), >= 2 boosting iterations;
+   box's host cores, one subprocess per case), >= 2 boosting iterations, driven through GBRL.step with the reference's own
+   gradient stream (the reference's fit() path has a data race on many threads, see tests/golden/make_golden_full.py);
  * C4: the 100 000-tree ensemble is written in the reference's wire format, loaded by the reference, and the 8192 x 128
    predictions of both engines are compared.
 
@@ -19,7 +20,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_DIR, compare_ensembles, make_gpu, TOL
+from helpers import GOLDEN_DIR, compare_ensembles, make_gpu, numpy_predict, TOL
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -55,7 +56,18 @@ def _check_stats(m, tag):
     assert st["max_noise_ratio"] < 3.0, "%s: observed rounding noise %.2f units is not covered twice by the band (6)" % (tag, st["max_noise_ratio"])
 
 
-@pytest.mark.parametrize("name", ["c1", "c1_l2", "c2", "j3", "c3", "c5"])
+def _replay_steps(m, X, y, exp, bias, lrs, iters, oblivious):
+    """Boosting loop through GBRL.step with the REFERENCE's gradient stream g_t = predict_t(X) - y, rebuilt bit for bit from the
+    expected ensemble's first t trees (helpers.numpy_predict)."""
+    m.set_bias(np.asarray(bias, np.float32))
+    for it in range(iters):
+        p = numpy_predict(exp, X, bias, lrs, it, oblivious)
+        if it > 0:      # the engine's own predictions agree with the stream it is fed
+            assert np.abs(m.predict_numpy(X[:65536]).reshape(-1, y.shape[1]).astype(np.float64) - p[:65536]).max() <= TOL
+        m.step(X, None, (p - y).astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["c1", "c1_l2", "s_greedy", "s_obl", "c2", "c2s", "j3", "c3", "c5"])
 def test_full_size_golden_from_reference(name):
     path = os.path.join(GOLDEN_DIR, "full_%s.npz" % name)
     if not os.path.exists(path):
@@ -63,17 +75,21 @@ def test_full_size_golden_from_reference(name):
     z = np.load(path, allow_pickle=False)
     n, f, d, depth, bins, iters, batch, seed, T = [int(v) for v in z["cfg"]]
     lrs = [(float(a), int(b), int(c)) for a, b, c in z["lrs"]]
+    mode = str(z["mode"]) if "mode" in z.files else "fit"
     X, y = _data(n, f, d, seed)
     m = _engine(f, d, depth, str(z["grow"]), str(z["score"]), n, lrs, T)
-    loss = m.fit(X, None, y, iters, False, "MultiRMSE")
     exp = {k: z["fit_" + k] for k in KEYS}
+    if mode == "fit":
+        loss = m.fit(X, None, y, iters, False, "MultiRMSE")
+        assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
+        assert np.abs(m.get_bias().astype(np.float64) - z["fit_bias"]).max() <= 1e-6
+    else:
+        _replay_steps(m, X, y, exp, z["fit_bias"], lrs, iters, str(z["grow"]) == "oblivious")
     compare_ensembles(exp, m.get_ensemble_data(), "full-size %s" % name)
-    assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
     head = z["fit_pred_head"]
     got = m.predict_numpy(X[:head.shape[0]]).reshape(head.shape)
     assert np.abs(got.astype(np.float64) - head).max() <= TOL
-    assert np.abs(m.get_bias().astype(np.float64) - z["fit_bias"]).max() <= 1e-6
-    _check_stats(m, "golden full_%s n=%d" % (name, n))
+    _check_stats(m, "golden full_%s n=%d (%s)" % (name, n, mode))
 
 
 FAMILIES = [
@@ -94,19 +110,42 @@ def test_baseline_family_vs_compiled_reference(name, n, f, d, depth, grow, score
     seed = 4242 + n % 89 + f
     out = str(tmp_path / "ref.npz")
     env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_fit_worker.py"), "fit", str(n), str(f), str(d), str(depth),
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_fit_worker.py"), "step", str(n), str(f), str(d), str(depth),
                         grow, score, str(iters), str(seed), out], capture_output=True, text=True, timeout=1500, env=env)
     assert r.returncode == 0 and "REF_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     z = np.load(out)
     X, y = _data(n, f, d, seed)
     lrs = [(0.1, 0, 1)] if d == 1 else [(0.1, 0, d - 1), (0.01, d - 1, d)]
     m = _engine(f, d, depth, grow, score, n, lrs, cores)
-    loss = m.fit(X, None, y, iters, False, "MultiRMSE")
-    compare_ensembles({k: z["fit_" + k] for k in KEYS}, m.get_ensemble_data(), name)
-    assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
+    exp = {k: z["fit_" + k] for k in KEYS}
+    _replay_steps(m, X, y, exp, z["fit_bias"], lrs, iters, grow == "oblivious")
+    compare_ensembles(exp, m.get_ensemble_data(), name)
     head = z["fit_pred_head"]
     assert np.abs(m.predict_numpy(X[:head.shape[0]]).reshape(head.shape).astype(np.float64) - head).max() <= TOL
     _check_stats(m, "%s n=%d T=%d (reference: %.1f s)" % (name, n, cores, float(z["seconds"])))
+
+
+@pytest.mark.parametrize("n,f,d,depth,grow,score", [(65536, 32, 1, 5, "greedy", "L2"), (50000, 24, 2, 5, "oblivious", "cosine")])
+def test_fit_path_vs_compiled_reference_single_thread(n, f, d, depth, grow, score, tmp_path):
+    """The supervised fit() loop (MultiRMSE, fitter.cpp:117-261) against the reference run on ONE thread, where its shared
+    temporaries cannot race: ensembles, loss and bias."""
+    from oracle.oracle import load_reference
+    if load_reference() is None:
+        pytest.skip("oracle/_ref not built")
+    seed, iters, out = 977 + f, 3, str(tmp_path / "ref.npz")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_fit_worker.py"), "fit", str(n), str(f), str(d), str(depth),
+                        grow, score, str(iters), str(seed), out], capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0 and "REF_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    z = np.load(out)
+    X, y = _data(n, f, d, seed)
+    lrs = [(0.1, 0, 1)] if d == 1 else [(0.1, 0, d - 1), (0.01, d - 1, d)]
+    m = _engine(f, d, depth, grow, score, n, lrs, 1)
+    loss = m.fit(X, None, y, iters, False, "MultiRMSE")
+    compare_ensembles({k: z["fit_" + k] for k in KEYS}, m.get_ensemble_data(), "fit T=1")
+    assert abs(loss - float(z["fit_loss"])) <= 1e-5 * max(1.0, abs(float(z["fit_loss"])))
+    assert np.abs(m.get_bias().astype(np.float64) - z["fit_bias"]).max() <= 1e-6
+    _check_stats(m, "fit T=1 n=%d f=%d %s %s" % (n, f, grow, score))
 
 
 def test_c4_predict_100k_trees_vs_compiled_reference(tmp_path):
