@@ -77,8 +77,15 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     ws.tile_hi = (int)((long long)ws.nT * (tg + 1) / gt);
     const size_t n1 = (size_t)(N > 0 ? N : 1);
     ws.order[0].ensure(n1 * sizeof(int)); ws.order[1].ensure(n1 * sizeof(int));
-    ws.nid.ensure(n1 * sizeof(int)); ws.rflag.ensure(n1); ws.rscan.ensure(n1 * sizeof(int));
-    ws.chunk_sums.ensure((size_t)(ceil_div((int)n1, 2048) + 1) * sizeof(int));
+    ws.nid.ensure(n1 * sizeof(int)); ws.rflag.ensure(n1 * sizeof(uint16_t) + 16);
+    {   // chunk totals / prefixes of the partition + its "CTAs done" counter (kept zero between launches)
+        const int cap = ceil_div((int)n1, 2048) + 1;
+        if (cap > ws.chunk_cap || !ws.chunk_sums.p) {
+            ws.chunk_cap = cap;
+            ws.chunk_sums.ensure((size_t)(cap + 1) * sizeof(int));
+            GB_CUDA(cudaMemsetAsync(ws.chunk_sums.p, 0, (size_t)(cap + 1) * sizeof(int), s));
+        }
+    }
     const int lv = md > 0 ? md - 1 : 0;
     const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + D) * sizeof(long long);
     ws.hist[0].ensure(slot_bytes << lv); ws.hist[1].ensure(slot_bytes << lv);

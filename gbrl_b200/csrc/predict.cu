@@ -79,98 +79,206 @@ __global__ void __launch_bounds__(128) predict_kernel(PredictParams P) {
         if (d < P.D) P.preds[(size_t)i * P.D + d] = theta[d];
 }
 
-// ---------------------------------------------------------------- tree-chunked predict (rollout shape)
-// BASELINE config 4 (100k trees x 8192 observations): 8192 samples cannot fill 148 SMs with one thread per sample, so
-// the tree range is cut into chunks: a CTA owns 32 samples (lane = sample) x one chunk of trees, its 4 warps split
-// the chunk.  The 32 observations are staged transposed in shared memory (xT[f][33]: lane == bank, conflict-free
-// for the uniform feature index of a tree level); tree parameters are warp-uniform loads.  Partial sums per chunk
-// are written out and combined in chunk order by a second kernel, so the result is deterministic (the reference's
-// own tree-parallel mode also sums per-thread partial buffers, predictor.cpp:147-165); agreement with the
-// sequential order is within float rounding (<= 1e-5 is tested).
+// ---------------------------------------------------------------- rollout-shape predict (BASELINE config 4)
+// 100k trees x 8192 observations: one thread per observation cannot fill 148 SMs, and cutting the tree range into
+// independently summed chunks changes the summation order -- at 100k trees the reference's own sequential fp32 rounding is
+// already 2e-5, so only the reference's ORDER gives predictions within 1e-5 of it.  What is sequential in
+// theta <- fl(theta - fl(lr * v_t)) (optimizer.cpp:110-118) is one FADD per (tree, output) -- 4 cycles; everything else (the
+// walk, the value gather, lr * v) is order-free.  So a CTA owns 64 observations and splits its warps:
+//   producer warps   walk the trees of the current chunk for a 32-observation sub-tile (lane = observation, features
+//                    transposed in shared memory: lane == bank) and store x = lr * v[leaf] into a shared element ring;
+//   consumer warps   (one per sub-tile) apply the PREVIOUS chunk's elements in tree order: theta = theta - x, bit for bit the
+//                    reference's sample-parallel / serial mode (predictor.cpp:167-178).
+// The split parameters and leaf values of a chunk are contiguous in the reference's SoA layout (types.h:279-304), so one
+// elected thread brings them into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), double
+// buffered one chunk ahead: the ensemble is read from L2 once per 64 observations instead of once per warp and tree.
+constexpr int PT_SAMPLES = 64, PT_SUB = 2, PT_WARPS = 16, PT_CONS = PT_SUB, PT_PROD = PT_WARPS - PT_CONS;
+constexpr int PT_XS = PT_SAMPLES + 1;          // row stride of the transposed observation tile (bank == lane)
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tPT_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra PT_DONE;\n\tbra PT_WAIT;\n\tPT_DONE:\n\t}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+
+struct TileLayout {          // byte offsets inside the dynamic shared memory of predict_tiles_kernel
+    int xT, stage[2], elems[2], bars;
+    int fi, fv, dep, ti, val;            // inside a stage
+    int val_bytes, stage_bytes, total;
+};
+static TileLayout tile_layout(int F, int md, int DM, int TC, int val_bytes) {
+    auto up = [](int v) { return (v + 127) & ~127; };
+    TileLayout L;
+    int o = 0;
+    L.xT = o; o += up(F * PT_XS * 4);
+    L.fi = 0; int so = up(TC * md * 4);
+    L.fv = so; so += up(TC * md * 4);
+    L.dep = so; so += up(TC * 4);
+    L.ti = so; so += up((TC + 4) * 4);
+    L.val = so; so += up(val_bytes + 16);
+    L.val_bytes = val_bytes; L.stage_bytes = so;
+    L.stage[0] = o; o += so; L.stage[1] = o; o += so;
+    const int eb = up(TC * PT_SUB * DM * 32 * 4);
+    L.elems[0] = o; o += eb; L.elems[1] = o; o += eb;
+    L.bars = o; o += 128;
+    L.total = o;
+    return L;
+}
+
 template <int DM>
-__global__ void __launch_bounds__(128) predict_chunk_kernel(PredictParams P, float *__restrict__ partials, int trees_per_chunk) {
-    extern __shared__ float xT[];                      // [F][33]
-    __shared__ float red[4][32][DM];
-    const int tile = blockIdx.x, chunk = blockIdx.y;
+__global__ void __launch_bounds__(PT_WARPS * 32, 1)
+predict_tiles_kernel(PredictParams P, TileLayout L, int TC, int n_trees_total, int n_leaves_total, long long val_capacity_floats) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_opt_of_dim[DM];
+    __shared__ int s_voff[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s0 = tile * 32;
-    for (int idx = threadIdx.x; idx < P.F * 32; idx += 128) {
-        const int s = idx / P.F, f = idx % P.F;
-        xT[f * 33 + s] = (s0 + s < P.N) ? P.X[(size_t)(s0 + s) * P.F + f] : 0.0f;
+    const int s0 = blockIdx.x * PT_SAMPLES;
+    const int md = P.md, D = P.D;
+    float *xT = reinterpret_cast<float *>(smem + L.xT);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bar[2] = {sbase + (uint32_t)L.bars, sbase + (uint32_t)L.bars + 8u};
+    // chunks are aligned to absolute multiples of TC so that every bulk copy starts on a 16-byte boundary
+    const int c_first = P.start_tree / TC, c_last = (P.stop_tree - 1) / TC;      // stop_tree > start_tree (checked by the launcher)
+    const int n_chunks = c_last - c_first + 1;
+
+    if (threadIdx.x == 0) { mbar_init(bar[0], 1); mbar_init(bar[1], 1); }
+    if (threadIdx.x < DM) {
+        int o_of = -1;
+        for (int o = 0; o < P.n_opts; ++o)
+            if ((int)threadIdx.x >= P.opts[o].start_idx && (int)threadIdx.x < P.opts[o].stop_idx) o_of = o;
+        s_opt_of_dim[threadIdx.x] = o_of;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // observations, transposed: xT[f][sample]
+    for (int idx = threadIdx.x; idx < P.F * PT_SAMPLES; idx += PT_WARPS * 32) {
+        const int sm = idx / P.F, f = idx - sm * P.F;
+        xT[f * PT_XS + sm] = (s0 + sm < P.N) ? P.X[(size_t)(s0 + sm) * P.F + f] : 0.0f;
     }
     __syncthreads();
-    const int c0 = P.start_tree + chunk * trees_per_chunk;
-    const int c1 = min(P.stop_tree, c0 + trees_per_chunk);
-    const int per_warp = (c1 - c0 + 3) / 4;
-    const int t0 = c0 + warp * per_warp, t1 = min(c1, t0 + per_warp);
-    float acc[DM];
+
+    // one elected thread: TMA bulk copies of a chunk's split parameters and leaf values into stage `b`
+    auto issue_chunk = [&](int c, int b) {
+        const int t0 = (c_first + c) * TC;
+        const int tcnt = min(TC, n_trees_total - t0);
+        const uint32_t st = sbase + (uint32_t)L.stage[b];
+        const int l0 = P.tree_indices[t0];
+        const int l1 = (t0 + tcnt < n_trees_total) ? P.tree_indices[t0 + tcnt] : n_leaves_total;
+        const long long v0 = (long long)l0 * D, v1 = (long long)l1 * D;
+        const long long a0 = v0 & ~3ll;                                   // align the start down to 16 bytes
+        long long a1 = (v1 + 3) & ~3ll;
+        if (a1 > val_capacity_floats) a1 = val_capacity_floats & ~3ll;    // never read past the allocation
+        s_voff[b] = (int)(v0 - a0);
+        const uint32_t b_fi = (uint32_t)(((tcnt * md * 4) + 15) & ~15), b_dep = (uint32_t)(((tcnt * 4) + 15) & ~15);
+        const uint32_t b_ti = (uint32_t)((((tcnt + 1) * 4) + 15) & ~15), b_val = (uint32_t)((a1 - a0) * 4);
+        mbar_expect_tx(bar[b], 2 * b_fi + b_dep + b_ti + b_val);
+        tma_bulk_g2s(st + L.fi, P.feature_indices + (size_t)t0 * md, b_fi, bar[b]);
+        tma_bulk_g2s(st + L.fv, P.feature_values + (size_t)t0 * md, b_fi, bar[b]);
+        tma_bulk_g2s(st + L.dep, P.depths + t0, b_dep, bar[b]);
+        tma_bulk_g2s(st + L.ti, P.tree_indices + t0, b_ti, bar[b]);
+        if (b_val) tma_bulk_g2s(st + L.val, P.values + a0, b_val, bar[b]);
+    };
+    if (threadIdx.x == 0) issue_chunk(0, 0);
+
+    float theta[DM];
+    const int csub = warp;                                   // consumer warps 0 .. PT_CONS-1 own sub-tile `warp`
+    if (warp < PT_CONS) {
+        const int i = s0 + csub * 32 + lane;
 #pragma unroll
-    for (int d = 0; d < DM; ++d) acc[d] = 0.0f;
-    const int md = P.md;
-    for (int t = t0; t < t1; ++t) {
-        int leaf;
-        if (P.oblivious) {
-            const int dep = P.depths[t];
-            int li = 0;
-            for (int k = 0; k < dep; ++k) {
-                const int f = P.feature_indices[(size_t)t * md + k];
-                const float thr = P.feature_values[(size_t)t * md + k];
-                li |= (xT[f * 33 + lane] > thr ? 1 : 0) << (dep - 1 - k);
-            }
-            leaf = P.tree_indices[t] + li;
-        } else {
-            const int *hf = P.heap_feat + (size_t)t * (1 << md);
-            const float *ht = P.heap_thr + (size_t)t * (1 << md);
-            int h = 0, f = hf[0];
-            if (f < 0) continue;
-            while (f >= 0) {
-                h = 2 * h + 1 + (xT[f * 33 + lane] > ht[h] ? 1 : 0);
-                f = (h < (1 << md) - 1) ? hf[h] : -1;
-            }
-            leaf = P.tree_indices[t] + P.heap_leaf[(size_t)t * (2 << md) + h];
+        for (int d = 0; d < DM; ++d) theta[d] = (d < D && i < P.N) ? (P.add_bias ? P.bias[d] : P.preds[(size_t)i * D + d]) : 0.0f;
+    }
+    uint32_t phase[2] = {0u, 0u};
+#pragma unroll 1
+    for (int c = 0; c <= n_chunks; ++c) {
+        const int b = c & 1;
+        if (c < n_chunks) {
+            if (threadIdx.x == 0 && c + 1 < n_chunks) issue_chunk(c + 1, b ^ 1);      // stage b^1 was last read in iteration c-1
+            mbar_wait(bar[b], phase[b]);
+            phase[b] ^= 1u;
         }
-        const float *v = P.values + (size_t)leaf * P.D;
-        for (int o = 0; o < P.n_opts; ++o) {
-            const DevOpt op = P.opts[o];
-            const float lr = sched_lr(op, t);
+        if (warp >= PT_CONS) {
+            if (c < n_chunks) {
+                // ---- producers: elements of chunk c
+                const int t0 = (c_first + c) * TC;
+                const int tcnt = min(TC, n_trees_total - t0);
+                const unsigned char *st = smem + L.stage[b];
+                const int *fi = reinterpret_cast<const int *>(st + L.fi);
+                const float *fv = reinterpret_cast<const float *>(st + L.fv);
+                const int *dep = reinterpret_cast<const int *>(st + L.dep);
+                const int *ti = reinterpret_cast<const int *>(st + L.ti);
+                const float *val = reinterpret_cast<const float *>(st + L.val) + s_voff[b];
+                float *E = reinterpret_cast<float *>(smem + L.elems[b]);
+                const int lbase = ti[0];
+                for (int task = warp - PT_CONS; task < tcnt * PT_SUB; task += PT_PROD) {
+                    const int j = task / PT_SUB, sub = task - j * PT_SUB;
+                    const int t = t0 + j;
+                    float *e = E + ((size_t)(j * PT_SUB + sub) * DM) * 32 + lane;
+                    if (t < P.start_tree || t >= P.stop_tree) continue;
+                    const int dj = dep[j];
+                    int li = 0;
+                    for (int k = 0; k < dj; ++k) {                                           // predictor.cpp:248-252
+                        const int f = fi[j * md + k];
+                        li |= (xT[f * PT_XS + sub * 32 + lane] > fv[j * md + k] ? 1 : 0) << (dj - 1 - k);
+                    }
+                    const float *v = val + (size_t)(ti[j] - lbase + li) * D;
+#pragma unroll
+                    for (int d = 0; d < DM; ++d) {
+                        float x = 0.0f;
+                        if (d < D) {
+                            const int o = s_opt_of_dim[d];
+                            if (o >= 0) x = sched_lr(P.opts[o], t) * v[d];                   // optimizer.cpp:110-118: lr * value ...
+                        }
+                        e[d * 32] = x;
+                    }
+                }
+            }
+        } else if (c > 0) {
+            // ---- consumers: chunk c-1, in tree order:  theta = theta - lr * value
+            const int t0 = (c_first + c - 1) * TC;
+            const int tcnt = min(TC, n_trees_total - t0);
+            const float *E = reinterpret_cast<const float *>(smem + L.elems[b ^ 1]);
+            const int j0 = max(0, P.start_tree - t0), j1 = min(tcnt, P.stop_tree - t0);
+            for (int j = j0; j < j1; ++j) {
+                const float *e = E + ((size_t)(j * PT_SUB + csub) * DM) * 32 + lane;
+#pragma unroll
+                for (int d = 0; d < DM; ++d) theta[d] = theta[d] - e[d * 32];
+            }
+        }
+        __syncthreads();
+    }
+    if (warp < PT_CONS) {
+        const int i = s0 + csub * 32 + lane;
+        if (i < P.N) {
 #pragma unroll
             for (int d = 0; d < DM; ++d)
-                if (d >= op.start_idx && d < op.stop_idx) acc[d] = acc[d] - lr * v[d];
+                if (d < D) P.preds[(size_t)i * D + d] = theta[d];
         }
     }
-#pragma unroll
-    for (int d = 0; d < DM; ++d) red[warp][lane][d] = acc[d];
-    __syncthreads();
-    if (warp == 0 && s0 + lane < P.N) {
-#pragma unroll
-        for (int d = 0; d < DM; ++d) {
-            if (d < P.D) {
-                float sum = red[0][lane][d];
-                sum = sum + red[1][lane][d]; sum = sum + red[2][lane][d]; sum = sum + red[3][lane][d];
-                partials[((size_t)chunk * P.N + s0 + lane) * P.D + d] = sum;
-            }
-        }
-    }
-}
-
-__global__ void predict_combine_kernel(const float *__restrict__ partials, const float *__restrict__ bias, float *__restrict__ preds,
-                                       int N, int D, int n_chunks, int add_bias) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)N * D) return;
-    float acc = add_bias ? bias[i % D] : preds[i];
-    for (int c = 0; c < n_chunks; ++c) acc = acc + partials[(size_t)c * N * D + i];
-    preds[i] = acc;
 }
 
 template <int DM>
-static void launch_predict_chunked(Model &m, const PredictParams &P, int n_chunks, int tpc, cudaStream_t s) {
-    const size_t smem = (size_t)P.F * 33 * sizeof(float);
-    if (smem > 48 * 1024) ensure_dyn_smem(predict_chunk_kernel<DM>, smem);
-    m.ws.pred_partials.ensure((size_t)n_chunks * P.N * P.D * sizeof(float));
-    dim3 grid(ceil_div(P.N, 32), n_chunks);
-    GB_LAUNCH(predict_chunk_kernel<DM>, grid, 128, smem, s, P, m.ws.pred_partials.as<float>(), tpc);
-    GB_LAUNCH(predict_combine_kernel, ceil_div(P.N * P.D, 256), 256, 0, s, m.ws.pred_partials.as<float>(), P.bias, P.preds, P.N, P.D,
-              n_chunks, P.add_bias);
+static bool launch_predict_tiles(Model &m, const PredictParams &P, cudaStream_t s) {
+    const Ensemble &e = m.ens;
+    const int md = P.md > 0 ? P.md : 1;
+    // trees per chunk: the leaf values of a chunk (<= TC * 2^md * D floats) must fit a 32 KB stage
+    int TC = 64;
+    while (TC > 4 && (long long)TC * (1ll << md) * P.D * 4 > 32768) TC >>= 1;
+    if ((long long)TC * (1ll << md) * P.D * 4 > 32768) return false;
+    const int val_bytes = TC * (1 << md) * P.D * 4 + 32;
+    const TileLayout L = tile_layout(P.F, md, DM, TC, val_bytes);
+    if (L.total > 220 * 1024) return false;
+    ensure_dyn_smem(predict_tiles_kernel<DM>, (size_t)L.total);
+    GB_LAUNCH(predict_tiles_kernel<DM>, ceil_div(P.N, PT_SAMPLES), PT_WARPS * 32, (size_t)L.total, s, P, L, TC, e.n_trees, e.n_leaves,
+              (long long)(e.values.bytes / sizeof(float)));
+    return true;
 }
 
 void upload_optimizers(Model &m, cudaStream_t s) {
@@ -204,20 +312,19 @@ void launch_predict(Model &m, const float *X, int N, int F, int start_tree, int 
     P.N = N; P.F = F; P.D = m.cfg.output_dim; P.md = m.cfg.max_depth; P.start_tree = start_tree; P.stop_tree = stop_tree;
     P.add_bias = add_bias ? 1 : 0; P.oblivious = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
     const int D = P.D;
-    // rollout shape: few samples, many trees -> cut the tree range into chunks (see predict_chunk_kernel)
+    // rollout shape (many trees): parallel walks + ordered accumulation (predict_tiles_kernel); oblivious trees, disjoint
+    // optimizer ranges (every output belongs to at most one optimizer: the learners' layout, actor_critic_learner.py:88)
     const int n_t = stop_tree - start_tree;
-    const int tiles = ceil_div(N, 32);
-    if (n_t >= 1024 && tiles * 4 < 148 * 24 && D <= 8 && (size_t)F * 33 * 4 <= 200 * 1024) {
-        int n_chunks = ceil_div(148 * 8, tiles);
-        if (n_chunks > n_t / 128) n_chunks = n_t / 128;
-        if (n_chunks < 1) n_chunks = 1;
-        const int tpc = ceil_div(n_t, n_chunks);
-        n_chunks = ceil_div(n_t, tpc);
-        if (D <= 1) launch_predict_chunked<1>(m, P, n_chunks, tpc, s);
-        else if (D <= 2) launch_predict_chunked<2>(m, P, n_chunks, tpc, s);
-        else if (D <= 4) launch_predict_chunked<4>(m, P, n_chunks, tpc, s);
-        else launch_predict_chunked<8>(m, P, n_chunks, tpc, s);
-        return;
+    bool disjoint = true;
+    for (size_t a = 0; a < m.opts.size(); ++a)
+        for (size_t b2 = a + 1; b2 < m.opts.size(); ++b2)
+            if (m.opts[a].start_idx < m.opts[b2].stop_idx && m.opts[b2].start_idx < m.opts[a].stop_idx) disjoint = false;
+    if (P.oblivious && n_t >= 256 && D <= 4 && disjoint && e.n_trees > 0) {
+        bool done = false;
+        if (D <= 1) done = launch_predict_tiles<1>(m, P, s);
+        else if (D <= 2) done = launch_predict_tiles<2>(m, P, s);
+        else done = launch_predict_tiles<4>(m, P, s);
+        if (done) return;
     }
     if (D <= 1) launch_predict_dm<1>(P, s);
     else if (D <= 2) launch_predict_dm<2>(P, s);

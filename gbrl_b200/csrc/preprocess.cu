@@ -326,9 +326,9 @@ __global__ void __launch_bounds__(128) dense_sim_kernel(DenseWide P) {
     spec::Cand cd[spec::J];
     spec::sim_group(P.pred[u], cnt, el, hd, cd);
     P.head[u] = hd;
-    if (hd.info & spec::F_CANDS) {
+    if (spec::head_flags(hd) & spec::F_CANDS) {
 #pragma unroll
-        for (int j = 1; j < spec::J; ++j) P.cand[(size_t)u * spec::J + j] = cd[j];
+        for (int j = 0; j < spec::J; ++j) P.cand[(size_t)u * spec::J + j] = cd[j];
     }
 }
 

@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(128) wide_sim_kernel(ReplayParams P, NodeArray
         spec::sim_group(pr, PASS == 0 ? rows : rows * D, el, hd, cd);
         const size_t o = (size_t)g * 2 * D + c;
         Wd.head[o] = hd;
-        if (hd.info & spec::F_CANDS) {
+        if (spec::head_flags(hd) & spec::F_CANDS) {
 #pragma unroll
-            for (int j = 1; j < spec::J; ++j) Wd.cand[o * spec::J + j] = cd[j];
+            for (int j = 0; j < spec::J; ++j) Wd.cand[o * spec::J + j] = cd[j];
         }
     }
 }
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
     constexpr int EPR = PASS == 0 ? 1 : D;                      // chain elements per row
     __shared__ float s_sum[2 * D];
     __shared__ float s_mean[2 * D];
-    const unsigned int full = 0xffffffffu;
+    __shared__ __align__(16) float s_wbuf[NCH][256 * EPR];      // per chain warp: staging of a group that is run sequentially
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
     if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
@@ -259,16 +259,11 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
                 e2.g = S.G + ((size_t)s0 + (size_t)g * GROUP_ROWS) * D;
                 e2.w = S.bits + S.woff[it] + g * 8;
                 const int cnt = min(GROUP_ROWS, n - g * GROUP_ROWS) * EPR;
-                float x[8 * EPR];
+                float x[8 * EPR];                                 // the lane's 8 * EPR consecutive chain elements
 #pragma unroll
-                for (int i = 0; i < 8 * EPR; ++i) { const int k = i * 32 + lane; x[i] = k < cnt ? e2(k) : 0.0f; }
-#pragma unroll
-                for (int i = 0; i < 8 * EPR; ++i) {
-                    if (i * 32 < cnt) {
-#pragma unroll
-                        for (int l = 0; l < 32; ++l) a = a + __shfl_sync(full, x[i], l);
-                    }
-                }
+                for (int i = 0; i < 8 * EPR; ++i) { const int k = lane * 8 * EPR + i; x[i] = k < cnt ? e2(k) : 0.0f; }
+                int dummy = 0;
+                a = seq::warp_seq_block<8 * EPR>(a, x, s_wbuf[c], dummy);      // broadcast LDS.128 feed: the speed of the FADD chain
                 return a;
             };
             const float acc = spec::walk_chain(ng, 0.0f, load_head, load_cand, seq_group, n_err, n_seq);

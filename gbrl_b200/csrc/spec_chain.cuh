@@ -27,27 +27,34 @@ namespace gb {
 namespace spec {
 
 constexpr int J = 8;                       // candidate starts per group (power of two)
-constexpr uint32_t F_NOSIM = 1u << 8;      // no usable prediction (zero / tiny / non-finite): always run sequentially
-constexpr uint32_t F_CANDS = 1u << 9;      // candidates 1..J-1 were simulated as well
+// flags in the low byte of Head::mflags
+constexpr uint32_t F_NOSIM = 1u;           // no usable prediction (zero / tiny / non-finite): always run sequentially
+constexpr uint32_t F_PFREE = 2u;           // candidate 0 serves every start on ulp(p)'s lattice (its own lattice is not coarser)
+constexpr uint32_t F_SIMPLE = 4u;          // candidates 0 / 1 (even / odd start) serve every start: lattice <= 2 ulp(p)
+constexpr uint32_t F_CANDS = 8u;           // the per-candidate records cand[0 .. J) were written
 constexpr float MARGIN_INF = 1.0e38f;
 
-// group record: head (candidate 0) + J-1 further candidates
+// group record.  The walk's fast path only needs the head: with a = c0 + D * ulp(p) the group maps
+//     a -> a + inc0            (D even, or F_PFREE)          inc0 = end0 - c0
+//     a -> a + inc0 + d1       (D odd)                        inc1 = end1 - (c0 + ulp)
+// provided |D - parity| * ulp < margin.  Everything else goes through the per-candidate records.
 struct Head {
     float c0;          // candidate 0: p with the low log2(J) mantissa bits cleared
     float end0;        // simulated end value from c0
-    float margin0;     // |delta| must be < margin0  (0 = only delta == 0 is usable)
-    uint32_t info;     // bits 0-7: lattice exponent el0 (delta must be a multiple of 2^(el0-150)); F_* flags
+    float d1;          // inc1 - inc0 (exact)
+    float mflags;      // min margin of candidates 0 / 1, low 8 mantissa bits replaced by the F_* flags
 };
 struct Cand { float end; float margin_el; };      // margin with its low 8 mantissa bits replaced by the lattice exponent
+__device__ __forceinline__ uint32_t head_flags(const Head &h) { return __float_as_uint(h.mflags) & 0xffu; }
 
-__device__ __forceinline__ float pack_margin(float margin, int el) {
+__device__ __forceinline__ float pack_margin(float margin, int low8) {
     if (!(margin > 0.0f)) margin = 0.0f;
     if (margin > MARGIN_INF) margin = MARGIN_INF;
-    return __uint_as_float((__float_as_uint(margin) & 0xffffff00u) | (uint32_t)(el & 0xff));     // rounds the margin DOWN
+    return __uint_as_float((__float_as_uint(margin) & 0xffffff00u) | (uint32_t)(low8 & 0xff));     // rounds the margin DOWN
 }
-__device__ __forceinline__ float unpack_margin(float packed, int &el) {
+__device__ __forceinline__ float unpack_margin(float packed, int &low8) {
     const uint32_t b = __float_as_uint(packed);
-    el = (int)(b & 0xffu);
+    low8 = (int)(b & 0xffu);
     return __uint_as_float(b & 0xffffff00u);
 }
 
@@ -90,12 +97,12 @@ struct Sim {
 
 // ---------------------------------------------------------------- simulation of one group (one lane)
 // elem(k), k in [0, cnt): the group's chain elements in order (+0 for "not a member").  Writes the head and, when the
-// lattice of candidate 0 is coarser than ulp(p), the other J-1 candidates.
+// lattice of candidate 0 is coarser than ulp(p), the per-candidate records.
 template <class Elem>
-__device__ __forceinline__ void sim_group(float p, int cnt, const Elem &elem, Head &hd, Cand *cands /* [J] , entry 0 unused */) {
+__device__ __forceinline__ void sim_group(float p, int cnt, const Elem &elem, Head &hd, Cand *cands /* [J] */) {
     float c0 = 0.0f, us = 0.0f;
     int pe = 0;
-    if (!cand_base(p, c0, us, pe)) { hd.c0 = 0.0f; hd.end0 = 0.0f; hd.margin0 = 0.0f; hd.info = F_NOSIM; return; }
+    if (!cand_base(p, c0, us, pe)) { hd.c0 = 0.0f; hd.end0 = 0.0f; hd.d1 = 0.0f; hd.mflags = pack_margin(0.0f, F_NOSIM); return; }
     Sim a;
     a.init(c0);
     bool any = false;
@@ -104,15 +111,14 @@ __device__ __forceinline__ void sim_group(float p, int cnt, const Elem &elem, He
         any |= !(x == 0.0f);
         a.step(x);
     }
-    hd.c0 = c0;
+    hd.c0 = c0; hd.d1 = 0.0f;
     if (!any) {                                   // s + 0 == s for every s: the group is the identity on any start
-        hd.end0 = c0; hd.margin0 = MARGIN_INF; hd.info = 0u;
+        hd.end0 = c0; hd.mflags = pack_margin(MARGIN_INF, F_PFREE);
         return;
     }
     const int el0 = a.lattice_exp();
-    hd.end0 = a.s; hd.margin0 = a.margin > 0.0f ? a.margin : 0.0f; hd.info = (uint32_t)(el0 & 0xff);
-    if (el0 <= pe) return;                        // every multiple of ulp(p) is on candidate 0's lattice already
-    hd.info |= F_CANDS;
+    hd.end0 = a.s;
+    if (el0 <= pe) { hd.mflags = pack_margin(a.margin, F_PFREE); return; }     // every multiple of ulp(p) is on candidate 0's lattice
     Sim c[J - 1];
 #pragma unroll
     for (int j = 1; j < J; ++j) c[j - 1].init(c0 + (float)j * us);      // exact: same binade as c0 (low bits were cleared)
@@ -121,8 +127,16 @@ __device__ __forceinline__ void sim_group(float p, int cnt, const Elem &elem, He
 #pragma unroll
         for (int j = 0; j < J - 1; ++j) c[j].step(x);                    // J-1 independent chains: the FADD latency is hidden by ILP
     }
+    cands[0].end = a.s; cands[0].margin_el = pack_margin(a.margin, el0);
 #pragma unroll
     for (int j = 1; j < J; ++j) { cands[j].end = c[j - 1].s; cands[j].margin_el = pack_margin(c[j - 1].margin, c[j - 1].lattice_exp()); }
+    // even / odd starts through candidates 0 / 1 alone?  (both lattices at most 2 ulp(p); the increment difference a float)
+    const int el1 = c[0].lattice_exp();
+    const double inc0 = (double)a.s - (double)c0, inc1 = (double)c[0].s - ((double)c0 + (double)us);
+    const float d1 = (float)(inc1 - inc0);
+    uint32_t fl = F_CANDS;
+    if (el0 <= pe + 1 && el1 <= pe + 1 && (double)d1 == inc1 - inc0) { fl |= F_SIMPLE; hd.d1 = d1; }
+    hd.mflags = pack_margin(fminf(a.margin, c[0].margin), fl);
 }
 
 // ---------------------------------------------------------------- helpers of the walk
@@ -152,102 +166,120 @@ __device__ __forceinline__ bool shift_ok(double delta, float margin, int el) {
 // The walk of ONE chain by one warp.
 //   ng                 number of groups
 //   load_head(g)       -> Head of group g           (called by lane g - w0 for the 32 groups of a window)
-//   load_cand(g, j)    -> Cand j (1..J-1) of group g (only for groups with F_CANDS)
+//   load_cand(g, j)    -> Cand j (0..J-1) of group g (only for groups with F_CANDS)
 //   seq_group(g, a)    -> runs group g as the plain sequential chain from the exact running sum a; WARP-collective
 // Returns the exact final sum (same value in every lane).  Counters: groups run sequentially; internal inconsistencies
-// (a running sum that is not a float -- cannot happen while the fp64 prefix is exact; tests assert it stays 0).
+// (a running sum that is not a float -- cannot happen while the arithmetic below is exact; tests assert it stays 0).
+//
+// Fast path: a RUN of consecutive groups whose candidates sit in the same binade as the run's first group and that are
+// served by candidates 0 / 1 is integer arithmetic in units of that binade's ulp: M <- M + I[parity(M)] (c0 has its low
+// bits cleared, so the parity of the running integer M is the parity of the group's own offset).  Two-entry tables compose
+// associatively, so one warp scan gives every group's incoming M; margins are then checked by all lanes at once.  The
+// first group that does not fit (other binade, coarser lattice, margin) is resolved on its own -- candidate records in
+// fp64, else the sequential chain -- and the scan resumes behind it.
 template <class LoadHead, class LoadCand, class SeqGroup>
 __device__ __forceinline__ float walk_chain(int ng, float a_start, LoadHead load_head, LoadCand load_cand, SeqGroup seq_group,
                                             int &n_err, int &n_seq) {
     const unsigned int full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    double base = (double)a_start;                      // exact running sum at the first live group of the window
+    double base = (double)a_start;                      // exact running sum at the first live group
+    Head nx;
+    nx.c0 = 0.0f; nx.end0 = 0.0f; nx.d1 = 0.0f; nx.mflags = 0.0f;
+    if (lane < ng) nx = load_head(lane);
 #pragma unroll 1
     for (int w0 = 0; w0 < ng; w0 += 32) {
         const int g = w0 + lane;
         const bool in_range = g < ng;
-        Head hd;
-        hd.c0 = 0.0f; hd.end0 = 0.0f; hd.margin0 = MARGIN_INF; hd.info = 0u;
-        if (in_range) hd = load_head(g);
-        Cand cd[J];
-        const bool has_cands = in_range && (hd.info & F_CANDS);
-        if (has_cands) {
+        const Head hd = nx;
+        if (w0 + 32 + lane < ng) nx = load_head(w0 + 32 + lane);          // next window's heads are in flight during this one
+        int flags;
+        const float margin = unpack_margin(hd.mflags, flags);
+        const uint32_t cb = __float_as_uint(hd.c0);
+        const int wn = min(32, ng - w0);
+        int live_from = 0;
+#pragma unroll 1
+        while (live_from < wn) {
+            // ---- the regular run starting at lane L = live_from
+            const int L = live_from;
+            const uint32_t cbL = __shfl_sync(full, cb, L);
+            const int peL = (int)((cbL >> 23) & 0xffu);
+            const float usL = __uint_as_float((cbL & 0x80000000u) | ((uint32_t)(peL > 23 ? peL - 23 : 1) << 23));
+            const double inv_us = 1.0 / (double)usL;                       // exact: a power of two
+            bool reg = in_range && lane >= L && !(flags & F_NOSIM) && (flags & (F_PFREE | F_SIMPLE)) && ((cb ^ cbL) >> 23) == 0u && peL >= 27;
+            int i0 = 0, i1 = 0, off = 0;
+            if (reg) {
+                const double q0 = ((double)hd.end0 - (double)hd.c0) * inv_us, q1 = q0 + (double)hd.d1 * inv_us;
+                const double qo = ((double)hd.c0 - (double)__uint_as_float(cbL)) * inv_us;
+                reg = q0 == rint(q0) && q1 == rint(q1) && fabs(q0) < 5.0e8 && fabs(q1) < 5.0e8 && fabs(qo) < 5.0e8;
+                if (reg) { i0 = (int)q0; i1 = (flags & F_PFREE) ? i0 : (int)q1; off = (int)qo; }
+            }
+            const double mLd = (base - (double)__uint_as_float(cbL)) * inv_us;   // incoming M of the run (units of usL)
+            const bool start_ok = mLd == rint(mLd) && fabs(mLd) < 5.0e8;
+            unsigned int stop = __ballot_sync(full, !reg && lane >= L);           // first lane that does not belong to the run
+            int R = stop ? (__ffs(stop) - 1) : 32;
+            if (!start_ok) R = L;
+            int F = L;                                                            // first lane NOT applied by the scan
+            if (R > L) {
+                const bool mine = lane >= L && lane < R;
+                int t0 = mine ? i0 : 0, t1 = mine ? i1 : 0;                        // inclusive composites for an even / odd M at lane L
 #pragma unroll
-            for (int j = 1; j < J; ++j) cd[j] = load_cand(g, j);
-        }
-        // the chosen candidate of this lane's group (0 until the walk says otherwise)
-        float c_sel = hd.c0, margin_sel = hd.margin0;
-        int el_sel = (int)(hd.info & 0xffu);
-        double inc_sel = in_range ? ((double)hd.end0 - (double)hd.c0) : 0.0;
-        bool nosim = in_range && (hd.info & F_NOSIM);
-        bool settled = false;                          // this lane's candidate choice is final
-        int live_from = 0;                             // lanes before it are consumed
-        // exactness guard of the fp64 prefix: exponent spread of everything that is added must stay below 2^29
-        {
-            int emin = 255, emax = 0;
-            if (in_range && !nosim) {
-                const int e1 = (int)((__float_as_uint(hd.c0) >> 23) & 0xff), e2 = (int)((__float_as_uint(hd.end0) >> 23) & 0xff);
-                emin = min(e1, e2 > 0 ? e2 : e1); emax = max(e1, e2);
-                if (has_cands) {
-#pragma unroll
-                    for (int j = 1; j < J; ++j) { const int e3 = (int)((__float_as_uint(cd[j].end) >> 23) & 0xff); emax = max(emax, e3); if (e3 > 0) emin = min(emin, e3); }
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int g0 = __shfl_up_sync(full, t0, o), g1 = __shfl_up_sync(full, t1, o);
+                    if (lane >= o) {
+                        const int n0 = g0 + ((g0 & 1) ? t1 : t0);
+                        const int n1 = g1 + (((g1 + 1) & 1) ? t1 : t0);
+                        t0 = n0; t1 = n1;
+                    }
+                }
+                const int mL = (int)mLd;
+                int e0 = __shfl_up_sync(full, t0, 1), e1 = __shfl_up_sync(full, t1, 1);
+                if (lane == 0) { e0 = 0; e1 = 0; }
+                const int M = mL + ((mL & 1) ? e1 : e0);                           // incoming running integer of this lane's group
+                const int Dg = M - off;                                            // the group's own offset: a = c0 + Dg * us
+                const int par = (flags & F_PFREE) ? 0 : (Dg & 1);
+                const bool okm = !mine || (fabsf((float)(Dg - par)) * fabsf(usL) < margin) || (Dg - par) == 0;
+                const unsigned int bad = __ballot_sync(full, !okm);
+                F = bad ? (__ffs(bad) - 1) : R;
+                if (F > L) {
+                    // lanes L .. F-1 are applied: the running integer behind lane F-1
+                    const int tot = __shfl_sync(full, (mL & 1) ? t1 : t0, F - 1);
+                    base = (double)__uint_as_float(cbL) + (double)(mL + tot) * (double)usL;
                 }
             }
-            emin = __reduce_min_sync(full, emin); emax = __reduce_max_sync(full, emax);
-            const int eb = (int)((__double2hiint(base) >> 20) & 0x7ff) - 1023 + 127;
-            if (base != 0.0) { emax = max(emax, eb); emin = min(emin, eb); }
-            if (emax - emin > 28) nosim = in_range;     // pathological dynamic range: run the window sequentially
-        }
-#pragma unroll 1
-        for (;;) {
-            const bool live = in_range && lane >= live_from;
-            // exclusive prefix of the chosen increments over the live lanes
-            double incv = live ? inc_sel : 0.0, pre = incv;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double v = shfl_up_d(pre, off);
-                if (lane >= off) pre += v;
-            }
-            const double tot = shfl_d(pre, 31);
-            const double A = base + (pre - incv);       // exact running sum at the start of this lane's group
-            bool ok = true;
-            if (live && !settled) ok = !nosim && shift_ok(A - (double)c_sel, margin_sel, el_sel) && ((double)(float)A == A);
-            const unsigned int bad = __ballot_sync(full, !ok);
-            if (!bad) { base += tot; break; }
-            const int F = __ffs(bad) - 1;
-            // lane F: is one of the other candidates usable for the actual start?
-            int found = 0;
-            if (lane == F && has_cands && !nosim && ((double)(float)A == A)) {
-                int pe; float c0, us;
-                cand_base(hd.c0, c0, us, pe);                              // hd.c0 has its low bits cleared already: c0 == hd.c0
-                const double D = (A - (double)hd.c0) / (double)us;
-                if (D == rint(D) && fabs(D) < 1.0e15) {
-                    const int j = (int)(((long long)D) & (long long)(J - 1));
-                    if (j != 0) {
-                        Cand cj = cd[1];
-#pragma unroll
-                        for (int t = 2; t < J; ++t) if (j == t) cj = cd[t];
-                        int el;
-                        const float mg = unpack_margin(cj.margin_el, el);
-                        const float cjv = hd.c0 + (float)j * us;
-                        if (shift_ok(A - (double)cjv, mg, el)) {
-                            c_sel = cjv; margin_sel = mg; el_sel = el; inc_sel = (double)cj.end - (double)cjv;
-                            found = 1;
+            live_from = F;
+            if (F >= wn) break;
+            // ---- group F on its own: candidate records in fp64, else the sequential chain
+            double nb = 0.0;
+            int how = 0;                                                           // 1: resolved from a record
+            if (lane == F && !(flags & F_NOSIM) && ((double)(float)base == base)) {
+                float c0, us;
+                int pe;
+                if (cand_base(hd.c0, c0, us, pe)) {
+                    const double delta = base - (double)hd.c0;
+                    if (flags & F_PFREE) {
+                        if (shift_ok(delta, margin, pe)) { nb = (double)hd.end0 + delta; how = 1; }
+                    } else if (flags & F_CANDS) {
+                        const double D = delta / (double)us;
+                        if (D == rint(D) && fabs(D) < 1.0e15) {
+                            const int j = (int)(((long long)D) & (long long)(J - 1));
+                            const Cand cj = load_cand(w0 + F, j);
+                            int el;
+                            const float mg = unpack_margin(cj.margin_el, el);
+                            const float cjv = hd.c0 + (float)j * us;
+                            if (shift_ok(base - (double)cjv, mg, el)) { nb = (double)cj.end + (base - (double)cjv); how = 1; }
                         }
                     }
                 }
             }
-            found = __shfl_sync(full, found, F);
-            if (found) { if (lane == F) settled = true; continue; }
-            // group F is run as the plain sequential chain from its exact start
-            const double AF = shfl_d(A, F);
-            const float aF = (float)AF;                 // exact: A of the first failing lane is built from verified groups only
-            if ((double)aF != AF) ++n_err;
-            const float a_next = seq_group(w0 + F, aF);
-            ++n_seq;
-            base = (double)a_next;
+            how = __shfl_sync(full, how, F);
+            if (how) base = shfl_d(nb, F);
+            else {
+                const float aF = (float)base;           // exact: built from verified groups only
+                if ((double)aF != base) ++n_err;
+                base = (double)seq_group(w0 + F, aF);
+                ++n_seq;
+            }
             live_from = F + 1;
-            if (w0 + live_from >= ng || live_from >= 32) break;
         }
     }
     if ((double)(float)base != base) ++n_err;

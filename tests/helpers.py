@@ -170,9 +170,7 @@ def numpy_predict(e, X, bias, lrs, n_trees, oblivious):
     for t in range(n_trees):
         l0, l1 = int(ti[t]), (int(ti[t + 1]) if t + 1 < len(ti) else nl)
         if oblivious:
-            dep = int(dp[t])
-            if dep == 0:
-                continue                                   # a depth-0 tree never matches (predictor.cpp:211-217)
+            dep = int(dp[t])                               # depth 0: leaf 0 is applied (predictor.cpp:244-258); its value is 0
             li = np.zeros(n, np.int64)
             for k in range(dep):
                 li |= (X[:, int(fi[t, k])] > fv[t, k]).astype(np.int64) << (dep - 1 - k)
