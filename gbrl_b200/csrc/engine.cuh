@@ -175,7 +175,9 @@ void raw_grad_scale(Model &m, const float *grads, int N, cudaStream_t s);       
 // tree growth
 void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, cudaStream_t s);
 // histogram.cu
-void launch_plan_level(Model &m, int level, cudaStream_t s);
+void launch_plan_level(Model &m, int level, cudaStream_t s);      // level 0; later levels: launch_decide plans level + 1
+struct PlanParams;
+PlanParams plan_params(const Model &m);
 int hist_item_rows(const Model &m);
 void launch_histogram(Model &m, int level, cudaStream_t s);
 // split.cu

@@ -171,18 +171,45 @@ __device__ __forceinline__ bool shift_ok(double delta, float margin, int el) {
 // Returns the exact final sum (same value in every lane).  Counters: groups run sequentially; internal inconsistencies
 // (a running sum that is not a float -- cannot happen while the arithmetic below is exact; tests assert it stays 0).
 //
-// Fast path: a RUN of consecutive groups whose candidates sit in the same binade as the run's first group and that are
-// served by candidates 0 / 1 is integer arithmetic in units of that binade's ulp: M <- M + I[parity(M)] (c0 has its low
-// bits cleared, so the parity of the running integer M is the parity of the group's own offset).  Two-entry tables compose
-// associatively, so one warp scan gives every group's incoming M; margins are then checked by all lanes at once.  The
-// first group that does not fit (other binade, coarser lattice, margin) is resolved on its own -- candidate records in
-// fp64, else the sequential chain -- and the scan resumes behind it.
+// A window of 32 groups is integer arithmetic in units of the finest ulp u of anything in the window (starts, ends, the
+// running sum): with M = a / u the group of lane g maps  M -> M + I0_g  (start on an even multiple of its own ulp 2^k_g u,
+// or F_PFREE)  or  M -> M + I0_g + dI_g  (odd multiple).  c0_g has its low bits cleared, so the parity is bit k_g of M.
+//   1. inclusive prefix of I0 over the lanes (int64 warp scan) = every group's incoming M if all parities were even;
+//   2. the parity-dependent groups are visited in order by the whole warp (a few integer instructions and three shuffles
+//      each): bit k of (own low bits + correction so far) picks the candidate, its dI joins the correction;
+//   3. all lanes check margin and lattice for their actual start at once.
+// The first group that does not fit (coarser lattice than 2 ulp, margin, no simulation) is resolved on its own -- candidate
+// records in fp64, else the sequential chain -- and the rest of the window is redone behind it.
+__device__ __forceinline__ long long shfl_ll(long long v, int src) {
+    int lo = (int)(v & 0xffffffffll), hi = (int)(v >> 32);
+    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+__device__ __forceinline__ long long shfl_up_ll(long long v, int d) {
+    int lo = (int)(v & 0xffffffffll), hi = (int)(v >> 32);
+    lo = __shfl_up_sync(0xffffffffu, lo, d); hi = __shfl_up_sync(0xffffffffu, hi, d);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+// exponent of the ulp of v (biased like the float exponent field; 255 for 0: "any lattice")
+__device__ __forceinline__ int ulp_exp(float v) {
+    const int e = (int)((__float_as_uint(v) >> 23) & 0xffu);
+    return (__float_as_uint(v) & 0x7fffffffu) == 0u ? 255 : e;
+}
+// v / 2^(emin-150) as an integer (v a multiple of that unit, exponent spread <= 36)
+__device__ __forceinline__ long long to_units(float v, int emin) {
+    const uint32_t b = __float_as_uint(v);
+    const int e = (int)((b >> 23) & 0xffu);
+    if ((b & 0x7fffffffu) == 0u) return 0;
+    const long long m = (long long)((b & 0x7fffffu) | 0x800000u) << (e - emin);
+    return (b >> 31) ? -m : m;
+}
+
 template <class LoadHead, class LoadCand, class SeqGroup>
 __device__ __forceinline__ float walk_chain(int ng, float a_start, LoadHead load_head, LoadCand load_cand, SeqGroup seq_group,
                                             int &n_err, int &n_seq) {
     const unsigned int full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    double base = (double)a_start;                      // exact running sum at the first live group
+    float base = a_start;                               // exact running sum at the first live group
     Head nx;
     nx.c0 = 0.0f; nx.end0 = 0.0f; nx.d1 = 0.0f; nx.mflags = 0.0f;
     if (lane < ng) nx = load_head(lane);
@@ -194,96 +221,121 @@ __device__ __forceinline__ float walk_chain(int ng, float a_start, LoadHead load
         if (w0 + 32 + lane < ng) nx = load_head(w0 + 32 + lane);          // next window's heads are in flight during this one
         int flags;
         const float margin = unpack_margin(hd.mflags, flags);
-        const uint32_t cb = __float_as_uint(hd.c0);
+        const int pe = (int)((__float_as_uint(hd.c0) >> 23) & 0xffu);
+        const bool usable = in_range && !(flags & F_NOSIM) && (flags & (F_PFREE | F_SIMPLE)) && pe >= 27;
         const int wn = min(32, ng - w0);
         int live_from = 0;
 #pragma unroll 1
         while (live_from < wn) {
-            // ---- the regular run starting at lane L = live_from
             const int L = live_from;
-            const uint32_t cbL = __shfl_sync(full, cb, L);
-            const int peL = (int)((cbL >> 23) & 0xffu);
-            const float usL = __uint_as_float((cbL & 0x80000000u) | ((uint32_t)(peL > 23 ? peL - 23 : 1) << 23));
-            const double inv_us = 1.0 / (double)usL;                       // exact: a power of two
-            bool reg = in_range && lane >= L && !(flags & F_NOSIM) && (flags & (F_PFREE | F_SIMPLE)) && ((cb ^ cbL) >> 23) == 0u && peL >= 27;
-            int i0 = 0, i1 = 0, off = 0;
-            if (reg) {
-                const double q0 = ((double)hd.end0 - (double)hd.c0) * inv_us, q1 = q0 + (double)hd.d1 * inv_us;
-                const double qo = ((double)hd.c0 - (double)__uint_as_float(cbL)) * inv_us;
-                reg = q0 == rint(q0) && q1 == rint(q1) && fabs(q0) < 5.0e8 && fabs(q1) < 5.0e8 && fabs(qo) < 5.0e8;
-                if (reg) { i0 = (int)q0; i1 = (flags & F_PFREE) ? i0 : (int)q1; off = (int)qo; }
+            // ---- the unit: finest ulp of the live lanes' starts / ends / increments and of the running sum
+            int e_lo = 255, e_hi = 0;
+            if (usable && lane >= L) {
+                e_lo = min(min(ulp_exp(hd.c0), ulp_exp(hd.end0)), ulp_exp(hd.d1));
+                e_hi = max(pe, (int)((__float_as_uint(hd.end0) >> 23) & 0xffu));
             }
-            const double mLd = (base - (double)__uint_as_float(cbL)) * inv_us;   // incoming M of the run (units of usL)
-            const bool start_ok = mLd == rint(mLd) && fabs(mLd) < 5.0e8;
-            unsigned int stop = __ballot_sync(full, !reg && lane >= L);           // first lane that does not belong to the run
-            int R = stop ? (__ffs(stop) - 1) : 32;
-            if (!start_ok) R = L;
-            int F = L;                                                            // first lane NOT applied by the scan
-            if (R > L) {
-                const bool mine = lane >= L && lane < R;
-                int t0 = mine ? i0 : 0, t1 = mine ? i1 : 0;                        // inclusive composites for an even / odd M at lane L
+            e_lo = min(e_lo, ulp_exp(base));
+            e_hi = max(e_hi, (int)((__float_as_uint(base) >> 23) & 0xffu));
+            e_lo = __reduce_min_sync(full, e_lo); e_hi = __reduce_max_sync(full, e_hi);
+            const bool span_ok = e_lo >= 24 && e_hi - e_lo <= 32;            // 24 mantissa bits + 32 + 5 (32 lanes) < 63
+            bool mine = usable && lane >= L && span_ok;
+            long long C0 = 0, I0 = 0, dI = 0;
+            int k = 0;
+            if (mine) {
+                C0 = to_units(hd.c0, e_lo);
+                I0 = to_units(hd.end0, e_lo) - C0;
+                dI = to_units(hd.d1, e_lo);
+                k = pe - e_lo;                                               // own ulp = 2^k units
+                if (dI > 0x3fffffffll || dI < -0x3fffffffll || k > 30) mine = false;
+            }
+            // the run ends at the first lane that is not usable
+            const unsigned int stop = __ballot_sync(full, !mine && lane >= L);
+            const int R = stop ? (__ffs(stop) - 1) : 32;
+            int F = L;
+            if (R > L && span_ok) {
+                const bool in_run = lane >= L && lane < R;
+                long long pre = in_run ? I0 : 0;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int g0 = __shfl_up_sync(full, t0, o), g1 = __shfl_up_sync(full, t1, o);
-                    if (lane >= o) {
-                        const int n0 = g0 + ((g0 & 1) ? t1 : t0);
-                        const int n1 = g1 + (((g1 + 1) & 1) ? t1 : t0);
-                        t0 = n0; t1 = n1;
+                    const long long v = shfl_up_ll(pre, o);
+                    if (lane >= o) pre += v;
+                }
+                const long long baseM = to_units(base, e_lo);
+                const long long Minc = baseM + pre - (in_run ? I0 : 0);      // incoming M if every parity before was even
+                // ---- parity-dependent lanes, in order
+                unsigned int todo = __ballot_sync(full, in_run && !(flags & F_PFREE));
+                const unsigned int alow = (unsigned int)(Minc & 0xffffffffll);
+                long long corr = 0, mycorr = 0;
+                int par = 0;
+                while (todo) {
+                    const int i = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const unsigned int ai = __shfl_sync(full, alow, i);
+                    const int ki = __shfl_sync(full, k, i);
+                    const int di = __shfl_sync(full, (int)dI, i);
+                    const int pi = (int)(((ai + (unsigned int)(corr & 0xffffffffll)) >> ki) & 1u);
+                    if (lane == i) { par = pi; mycorr = corr; }
+                    if (pi) corr += di;
+                    if (lane > i) mycorr = corr;
+                }
+                if (flags & F_PFREE) { par = 0; }
+                // lanes after the last parity lane took mycorr = corr above; parity-free lanes before any parity lane keep 0
+                const long long M = Minc + mycorr;
+                const long long dl = M - C0;                                 // a - c0 in units
+                const long long step1 = (__float_as_uint(hd.c0) >> 31) ? -(1ll << k) : (1ll << k);      // candidate 1 = c0 + signed ulp
+                const long long dr = dl - (par ? step1 : 0ll);               // remainder after the chosen candidate
+                bool ok = true;
+                if (in_run) {
+                    ok = (dl & ((1ll << k) - 1ll)) == 0ll;                   // the start is on the group's own lattice
+                    if (ok && dr != 0) {
+                        const long long adr = dr < 0 ? -dr : dr;
+                        ok = adr < (1ll << 40) && (float)adr * __uint_as_float((uint32_t)(e_lo - 23) << 23) < margin;      // unit = 2^(e_lo - 150)
                     }
                 }
-                const int mL = (int)mLd;
-                int e0 = __shfl_up_sync(full, t0, 1), e1 = __shfl_up_sync(full, t1, 1);
-                if (lane == 0) { e0 = 0; e1 = 0; }
-                const int M = mL + ((mL & 1) ? e1 : e0);                           // incoming running integer of this lane's group
-                const int Dg = M - off;                                            // the group's own offset: a = c0 + Dg * us
-                const int par = (flags & F_PFREE) ? 0 : (Dg & 1);
-                const bool okm = !mine || (fabsf((float)(Dg - par)) * fabsf(usL) < margin) || (Dg - par) == 0;
-                const unsigned int bad = __ballot_sync(full, !okm);
+                const unsigned int bad = __ballot_sync(full, !ok);
                 F = bad ? (__ffs(bad) - 1) : R;
                 if (F > L) {
-                    // lanes L .. F-1 are applied: the running integer behind lane F-1
-                    const int tot = __shfl_sync(full, (mL & 1) ? t1 : t0, F - 1);
-                    base = (double)__uint_as_float(cbL) + (double)(mL + tot) * (double)usL;
+                    // lanes L .. F-1 are applied: the running sum behind lane F-1
+                    const long long Mout = M + I0 + (par ? dI : 0);
+                    const long long Mo = shfl_ll(Mout, F - 1);
+                    const double v = (double)Mo * pow2d(e_lo - 150);
+                    base = (float)v;
+                    if ((double)base != v) ++n_err;
                 }
             }
             live_from = F;
             if (F >= wn) break;
             // ---- group F on its own: candidate records in fp64, else the sequential chain
-            double nb = 0.0;
+            float nb = 0.0f;
             int how = 0;                                                           // 1: resolved from a record
-            if (lane == F && !(flags & F_NOSIM) && ((double)(float)base == base)) {
+            if (lane == F && in_range && !(flags & F_NOSIM)) {
                 float c0, us;
-                int pe;
-                if (cand_base(hd.c0, c0, us, pe)) {
-                    const double delta = base - (double)hd.c0;
+                int pe2;
+                if (cand_base(hd.c0, c0, us, pe2)) {
+                    const double delta = (double)base - (double)hd.c0;
                     if (flags & F_PFREE) {
-                        if (shift_ok(delta, margin, pe)) { nb = (double)hd.end0 + delta; how = 1; }
+                        if (shift_ok(delta, margin, pe2)) { const double v = (double)hd.end0 + delta; nb = (float)v; how = ((double)nb == v); }
                     } else if (flags & F_CANDS) {
-                        const double D = delta / (double)us;
+                        const double D = delta * (1.0 / (double)us);
                         if (D == rint(D) && fabs(D) < 1.0e15) {
                             const int j = (int)(((long long)D) & (long long)(J - 1));
                             const Cand cj = load_cand(w0 + F, j);
                             int el;
                             const float mg = unpack_margin(cj.margin_el, el);
                             const float cjv = hd.c0 + (float)j * us;
-                            if (shift_ok(base - (double)cjv, mg, el)) { nb = (double)cj.end + (base - (double)cjv); how = 1; }
+                            const double dj = (double)base - (double)cjv;
+                            if (shift_ok(dj, mg, el)) { const double v = (double)cj.end + dj; nb = (float)v; how = ((double)nb == v); }
                         }
                     }
                 }
             }
             how = __shfl_sync(full, how, F);
-            if (how) base = shfl_d(nb, F);
-            else {
-                const float aF = (float)base;           // exact: built from verified groups only
-                if ((double)aF != base) ++n_err;
-                base = (double)seq_group(w0 + F, aF);
-                ++n_seq;
-            }
+            if (how) base = __shfl_sync(full, nb, F);
+            else { base = seq_group(w0 + F, base); ++n_seq; }
             live_from = F + 1;
         }
     }
-    if ((double)(float)base != base) ++n_err;
-    return (float)base;
+    return base;
 }
 
 }  // namespace spec

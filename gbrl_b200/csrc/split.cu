@@ -26,6 +26,7 @@
 #include "engine.cuh"
 #include "chain.cuh"
 #include "replay.cuh"
+#include "plan.cuh"
 #include <cfloat>
 #include <cstdlib>
 #include <climits>
@@ -1198,8 +1199,8 @@ __device__ void apply_split(NodeArrays na, const DecideParams &P, int h, int can
     // called by one warp; writes the split and initialises both children
     const int lane = threadIdx.x & 31;
     const int f = cand / P.B, j = cand % P.B;
-    __shared__ long long s_r[8][65];
-    long long *r = s_r[(threadIdx.x >> 5) & 7];
+    __shared__ long long s_r[32][65];
+    long long *r = s_r[(threadIdx.x >> 5) & 31];
     warp_right_sums(Hn, P.nT, P.D, f, j, r);
     __syncwarp();
     if (lane == 0) {
@@ -1222,8 +1223,8 @@ __device__ void apply_split(NodeArrays na, const DecideParams &P, int h, int can
 }
 
 // greedy: one warp per node of the level
-__global__ void __launch_bounds__(32) decide_greedy_kernel(DecideParams P, NodeArrays na) {
-    const int p = blockIdx.x, h = level_base(P.level) + p, lane = threadIdx.x;
+__device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) {
+    const int h = level_base(P.level) + p, lane = threadIdx.x & 31;
     if (na.state[h] != NODE_OPEN) return;
     float g = na.best_gain[h];
     int c = na.best_idx[h];
@@ -1270,8 +1271,8 @@ __global__ void __launch_bounds__(32) decide_greedy_kernel(DecideParams P, NodeA
     }
 }
 
-// oblivious: one CTA, warp w handles nodes w, w+8, ...
-__global__ void __launch_bounds__(256) decide_oblivious_kernel(DecideParams P, NodeArrays na) {
+// oblivious: one CTA, warp w handles nodes w, w + #warps, ...
+__device__ void decide_oblivious_body(const DecideParams &P, NodeArrays na) {
     __shared__ int s_cand;
     const int base = level_base(P.level);
     if (na.state[base] != NODE_OPEN) return;
@@ -1295,7 +1296,7 @@ __global__ void __launch_bounds__(256) decide_oblivious_kernel(DecideParams P, N
     __syncthreads();
     const int c = s_cand;
     const int warp = threadIdx.x >> 5;
-    for (int p = warp; p < P.nn; p += 8) {
+    for (int p = warp; p < P.nn; p += (int)(blockDim.x >> 5)) {
         const int h = base + p;
         if (c < 0) {
             if ((threadIdx.x & 31) == 0) na.state[h] = NODE_LEAF;   // fitter.cpp:458 break
@@ -1304,6 +1305,20 @@ __global__ void __launch_bounds__(256) decide_oblivious_kernel(DecideParams P, N
             apply_split(na, P, h, c, Hn);
         }
     }
+}
+
+// One CTA: the split decisions of level `level` (fitter.cpp:338-371 / 448-477), then -- the children's segments and states
+// being known -- the histogram work items of level + 1 (plan.cuh).  One launch instead of three per level.
+__global__ void __launch_bounds__(1024) decide_plan_kernel(DecideParams P, NodeArrays na, PlanParams Q, int oblivious) {
+    if (oblivious) decide_oblivious_body(P, na);
+    else {
+        for (int p = threadIdx.x >> 5; p < P.nn; p += (int)(blockDim.x >> 5)) decide_greedy_node(P, na, p);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (P.level + 1 < P.max_depth)
+        plan_level_body(na, P.ctl, Q.items, Q.items_cap, P.level + 1, Q.max_depth, Q.nT_local, Q.use_subtraction, Q.oblivious, Q.row_groups,
+                        Q.row_group, Q.item_rows_max);
 }
 
 // ---------------------------------------------------------------- launchers
@@ -1430,8 +1445,7 @@ void launch_decide(Model &m, int level, cudaStream_t s) {
     P.rev_map = m.rev_num_map.as<int>(); P.replay = ws.replay.as<ReplayItem>(); P.replay_scores = ws.replay_scores.as<float>();
     P.obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap); P.ctl = ws.ctl.as<Ctl>();
     P.scores = ws.scores.as<float>();
-    if (m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS) GB_LAUNCH(decide_oblivious_kernel, 1, 256, 0, s, P, ws.na);
-    else GB_LAUNCH(decide_greedy_kernel, P.nn, 32, 0, s, P, ws.na);
+    GB_LAUNCH(decide_plan_kernel, 1, 1024, 0, s, P, ws.na, plan_params(m), m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? 1 : 0);
 }
 
 }  // namespace gb

@@ -279,9 +279,9 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
     ensure_ensemble_capacity(m, 1, s);
     { ProfScope ps(m, P_PRE, s); raw_grad_scale(m, raw_grads, N, s); launch_init_tree(m, N, s); }
     const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + ws.D) * sizeof(long long);
+    if (md > 0) { ProfScope ps(m, P_DECIDE, s); launch_plan_level(m, 0, s); }
     for (int level = 0; level < md; ++level) {
-        { ProfScope ps(m, P_DECIDE, s); launch_plan_level(m, level, s);
-          GB_CUDA(cudaMemsetAsync(ws.hist[level & 1].p, 0, slot_bytes << level, s)); }
+        { ProfScope ps(m, P_DECIDE, s); GB_CUDA(cudaMemsetAsync(ws.hist[level & 1].p, 0, slot_bytes << level, s)); }
         { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
         if (m.world > 1) { ProfScope ps(m, P_ALLREDUCE, s);
             dist_allreduce_hist(m, ws.hist[level & 1].as<long long>(), (slot_bytes << level) / sizeof(long long), s); }
