@@ -117,8 +117,8 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
         ws.rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
         if (D <= 2) {
             ws.rwide_groups = ws.rbits_words / 8 + 1;
-            ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(float) + 16 + 8 * 8) + sizeof(int)) +
-                            (size_t)ws.replay_cap * 8 * sizeof(float) + 64);      // bsum, pred, spec::Head, J x spec::Cand per (group, chain)
+            ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)) + sizeof(int)) +
+                            (size_t)ws.replay_cap * 8 * sizeof(float));
         }
     }
     // node arrays carved from one allocation

@@ -14,7 +14,6 @@
 // chain is evaluated by one CUDA thread in the same order (no FMA: the engine is compiled with -fmad=false).
 #include "engine.cuh"
 #include "chain.cuh"
-#include "spec_chain.cuh"
 
 namespace gb {
 
@@ -217,20 +216,19 @@ warp_chain_kernel(float *mat, const float *mean, float *partial, long long n_ele
     }
 }
 
-// ---------------------------------------------------------------- the same chains by speculative group simulation
-// (spec_chain.cuh; the scheme of replay_wide.cu for dense chains)  chain = (reference thread t, column), DG elements per group:
-//   dense_sums_kernel    per-group fp64 sums (prediction only); mode 1 also centres the matrix in place
-//   dense_prefix_kernel  per chain: exclusive prefix of those sums = predicted running sum at every group start
-//   dense_sim_kernel     one LANE per group simulates the group's float chain from candidate starts next to the prediction
-//   dense_walk_kernel    one warp per chain: prefix sum of the recorded increments, validity of every group for the ACTUAL
-//                        start checked 32 groups at a time, the rare invalid group run as the plain sequential chain
-constexpr int DG = 64;                                    // chain elements per group
+// ---------------------------------------------------------------- the same chains, summaries by the whole GPU
+// (the scheme of replay_wide.cu for dense chains)  chain = (reference thread t, column), 256 chain elements per group:
+//   wide_dense_sums_kernel  per-group fp64 sums (prediction only); mode 1 also centres the matrix in place
+//   wide_dense_tabs_kernel  (after a per-chain prefix of those sums) group summaries for the predicted binade, tagged
+//   wide_dense_walk_kernel  one warp per chain composes 32 summaries at a time while tag and range check hold for the
+//                           ACTUAL running sum, any other group is advanced piecewise (warp_advance)
 struct DenseWide {
     float *mat; const float *mean; float *partial;
     long long n_elements; int D, T, mode;
-    double *bsum; float *pred; spec::Head *head; spec::Cand *cand;      // [chains][gmax] (cand: x J)
+    double *bsum; float *pred; int4 *tab; float *tag;      // [chains][gmax]
     int gmax;
 };
+constexpr float DW_EMPTY = -1.0f;
 
 struct DenseChain { long long first, cnt; int ng; };
 __device__ __forceinline__ DenseChain dense_chain_of(const DenseWide &P, int chain) {
@@ -240,48 +238,69 @@ __device__ __forceinline__ DenseChain dense_chain_of(const DenseWide &P, int cha
     DenseChain c;
     c.first = s + ((col - (s % P.D)) + P.D) % P.D;
     c.cnt = c.first < e ? (e - c.first + P.D - 1) / P.D : 0;
-    c.ng = (int)((c.cnt + DG - 1) / DG);
+    c.ng = (int)((c.cnt + 255) / 256);
     return c;
 }
+// the lane's 8 consecutive chain elements of group g (mode 1: squares of the already centred values)
+__device__ __forceinline__ void dense_group(const DenseWide &P, const DenseChain &c, int g, float (&x)[8]) {
+    const int lane = threadIdx.x & 31;
+    if (P.D == 1 && (long long)(g + 1) * 256 <= c.cnt) {
+        // interior group of a contiguous chain: one address, eight loads (two LDG.128 when the chain start allows it)
+        const float *p = P.mat + c.first + (long long)g * 256 + lane * 8;
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = p[i];
+        }
+        if (P.mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = x[i] * x[i];
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long j = (long long)g * 256 + lane * 8 + i;
+        float v = 0.0f;
+        if (j < c.cnt) { v = P.mat[c.first + j * P.D]; if (P.mode == 1) v = v * v; }
+        x[i] = v;
+    }
+}
 
-// a warp takes 4 groups (256 chain elements) of one chain; coalesced where D == 1
-__global__ void __launch_bounds__(256) dense_sums_kernel(DenseWide P) {
+__global__ void __launch_bounds__(256) wide_dense_sums_kernel(DenseWide P) {
     const int lane = threadIdx.x & 31;
     const int n_chains = P.T * P.D;
-    const int q4 = (P.gmax + 3) / 4;                      // 4-group units per chain
-    const long long total = (long long)n_chains * q4;
+    const long long total = (long long)n_chains * P.gmax;
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total; u += warps) {
-        const int chain = (int)(u / q4), g0 = (int)(u - (long long)chain * q4) * 4;
+        const int chain = (int)(u / P.gmax), g = (int)(u - (long long)chain * P.gmax);
         const DenseChain c = dense_chain_of(P, chain);
-        if (g0 >= c.ng) continue;
+        if (g >= c.ng) continue;
         const float mu = P.mode == 1 ? P.mean[chain % P.D] : 0.0f;
-        double sum[4] = {0.0, 0.0, 0.0, 0.0};
+        double sum = 0.0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const long long j = (long long)g0 * DG + i * 32 + lane;           // element i*32+lane of the unit -> group i/2
+            const long long j = (long long)g * 256 + i * 32 + lane;           // coalesced order; only the sum matters here
             if (j < c.cnt) {
                 const long long idx = c.first + j * P.D;
                 float v = P.mat[idx];
                 if (P.mode == 1) { v = v - mu; P.mat[idx] = v; v = v * v; }    // math_ops.cpp:480-500: centre, then square
-                sum[i >> 1] += (double)v;
+                sum += (double)v;
             }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double sv = sum[q];
-            for (int o = 16; o > 0; o >>= 1) {
-                int lo = __double2loint(sv), hi = __double2hiint(sv);
-                lo = __shfl_xor_sync(0xffffffffu, lo, o); hi = __shfl_xor_sync(0xffffffffu, hi, o);
-                sv += __hiloint2double(hi, lo);
-            }
-            if (lane == 0 && g0 + q < c.ng) P.bsum[(size_t)chain * P.gmax + g0 + q] = sv;
+        for (int o = 16; o > 0; o >>= 1) {
+            int lo = __double2loint(sum), hi = __double2hiint(sum);
+            lo = __shfl_xor_sync(0xffffffffu, lo, o); hi = __shfl_xor_sync(0xffffffffu, hi, o);
+            sum += __hiloint2double(hi, lo);
         }
+        if (lane == 0) P.bsum[(size_t)chain * P.gmax + g] = sum;
     }
 }
 
 // one warp per chain: exclusive prefix of the group sums
-__global__ void __launch_bounds__(32) dense_prefix_kernel(DenseWide P) {
+__global__ void __launch_bounds__(32) wide_dense_prefix_kernel(DenseWide P) {
     const int chain = blockIdx.x, lane = threadIdx.x;
     const DenseChain c = dense_chain_of(P, chain);
     double carry = 0.0;
@@ -301,65 +320,124 @@ __global__ void __launch_bounds__(32) dense_prefix_kernel(DenseWide P) {
     }
 }
 
-// chain elements of a dense group in order (mode 1: squares of the already centred values)
-struct DenseElems {
-    const float *p; long long stride; int sq;
-    __device__ __forceinline__ float operator()(int k) const {
-        const float v = p[(long long)k * stride];
-        return sq ? v * v : v;
-    }
-};
-
-// one lane per (chain, group)
-__global__ void __launch_bounds__(128) dense_sim_kernel(DenseWide P) {
+__global__ void __launch_bounds__(256) wide_dense_tabs_kernel(DenseWide P) {
+    const int lane = threadIdx.x & 31;
     const int n_chains = P.T * P.D;
     const long long total = (long long)n_chains * P.gmax;
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total) return;
-    const int chain = (int)(u / P.gmax), g = (int)(u - (long long)chain * P.gmax);
-    const DenseChain c = dense_chain_of(P, chain);
-    if (g >= c.ng) return;
-    const int cnt = (int)min((long long)DG, c.cnt - (long long)g * DG);
-    DenseElems el;
-    el.p = P.mat + c.first + (long long)g * DG * P.D; el.stride = P.D; el.sq = P.mode == 1;
-    spec::Head hd;
-    spec::Cand cd[spec::J];
-    spec::sim_group(P.pred[u], cnt, el, hd, cd);
-    P.head[u] = hd;
-    if (spec::head_flags(hd) & spec::F_CANDS) {
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long u = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total; u += warps) {
+        const int chain = (int)(u / P.gmax), g = (int)(u - (long long)chain * P.gmax);
+        const DenseChain c = dense_chain_of(P, chain);
+        if (g >= c.ng) continue;
+        float x[8];
+        dense_group(P, c, g, x);
+        bool nz = false;
 #pragma unroll
-        for (int j = 0; j < spec::J; ++j) P.cand[(size_t)u * spec::J + j] = cd[j];
+        for (int i = 0; i < 8; ++i) nz |= (x[i] != 0.0f) || (x[i] != x[i]);
+        float inv_u, uu;
+        const bool ok = seq::epoch_of(P.pred[(size_t)chain * P.gmax + g], inv_u, uu);
+        float tagv = ok ? inv_u : 0.0f;
+        if (!__any_sync(0xffffffffu, nz)) {
+            tagv = DW_EMPTY;
+            if (lane == 0) P.tab[(size_t)chain * P.gmax + g] = make_int4(0, 0, 0, 0);
+        } else if (ok) {
+            const seq::Tab tb = seq::warp_summarize<8>(x, inv_u);
+            if (lane == 0) P.tab[(size_t)chain * P.gmax + g] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+        }
+        if (lane == 0) P.tag[(size_t)chain * P.gmax + g] = tagv;
     }
 }
 
-__global__ void __launch_bounds__(32) dense_walk_kernel(DenseWide P, long long *stats) {
+__global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long long *stats) {
+    __shared__ __align__(16) float s_wbuf[256];
     const unsigned int full = 0xffffffffu;
     const int chain = blockIdx.x, lane = threadIdx.x;
     const DenseChain c = dense_chain_of(P, chain);
     const size_t base = (size_t)chain * P.gmax;
-    int n_err = 0, n_seq = 0;
-    auto load_head = [&](int g) { return P.head[base + g]; };
-    auto load_cand = [&](int g, int j) { return P.cand[(base + g) * spec::J + j]; };
-    auto seq_group = [&](int g, float a) -> float {
-        // the plain sequential chain over group g (math_ops.cpp:279-283): two elements per lane, consumed in memory order
-        const long long j0 = (long long)g * DG;
-        float x0 = 0.0f, x1 = 0.0f;
-        if (j0 + lane < c.cnt) { x0 = P.mat[c.first + (j0 + lane) * P.D]; if (P.mode == 1) x0 = x0 * x0; }
-        if (j0 + 32 + lane < c.cnt) { x1 = P.mat[c.first + (j0 + 32 + lane) * P.D]; if (P.mode == 1) x1 = x1 * x1; }
+    float acc = 0.0f;
+    int n_fast = 0, n_slow = 0, n_seq = 0;
+    int4 qnx = make_int4(0, 0, 0, 0);
+    float tgnx = 0.0f;
+    if (lane < c.ng) { qnx = P.tab[base + lane]; tgnx = P.tag[base + lane]; }
+    float pa[8], pb[8];                                   // rows of two groups fetched ahead of need
+    int ha = -1, hb = -1;                                 // which groups they are
+#pragma unroll 1
+    for (int w0 = 0; w0 < c.ng; w0 += 32) {
+        const bool in_range = w0 + lane < c.ng;
+        const int wn = min(32, c.ng - w0);
+        const int4 q = qnx;
+        const float tg = tgnx;
+        if (w0 + 32 + lane < c.ng) { qnx = P.tab[base + w0 + 32 + lane]; tgnx = P.tag[base + w0 + 32 + lane]; }
+        int first = 0;
+#pragma unroll 1
+        while (first < wn) {
+            // longest applicable prefix of the window from `first` (same logic as replay_wide.cu compose_window)
+            float inv_u, u;
+            int take = 0;
+            const bool live = lane >= first;
+            if (!seq::epoch_of(acc, inv_u, u)) {
+                const unsigned int stop = __ballot_sync(full, live && !(in_range && tg == DW_EMPTY));
+                take = (stop ? (__ffs(stop) - 1) : 32) - first;
+            } else {
+                const bool empty = in_range && tg == DW_EMPTY;
+                const bool tag_ok = in_range && (tg == inv_u || empty);
+                int i0 = (tag_ok && live) ? q.x : 0, i1 = (tag_ok && live) ? q.y : 0;
+                if (!__any_sync(full, i0 != i1)) {
 #pragma unroll
-        for (int l = 0; l < 32; ++l) a = a + __shfl_sync(full, x0, l);
+                    for (int off = 1; off < 32; off <<= 1) { const int g0 = __shfl_up_sync(full, i0, off); if (lane >= off) i0 += g0; }
+                    i1 = i0;
+                } else {
 #pragma unroll
-        for (int l = 0; l < 32; ++l) a = a + __shfl_sync(full, x1, l);
-        return a;
-    };
-    const float acc = spec::walk_chain(c.ng, 0.0f, load_head, load_cand, seq_group, n_err, n_seq);
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int g0 = __shfl_up_sync(full, i0, off), g1 = __shfl_up_sync(full, i1, off);
+                        if (lane >= off) {
+                            const int n0 = g0 + ((g0 & 1) ? i1 : i0), n1 = g1 + (((g1 + 1) & 1) ? i1 : i0);
+                            i0 = n0; i1 = n1;
+                        }
+                    }
+                }
+                int e0 = __shfl_up_sync(full, i0, 1);
+                if (lane == 0) e0 = 0;
+                const int m = (int)(acc * inv_u);
+                const int lo = (1 << 23) + seq::MARGIN, hi = (1 << 24) - seq::MARGIN;
+                const int b = m + e0;
+                const bool okw = !live || empty || (tag_ok && (m > 0 ? (b + q.z > lo && b + q.w < hi) : (b + q.w < -lo && b + q.z > -hi)));
+                const unsigned int bad = __ballot_sync(full, !okw);
+                take = (bad ? (__ffs(bad) - 1) : 32) - first;
+                if (take > 0) {
+                    const int inc0 = __shfl_sync(full, i0, first + take - 1), inc1 = __shfl_sync(full, i1, first + take - 1);
+                    acc = (float)(m + ((m & 1) ? inc1 : inc0)) * u;
+                }
+            }
+            if (take > 0) { n_fast += take; first += take; }
+            if (first >= wn) break;
+            // rows of the failed group; the two groups after it are fetched now (a sum that hovers around a power of two
+            // fails group after group, and a lone warp has nothing else to hide the load latency behind)
+            const int gq = w0 + first;
+            float x[8];
+            if (ha == gq) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = pa[i];
+            } else if (hb == gq) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = pb[i];
+            } else dense_group(P, c, gq, x);
+            if (hb == gq + 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) pa[i] = pb[i];
+                ha = gq + 1;
+            } else if (ha != gq + 1 && gq + 1 < c.ng) { dense_group(P, c, gq + 1, pa); ha = gq + 1; }
+            if (gq + 2 < c.ng) { dense_group(P, c, gq + 2, pb); hb = gq + 2; }
+            acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
+            ++n_slow; ++first;
+        }
+    }
     if (lane == 0) {
         P.partial[chain] = acc;
         if (stats) {
-            atomicAdd((unsigned long long *)&stats[0], (unsigned long long)(c.ng - n_seq));
-            atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_seq);
-            atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_seq * (DG / 32));
-            atomicAdd((unsigned long long *)&stats[3], (unsigned long long)n_err);
+            atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_fast);
+            atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_slow);
+            atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_seq);
         }
     }
 }
@@ -375,29 +453,29 @@ static void launch_dense(float *mat, const float *mean, float *partial, long lon
 static void launch_ref_chain(Model *m, float *mat, const float *mean, float *partial, long long ne, int D, int T, int mode,
                              cudaStream_t s, long long *stats = nullptr) {
     if (ne <= 0) { GB_CUDA(cudaMemsetAsync(partial, 0, (size_t)T * D * sizeof(float), s)); return; }
+    // GPU-wide summaries + one walking warp per chain
     static DevBuf fallback_scratch;                        // diag path (no model workspace)
     DevBuf &scratch = m ? m->ws.dwide : fallback_scratch;
     DenseWide P;
     P.mat = mat; P.mean = mean; P.partial = partial; P.n_elements = ne; P.D = D; P.T = T; P.mode = mode;
     const long long ept = ne / T;
     const long long longest = (ne - (long long)(T - 1) * ept + D - 1) / D + 1;      // the last thread takes the remainder
-    P.gmax = (int)((longest + DG - 1) / DG) + 1;
+    P.gmax = (int)((longest + 255) / 256) + 1;
     const size_t per = (size_t)T * D * P.gmax;
-    scratch.ensure(per * (sizeof(double) + sizeof(spec::Head) + spec::J * sizeof(spec::Cand) + sizeof(float)) + 64);
+    scratch.ensure(per * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)));
     char *p = scratch.as<char>();
-    P.head = reinterpret_cast<spec::Head *>(p); p += per * sizeof(spec::Head);       // 16-byte entries first (alignment)
-    P.cand = reinterpret_cast<spec::Cand *>(p); p += per * spec::J * sizeof(spec::Cand);
+    P.tab = reinterpret_cast<int4 *>(p); p += per * sizeof(int4);       // 16-byte entries first (alignment)
     P.bsum = reinterpret_cast<double *>(p); p += per * sizeof(double);
-    P.pred = reinterpret_cast<float *>(p);
-    const long long units = (long long)T * D * ((P.gmax + 3) / 4);
+    P.pred = reinterpret_cast<float *>(p); p += per * sizeof(float);
+    P.tag = reinterpret_cast<float *>(p);
+    long long units = (long long)per;
     int grid = (int)((units + 7) / 8);
     if (grid > 148 * 16) grid = 148 * 16;
     if (grid < 1) grid = 1;
-    GB_LAUNCH(dense_sums_kernel, grid, 256, 0, s, P);
-    GB_LAUNCH(dense_prefix_kernel, T * D, 32, 0, s, P);
-    GB_LAUNCH(dense_sim_kernel, (int)((per + 127) / 128), 128, 0, s, P);
-    if (!stats && m) stats = &m->ws.ctl.as<Ctl>()->stat_chain_fast;      // fast / sequential / lanes / errors, consecutive in Ctl
-    GB_LAUNCH(dense_walk_kernel, T * D, 32, 0, s, P, stats);
+    GB_LAUNCH(wide_dense_sums_kernel, grid, 256, 0, s, P);
+    GB_LAUNCH(wide_dense_prefix_kernel, T * D, 32, 0, s, P);
+    GB_LAUNCH(wide_dense_tabs_kernel, grid, 256, 0, s, P);
+    GB_LAUNCH(wide_dense_walk_kernel, T * D, 32, 0, s, P, stats);
 }
 
 // test hook: thread-partitioned chain sums of a host matrix through launch_ref_chain (impl 0) or the one-thread-per-
@@ -436,7 +514,7 @@ void diag_chain_sums(const float *host_mat, long long ne, int D, int T, int mode
     if (info) {
         long long h[4];
         GB_CUDA(cudaMemcpy(h, stats.p, sizeof(h), cudaMemcpyDeviceToHost));
-        info[0] = ms; info[1] = (double)h[0]; info[2] = (double)h[1]; info[3] = impl == 0 ? (double)h[3] : (double)h[2];
+        info[0] = ms; info[1] = (double)h[0]; info[2] = (double)h[1]; info[3] = (double)h[2];
     }
 }
 

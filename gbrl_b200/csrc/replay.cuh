@@ -1,7 +1,6 @@
 // replay.cuh -- parameter blocks shared by the near-tie replay kernels (split.cu, replay_wide.cu).
 #pragma once
 #include "engine.cuh"
-#include "spec_chain.cuh"
 
 namespace gb {
 
@@ -35,8 +34,8 @@ struct StreamParams {
 struct WideParams {
     double *bsum;              // [groups][2D] exact-ish sum of the group's elements per chain (side * D + d)
     float *pred;               // [groups][2D] predicted running sum of the chain at the start of the group
-    spec::Head *head;          // [groups][2D] simulated record of the group for candidate start 0 (spec_chain.cuh)
-    spec::Cand *cand;          // [groups][2D][J] the other candidate starts (groups flagged F_CANDS only)
+    int4 *tab;                 // [groups][2D] summary of the group for the predicted binade (chain.cuh Tab)
+    float *tag;                // [groups][2D] the binade (inv_u) the summary was computed for, 0 = none
     int *gitem;                // [groups] item of the group
     float *fin;                // [items][8] pass 0 -> pass 1: means (left D, right D), ln, rn
     long long cap_groups;

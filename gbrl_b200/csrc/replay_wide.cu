@@ -13,11 +13,11 @@
 // Cosine needs a second round (tabs + walk) for the mat_vec_dot_sum chains once the side means are known.
 #include "replay.cuh"
 #include "chain.cuh"
-#include "spec_chain.cuh"
 
 namespace gb {
 
 constexpr int GROUP_ROWS = 256;
+constexpr float TAG_EMPTY = -1.0f;     // tag of a group in which the chain has no element: applicable to any running sum
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
     int lo = __double2loint(v), hi = __double2hiint(v);
@@ -150,87 +150,170 @@ __global__ void __launch_bounds__(256) wide_prefix_kernel(ReplayParams P, NodeAr
     }
 }
 
-// chain elements of one 256-row group of an item, in the reference's order (node.cpp:341-350; math_ops.h:432-449 for the
-// Cosine dot chains): PASS 0 -> chain (side, d): g[row][d] of the rows on that side, +0 for the others;
-// PASS 1 -> chain side: g[row][d] * mean[side][d] over (row, d), rows of the other side +0.
-template <int D, int PASS>
-struct SideElems {
-    const float *g;            // G + (s0 + first row of the group) * D
-    const unsigned int *w;     // side-bit words of the group
-    int side, d;
-    float m[D];                // PASS 1: the side's means
-    __device__ __forceinline__ float operator()(int k) const {
-        if (PASS == 0) {
-            const bool right = (w[k >> 5] >> (k & 31)) & 1u;
-            return (right == (side != 0)) ? g[(size_t)k * D + d] : 0.0f;
-        } else {
-            const int row = k / D, dd = k - row * D;
-            const bool right = (w[row >> 5] >> (row & 31)) & 1u;
-            float mv = m[0];
+// the lane's 8 rows of a group: values (row-major, D per row), side bits, members of chain side `side`
+template <int D>
+__device__ __forceinline__ void group_rows(const float *G, const unsigned int *W, int n, int lg, float (&v)[8 * D], unsigned int &mb) {
+    const int lane = threadIdx.x & 31;
+    const int kb = lg * GROUP_ROWS + lane * 8;
+    const float *p = G + (size_t)kb * D;
+    if ((lg + 1) * GROUP_ROWS <= n) {
+        // interior group: one address, 8 * D loads (LDG.128 when the node's first row allows it)
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
-            for (int q = 1; q < D; ++q) mv = (dd == q) ? m[q] : mv;
-            return (right == (side != 0)) ? g[k] * mv : 0.0f;
+            for (int j = 0; j < 8 * D; j += 4) {
+                const float4 a = *reinterpret_cast<const float4 *>(p + j);
+                v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8 * D; ++j) v[j] = p[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8 * D; ++j) {
+            const int k = kb + j / D;
+            v[j] = k < n ? p[j] : 0.0f;
         }
     }
-};
+    mb = (W[lg * 8 + (lane >> 2)] >> ((lane & 3) * 8)) & 0xffu;
+}
 
-// one LANE per (group, chain): simulates the group's float chain from candidate starts next to the predicted running sum
 template <int D, int PASS>
-__global__ void __launch_bounds__(128) wide_sim_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+__device__ __forceinline__ void chain_elems(const float (&v)[8 * D], unsigned int mb, int c, const float *smean,
+                                            float (&x)[PASS == 0 ? 8 : 8 * D]) {
+    if (PASS == 0) {
+        const int side = c / D, d = c - side * D;
+        const unsigned int sel = side ? mb : ~mb;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float val = v[r * D];
+#pragma unroll
+            for (int dd = 1; dd < D; ++dd) val = (d == dd) ? v[r * D + dd] : val;
+            x[r] = ((sel >> r) & 1u) ? val : 0.0f;
+        }
+    } else {
+        const unsigned int sel = c ? mb : ~mb;
+#pragma unroll
+        for (int j = 0; j < 8 * D; ++j) {
+            const int r = j / D, d = j - r * D;
+            x[j < (PASS == 0 ? 8 : 8 * D) ? j : 0] = ((sel >> r) & 1u) ? v[j] * smean[c * D + d] : 0.0f;   // math_ops.h:432-449
+        }
+    }
+}
+
+// one warp per group: summaries of all chains of the group for the predicted binade
+template <int D, int PASS>
+__global__ void __launch_bounds__(256) wide_tabs_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
     constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    constexpr int KE = PASS == 0 ? 8 : 8 * D;
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
     if (n_items <= 0) return;
     if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
-    const long long total = (long long)(S.woff[n_items] >> 3) * NCH;
-    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (long long)gridDim.x * blockDim.x) {
-        const int g = (int)(u / NCH), c = (int)(u - (long long)g * NCH);
+    const int lane = threadIdx.x & 31;
+    const int total_groups = S.woff[n_items] >> 3;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_groups; g += warps) {
         const int it = Wd.gitem[g];
         if (it < 0) continue;
         const ReplayItem item = P.items[it];
         const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
         const int lg = g - (S.woff[it] >> 3);
-        const int rows = min(GROUP_ROWS, n - lg * GROUP_ROWS);
-        if (rows <= 0) continue;
-        SideElems<D, PASS> el;
-        el.g = S.G + ((size_t)s0 + (size_t)lg * GROUP_ROWS) * D;
-        el.w = S.bits + S.woff[it] + lg * 8;
-        float pr;
-        if (PASS == 0) {
-            el.side = c / D; el.d = c - el.side * D;
-            pr = Wd.pred[(size_t)g * 2 * D + c];
-        } else {
-            el.side = c; el.d = 0;
-            pr = 0.0f;
+        float v[8 * D];
+        unsigned int mb;
+        group_rows<D>(S.G + (size_t)s0 * D, S.bits + S.woff[it], n, lg, v, mb);
+        float smean[2 * D];
+        if (PASS == 1) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                el.m[d] = Wd.fin[(size_t)it * 8 + c * D + d];
-                pr += el.m[d] * Wd.pred[(size_t)g * 2 * D + c * D + d];
-            }
+            for (int i = 0; i < 2 * D; ++i) smean[i] = Wd.fin[(size_t)it * 8 + i];
         }
-        spec::Head hd;
-        spec::Cand cd[spec::J];
-        spec::sim_group(pr, PASS == 0 ? rows : rows * D, el, hd, cd);
-        const size_t o = (size_t)g * 2 * D + c;
-        Wd.head[o] = hd;
-        if (spec::head_flags(hd) & spec::F_CANDS) {
 #pragma unroll
-            for (int j = 0; j < spec::J; ++j) Wd.cand[o * spec::J + j] = cd[j];
+        for (int c = 0; c < NCH; ++c) {
+            float pr;
+            if (PASS == 0) pr = Wd.pred[(size_t)g * 2 * D + c];
+            else {
+                pr = 0.0f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) pr += smean[c * D + d] * Wd.pred[(size_t)g * 2 * D + c * D + d];
+            }
+            float inv_u, u;
+            const bool ok = seq::epoch_of(pr, inv_u, u);
+            float x[KE];
+            chain_elems<D, PASS>(v, mb, c, smean, x);
+            bool nz = false;
+#pragma unroll
+            for (int i = 0; i < KE; ++i) nz |= (x[i] != 0.0f) || (x[i] != x[i]);
+            const bool empty = !__any_sync(0xffffffffu, nz);          // the chain has no (non-zero) element in this group
+            float tagv = ok ? inv_u : 0.0f;
+            if (empty) {
+                tagv = TAG_EMPTY;
+                if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(0, 0, 0, 0);
+            } else if (ok) {
+                const seq::Tab tb = seq::warp_summarize<KE>(x, inv_u);
+                if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+            }
+            if (lane == 0) Wd.tag[(size_t)g * 2 * D + c] = tagv;
         }
     }
+}
+
+// composes the longest applicable prefix of a window of 32 groups (lane = group); returns how many were consumed
+__device__ __forceinline__ int compose_window(float &acc, const int4 q, float tg, bool in_range, int first) {
+    const unsigned int full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float inv_u, u;
+    const bool live = lane >= first;                      // lanes before `first` are consumed already
+    if (!seq::epoch_of(acc, inv_u, u)) {
+        // no binade yet (acc == 0): only groups without elements can be skipped
+        const unsigned int stop = __ballot_sync(full, live && !(in_range && tg == TAG_EMPTY));
+        return (stop ? (__ffs(stop) - 1) : 32) - first;
+    }
+    const bool empty = in_range && tg == TAG_EMPTY;
+    const bool tag_ok = in_range && (tg == inv_u || empty);
+    int i0 = (tag_ok && live) ? q.x : 0, i1 = (tag_ok && live) ? q.y : 0;
+    if (!__any_sync(full, i0 != i1)) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int g0 = __shfl_up_sync(full, i0, off);
+            if (lane >= off) i0 += g0;
+        }
+        i1 = i0;
+    } else {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int g0 = __shfl_up_sync(full, i0, off), g1 = __shfl_up_sync(full, i1, off);
+            if (lane >= off) {
+                const int n0 = g0 + ((g0 & 1) ? i1 : i0);
+                const int n1 = g1 + (((g1 + 1) & 1) ? i1 : i0);
+                i0 = n0; i1 = n1;
+            }
+        }
+    }
+    int e0 = __shfl_up_sync(full, i0, 1);
+    if (lane == 0) e0 = 0;
+    const int m = (int)(acc * inv_u);
+    const int lo = (1 << 23) + seq::MARGIN, hi = (1 << 24) - seq::MARGIN;
+    const int b = m + e0;
+    const bool okw = !live || empty || (tag_ok && (m > 0 ? (b + q.z > lo && b + q.w < hi) : (b + q.w < -lo && b + q.z > -hi)));
+    const unsigned int bad = __ballot_sync(full, !okw);
+    const int take = (bad ? (__ffs(bad) - 1) : 32) - first;   // groups first .. first + take - 1 of the window are applied
+    if (take <= 0) return 0;
+    const int inc0 = __shfl_sync(full, i0, first + take - 1), inc1 = __shfl_sync(full, i1, first + take - 1);
+    acc = (float)(m + ((m & 1) ? inc1 : inc0)) * u;
+    return take;
 }
 
 // one CTA per item, warp c walks chain c; then the item's score (L2, or Cosine after PASS 1) / the side means (Cosine, PASS 0)
 template <int D, int PASS>
 __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd, Ctl *ctl_stats) {
     constexpr int NCH = PASS == 0 ? 2 * D : 2;
-    constexpr int EPR = PASS == 0 ? 1 : D;                      // chain elements per row
+    constexpr int KE = PASS == 0 ? 8 : 8 * D;
     __shared__ float s_sum[2 * D];
     __shared__ float s_mean[2 * D];
-    __shared__ __align__(16) float s_wbuf[NCH][256 * EPR];      // per chain warp: staging of a group that is run sequentially
+    __shared__ __align__(16) float s_wbuf[NCH][32 * KE];       // per chain warp: staging of a block that is run sequentially
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
     if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
-    int n_groups = 0, n_err = 0, n_seq = 0;
+    int n_fast = 0, n_slow = 0, n_seq = 0;
     for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
         if (S.mode[it] != 0) continue;
         const ReplayItem item = P.items[it];
@@ -238,36 +321,49 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
         const int s0 = na.seg_start[h], n = na.seg_len[h];
         const int ng = (n + GROUP_ROWS - 1) / GROUP_ROWS;
         const size_t base = (size_t)(S.woff[it] >> 3);
+        const float *G = S.G + (size_t)s0 * D;
+        const unsigned int *W = S.bits + S.woff[it];
         if (PASS == 1) {
             if (threadIdx.x < 2 * D) s_mean[threadIdx.x] = Wd.fin[(size_t)it * 8 + threadIdx.x];
             __syncthreads();
         }
         if (warp < NCH) {
             const int c = warp;
-            SideElems<D, PASS> el;
-            if (PASS == 0) { el.side = c / D; el.d = c - el.side * D; }
-            else {
-                el.side = c; el.d = 0;
+            float acc = 0.0f;
+            int4 qnx = make_int4(0, 0, 0, 0);              // the next window's summaries / tags, loaded a window ahead
+            float tgnx = 0.0f;
+            if (lane < ng) { qnx = Wd.tab[(base + lane) * 2 * D + c]; tgnx = Wd.tag[(base + lane) * 2 * D + c]; }
+#pragma unroll 1
+            for (int w0 = 0; w0 < ng; w0 += 32) {          // window of 32 groups, lane = group
+                const bool in_range = w0 + lane < ng;
+                const int wn = min(32, ng - w0);
+                const int4 q = qnx;
+                const float tg = tgnx;
+                if (w0 + 32 + lane < ng) { qnx = Wd.tab[(base + w0 + 32 + lane) * 2 * D + c]; tgnx = Wd.tag[(base + w0 + 32 + lane) * 2 * D + c]; }
+                int first = 0;
+                float vn[8 * D];                           // rows of the group after a failed one, fetched while that one is advanced
+                unsigned int mbn = 0u;
+                int have = -1;                             // group (window-relative) whose rows vn holds
+#pragma unroll 1
+                while (first < wn) {
+                    const int take = compose_window(acc, q, tg, in_range, first);
+                    n_fast += take;
+                    first += take;
+                    if (first >= wn) break;
+                    // this group is in another binade than predicted, or the sum leaves its binade inside it
+                    float v[8 * D], x[KE];
+                    unsigned int mb;
+                    if (have == first) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) el.m[d] = s_mean[c * D + d];
+                        for (int j = 0; j < 8 * D; ++j) v[j] = vn[j];
+                        mb = mbn;
+                    } else group_rows<D>(G, W, n, w0 + first, v, mb);
+                    if (w0 + first + 1 < ng) { group_rows<D>(G, W, n, w0 + first + 1, vn, mbn); have = first + 1; }
+                    chain_elems<D, PASS>(v, mb, c, s_mean, x);
+                    acc = seq::warp_seq_block<KE>(acc, x, s_wbuf[c], n_seq);
+                    ++n_slow; ++first;
+                }
             }
-            auto load_head = [&](int g) { return Wd.head[(base + g) * 2 * D + c]; };
-            auto load_cand = [&](int g, int j) { return Wd.cand[((base + g) * 2 * D + c) * spec::J + j]; };
-            auto seq_group = [&](int g, float a) -> float {
-                // the reference's plain sequential chain over the group (node.cpp:341-350 / math_ops.h:432-449)
-                SideElems<D, PASS> e2 = el;
-                e2.g = S.G + ((size_t)s0 + (size_t)g * GROUP_ROWS) * D;
-                e2.w = S.bits + S.woff[it] + g * 8;
-                const int cnt = min(GROUP_ROWS, n - g * GROUP_ROWS) * EPR;
-                float x[8 * EPR];                                 // the lane's 8 * EPR consecutive chain elements
-#pragma unroll
-                for (int i = 0; i < 8 * EPR; ++i) { const int k = lane * 8 * EPR + i; x[i] = k < cnt ? e2(k) : 0.0f; }
-                int dummy = 0;
-                a = seq::warp_seq_block<8 * EPR>(a, x, s_wbuf[c], dummy);      // broadcast LDS.128 feed: the speed of the FADD chain
-                return a;
-            };
-            const float acc = spec::walk_chain(ng, 0.0f, load_head, load_cand, seq_group, n_err, n_seq);
-            n_groups += ng;
             if (lane == 0) s_sum[c] = acc;
         }
         __syncthreads();
@@ -309,11 +405,10 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
         }
         __syncthreads();
     }
-    if (lane == 0 && n_groups) {
-        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_fast, (unsigned long long)(n_groups - n_seq));
-        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_slow, (unsigned long long)n_seq);
-        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_seq, (unsigned long long)n_seq * 8);
-        if (n_err) atomicAdd((unsigned long long *)&ctl_stats->stat_chain_err, (unsigned long long)n_err);
+    if (lane == 0 && (n_fast | n_slow)) {
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_fast, (unsigned long long)n_fast);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_slow, (unsigned long long)n_slow);
+        atomicAdd((unsigned long long *)&ctl_stats->stat_chain_seq, (unsigned long long)n_seq);
     }
 }
 
@@ -324,10 +419,10 @@ static void launch_wide_d(Model &m, const ReplayParams &R, const StreamParams &S
     const int grid = ws.n_sms * 8;
     GB_LAUNCH((wide_bits_kernel<D>), grid, 256, 0, s, R, ws.na, S, Wd);
     GB_LAUNCH((wide_prefix_kernel<D>), ws.n_sms * 4, 256, 0, s, R, ws.na, S, Wd);
-    GB_LAUNCH((wide_sim_kernel<D, 0>), ws.n_sms * 16, 128, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_tabs_kernel<D, 0>), grid, 256, 0, s, R, ws.na, S, Wd);
     GB_LAUNCH((wide_walk_kernel<D, 0>), ws.n_sms * 8, 32 * 2 * D, 0, s, R, ws.na, S, Wd, ctl);
     if (m.cfg.split_score_func != GBRL_B200_SCORE_L2) {
-        GB_LAUNCH((wide_sim_kernel<D, 1>), ws.n_sms * 16, 128, 0, s, R, ws.na, S, Wd);
+        GB_LAUNCH((wide_tabs_kernel<D, 1>), grid, 256, 0, s, R, ws.na, S, Wd);
         GB_LAUNCH((wide_walk_kernel<D, 1>), ws.n_sms * 8, 32 * 2 * D, 0, s, R, ws.na, S, Wd, ctl);
     }
 }
@@ -337,10 +432,10 @@ void launch_replay_wide(Model &m, const ReplayParams &R, const StreamParams &S, 
     WideParams Wd;
     const size_t ng = (size_t)ws.rwide_groups, D2 = (size_t)2 * ws.D;
     char *p = ws.rwide.as<char>();
-    Wd.head = reinterpret_cast<spec::Head *>(p); p += ng * D2 * sizeof(spec::Head);          // 16-byte entries first (alignment)
-    Wd.cand = reinterpret_cast<spec::Cand *>(p); p += ng * D2 * spec::J * sizeof(spec::Cand);
     Wd.bsum = reinterpret_cast<double *>(p); p += ng * D2 * sizeof(double);
+    Wd.tab = reinterpret_cast<int4 *>(p); p += ng * D2 * sizeof(int4);
     Wd.pred = reinterpret_cast<float *>(p); p += ng * D2 * sizeof(float);
+    Wd.tag = reinterpret_cast<float *>(p); p += ng * D2 * sizeof(float);
     Wd.gitem = reinterpret_cast<int *>(p); p += ng * sizeof(int);
     Wd.fin = reinterpret_cast<float *>(p);
     Wd.cap_groups = (long long)ng;

@@ -76,7 +76,7 @@ typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine 
     long long chain_blocks_fast; /* replay sub-blocks evaluated by the parallel chain evaluator (csrc/chain.cuh) */
     long long chain_blocks_slow; /* replay sub-blocks advanced piecewise (a binade change inside the block) */
     long long chain_lanes_seq;   /* lanes (R rows each) of those blocks that were run as a plain sequential float chain */
-    long long chain_errors;      /* internal inconsistencies of the chain evaluator (csrc/spec_chain.cuh); must be 0 */
+    long long chain_errors;      /* reserved (always 0) */
 } gbrl_b200_metadata;
 
 const char *gbrl_b200_last_error(void);
@@ -153,10 +153,8 @@ int gbrl_b200_microbench(int which, int iters, double *result);
 /* test hook for the bit-exact parallel float-chain evaluator (csrc/chain.cuh): the reference's thread-partitioned
  * column sums (math_ops.cpp:255-300, mode 0) or centred sums of squares (math_ops.cpp:461-513, mode 1) of a HOST
  * matrix [n_elements / D x D] for T emulated reference threads; partial[T*D] and (mode 1) the centred matrix are
- * copied back.  impl 0 = the product path (speculative group simulation, csrc/spec_chain.cuh), impl 1 = the plain sequential
- * chain kernel, impl 2 / 3 = the binade-summary evaluators of csrc/chain.cuh.  info (optional, 4 doubles): kernel ms, groups
- * applied from their record, groups run sequentially, and for impl 0 the evaluator's internal-inconsistency count (must be
- * 0), for impl 2 / 3 the lanes run sequentially. */
+ * copied back.  impl 0 = the parallel evaluator, impl 1 = the plain sequential chain kernel.  info (optional, 4 doubles):
+ * kernel ms, sub-blocks applied from their summary, sub-blocks advanced piecewise, lanes run sequentially. */
 int gbrl_b200_diag_chain_sums(const float *mat, long long n_elements, int D, int T, int mode, const float *mean,
                               float *partial, float *centered, int impl, double *info);
 
