@@ -10,44 +10,217 @@
 //     code(x) = #{j : thr_j < x} satisfies  x > thr_j  <=>  code(x) > j, so one u16 code per
 //     (sample, feature) replaces every later float comparison of the histogram pass.
 //
-// The exact per-column order statistics use cub::DeviceRadixSort per column (library call on a row that
-// SURVEY 8f lists as "next"); everything else here is hand-written.
+// The exact per-column order statistics come from a hand-written radix multi-select (no sort, no library call).
 #include "engine.cuh"
 #include <cstdlib>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_segmented_sort.cuh>
 #include <cfloat>
 
 namespace gb {
 
-// transpose a 32-column slab of row-major X into column-major colbuf[c][i]
-__global__ void transpose_slab_kernel(const float *__restrict__ X, float *__restrict__ cols, int N, int F, int f0, int nf) {
-    __shared__ float tile[32][33];
-    int i0 = blockIdx.x * 32;
-    int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    for (int r = ty; r < 32; r += 8) {
-        int i = i0 + r, f = f0 + tx;
-        tile[r][tx] = (i < N && tx < nf) ? X[(size_t)i * F + f] : 0.0f;
+// ---------------------------------------------------------------- exact multi-select (quantile thresholds)
+// The B order statistics of every column, without sorting: a three-digit MSB radix select (11 + 11 + 10 bits of the
+// order-preserving key of the float) run for all 256 ranks of all columns at once.
+//   pass A  histogram of digit 1 of every element            (shared-memory counters, lane == column: coalesced rows)
+//   scan A  per target rank: its digit-1 bin and the rank inside that bin; targets with the same bin share a "leader"
+//   pass B  elements whose digit 1 is some target's bin: histogram of digit 2 in the leader's row
+//   scan B  per target: digit 2 and the remaining rank
+//   pass C  elements whose 22-bit prefix is some target's prefix: histogram of digit 3
+//   scan C  per target: digit 3 -> the key -> the threshold (an exact data value, bit for bit what a sort would deliver)
+// X is read three times (coalesced 128-byte row segments); only a few per cent of the elements reach passes B / C.
+constexpr int SEL_D1 = 2048, SEL_D2 = 2048, SEL_D3 = 1024;
+constexpr int SEL_THREADS = 512;
+
+__device__ __forceinline__ uint32_t sel_key(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // ascending unsigned order == ascending float order
+}
+__device__ __forceinline__ float sel_unkey(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// 0-based rank of threshold b in the ascending column (split_candidate_generator.cpp:216-240)
+__device__ __forceinline__ long long sel_rank(int b, int N, int B) {
+    const int actual = B + 1;
+    const int spb = N / actual, rem = N % actual;
+    long long idx = (long long)(b + 1) * spb + (b + 1 < rem ? b + 1 : rem) - 1;
+    if (idx < 0) idx = 0;   // N < n_bins+1: the reference reads index -1 (UB); we clamp
+    return idx;
+}
+
+struct SelParams {
+    const float *X; int N, F, B;
+    unsigned int *hist1;        // [F][SEL_D1]
+    unsigned int *hist2;        // [F][B][SEL_D2]   row of the leader target
+    unsigned int *hist3;        // [F][B][SEL_D3]
+    uint16_t *map1;             // [F][SEL_D1]  digit 1 -> leader target (0xffff: no target in this bin)
+    unsigned int *key2;         // [F][B]       22-bit prefix of every target (ascending in b)
+    int *lead1, *lead2;         // [F][B]       leader target of target b after digit 1 / digit 2
+    long long *rank1, *rank2;   // [F][B]       remaining rank inside the bin
+    float *thr;                 // [F][B]
+};
+
+// PASS 0: digit-1 histogram in shared memory (two columns per 32-bit word); PASS 1 / 2: filtered global histograms
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS, 1) sel_pass_kernel(SelParams P, int rows_per_cta) {
+    extern __shared__ unsigned int sm[];
+    const int slab = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = slab * 32 + lane;
+    const bool has_col = col < P.F;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(P.N, r0 + rows_per_cta);
+    uint16_t *smap = reinterpret_cast<uint16_t *>(sm);                       // PASS >= 1: [32][SEL_D1] u16
+    unsigned int *skey = sm + 32 * SEL_D1 / 2;                               // PASS 2:    [32][B] sorted 22-bit prefixes
+    if (PASS == 0) {
+        for (int i = threadIdx.x; i < SEL_D1 * 16; i += SEL_THREADS) sm[i] = 0u;
+    } else {
+        for (int i = threadIdx.x; i < 32 * SEL_D1; i += SEL_THREADS) {
+            const int c = i / SEL_D1, d = i - c * SEL_D1;
+            smap[i] = (slab * 32 + c < P.F) ? P.map1[(size_t)(slab * 32 + c) * SEL_D1 + d] : (uint16_t)0xffff;
+        }
+        if (PASS == 2) {
+            for (int i = threadIdx.x; i < 32 * P.B; i += SEL_THREADS) {
+                const int c = i / P.B, b = i - c * P.B;
+                skey[i] = (slab * 32 + c < P.F) ? P.key2[(size_t)(slab * 32 + c) * P.B + b] : 0xffffffffu;
+            }
+        }
     }
     __syncthreads();
-    for (int c = ty; c < 32; c += 8) {
-        int i = i0 + tx;
-        if (i < N && c < nf) cols[(size_t)c * N + i] = tile[tx][c];
+    constexpr int NWARP = SEL_THREADS / 32, UNR = 4;
+    for (int rowb = r0 + warp; rowb < r1; rowb += NWARP * UNR) {
+        uint32_t kk[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {                      // independent loads first: the pass is a latency-bound stream
+            const int row = rowb + u * NWARP;
+            kk[u] = (has_col && row < r1) ? sel_key(P.X[(size_t)row * P.F + col]) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            if (!has_col || rowb + u * NWARP >= r1) continue;
+            const uint32_t k = kk[u];
+            const uint32_t d1 = k >> 21;
+            if (PASS == 0) {
+                atomicAdd(&sm[d1 * 16 + (lane >> 1)], (lane & 1) ? 0x10000u : 1u);
+            } else {
+                const unsigned int ld = smap[lane * SEL_D1 + d1];
+                if (ld == 0xffffu) continue;
+                if (PASS == 1) {
+                    atomicAdd(&P.hist2[((size_t)col * P.B + ld) * SEL_D2 + ((k >> 10) & 0x7ffu)], 1u);
+                } else {
+                    // first target whose 22-bit prefix equals this element's (targets ascending): lower bound from the digit-1 leader on
+                    const uint32_t pre = k >> 10;
+                    const unsigned int *kc = skey + lane * P.B;
+                    int lo = (int)ld, hi = P.B;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (kc[mid] < pre) lo = mid + 1; else hi = mid; }
+                    if (lo < P.B && kc[lo] == pre) atomicAdd(&P.hist3[((size_t)col * P.B + lo) * SEL_D3 + (k & 0x3ffu)], 1u);
+                }
+            }
+        }
+    }
+    if (PASS == 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SEL_D1 * 16; i += SEL_THREADS) {
+            const unsigned int w = sm[i];
+            if (!w) continue;
+            const int d = i >> 4, c = slab * 32 + (i & 15) * 2;
+            if ((w & 0xffffu) && c < P.F) atomicAdd(&P.hist1[(size_t)c * SEL_D1 + d], w & 0xffffu);
+            if ((w >> 16) && c + 1 < P.F) atomicAdd(&P.hist1[(size_t)(c + 1) * SEL_D1 + d], w >> 16);
+        }
     }
 }
 
-// split_candidate_generator.cpp:216-240: thr[f][b] = sorted[cum_b - 1]; blockIdx.y = column inside the sorted slab
-__global__ void pick_quantiles_kernel(const float *__restrict__ sorted_cols, float *__restrict__ thr, int N, int B, int f0) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const float *sorted_col = sorted_cols + (size_t)blockIdx.y * N;
-    const int f = f0 + blockIdx.y;
-    int actual = B + 1;
-    int spb = N / actual, rem = N % actual;
-    long long cum = (long long)(b + 1) * spb + (b + 1 < rem ? b + 1 : rem);
-    long long idx = cum - 1;
-    if (idx < 0) idx = 0;   // N < n_bins+1: the reference reads index -1 (UB); we clamp
-    thr[(size_t)f * B + b] = sorted_col[idx];
+// exclusive prefix of `bins` counters (<= 8 per thread of a 256-thread CTA) into shared memory; returns nothing
+template <int BINS>
+__device__ __forceinline__ void block_prefix_256(const unsigned int *__restrict__ h, long long *s_pre /* [BINS + 1] */) {
+    __shared__ long long s_w[8];
+    constexpr int PER = BINS / 256;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    unsigned int v[PER];
+    long long loc = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { v[j] = h[t * PER + j]; loc += v[j]; }
+    long long inc = loc;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int hi = __shfl_up_sync(0xffffffffu, (int)(inc >> 32), o);
+        const unsigned int lo = (unsigned int)__shfl_up_sync(0xffffffffu, (int)(inc & 0xffffffffll), o);
+        if (lane >= o) inc += ((long long)hi << 32) | lo;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    long long base = 0;
+    for (int w = 0; w < warp; ++w) base += s_w[w];
+    long long run = base + inc - loc;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { s_pre[t * PER + j] = run; run += v[j]; }
+    if (t == 255) s_pre[BINS] = run;
+    __syncthreads();
+}
+
+// bin whose [pre[d], pre[d+1]) holds rank r
+template <int BINS>
+__device__ __forceinline__ int find_bin(const long long *s_pre, long long r) {
+    int lo = 0, hi = BINS - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[mid] <= r) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+// scan A: one CTA per column
+__global__ void __launch_bounds__(256) sel_scan1_kernel(SelParams P) {
+    __shared__ long long s_pre[SEL_D1 + 1];
+    __shared__ int s_d1[NB];
+    const int col = blockIdx.x;
+    block_prefix_256<SEL_D1>(P.hist1 + (size_t)col * SEL_D1, s_pre);
+    for (int i = threadIdx.x; i < SEL_D1; i += 256) P.map1[(size_t)col * SEL_D1 + i] = 0xffff;
+    const int b = threadIdx.x;
+    int d1 = 0;
+    if (b < P.B) {
+        const long long r = sel_rank(b, P.N, P.B);
+        d1 = find_bin<SEL_D1>(s_pre, r);
+        P.rank1[(size_t)col * P.B + b] = r - s_pre[d1];
+        s_d1[b] = d1;
+    }
+    __syncthreads();
+    if (b < P.B) {
+        int ld = b;
+        while (ld > 0 && s_d1[ld - 1] == d1) --ld;           // ranks ascend, so equal bins are adjacent
+        P.lead1[(size_t)col * P.B + b] = ld;
+        P.key2[(size_t)col * P.B + b] = (unsigned int)d1 << 11;
+        if (ld == b) P.map1[(size_t)col * SEL_D1 + d1] = (uint16_t)b;
+    }
+}
+
+// scan B: one CTA per (column, target)
+__global__ void __launch_bounds__(256) sel_scan2_kernel(SelParams P) {
+    __shared__ long long s_pre[SEL_D2 + 1];
+    const int col = blockIdx.x / P.B, b = blockIdx.x - col * P.B;
+    const size_t o = (size_t)col * P.B + b;
+    block_prefix_256<SEL_D2>(P.hist2 + ((size_t)col * P.B + P.lead1[o]) * SEL_D2, s_pre);
+    if (threadIdx.x == 0) {
+        const long long r = P.rank1[o];
+        const int d2 = find_bin<SEL_D2>(s_pre, r);
+        P.rank2[o] = r - s_pre[d2];
+        P.key2[o] |= (unsigned int)d2;
+    }
+}
+
+// leaders after digit 2 (equal 22-bit prefixes are adjacent); one thread per (column, target)
+__global__ void sel_lead2_kernel(SelParams P) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.F * P.B) return;
+    const int col = i / P.B, b = i - col * P.B;
+    const unsigned int *k = P.key2 + (size_t)col * P.B;
+    int ld = b;
+    while (ld > 0 && k[ld - 1] == k[b]) --ld;
+    P.lead2[i] = ld;
+}
+
+// scan C: one CTA per (column, target) -> the threshold
+__global__ void __launch_bounds__(256) sel_scan3_kernel(SelParams P) {
+    __shared__ long long s_pre[SEL_D3 + 1];
+    const int col = blockIdx.x / P.B, b = blockIdx.x - col * P.B;
+    const size_t o = (size_t)col * P.B + b;
+    block_prefix_256<SEL_D3>(P.hist3 + ((size_t)col * P.B + P.lead2[o]) * SEL_D3, s_pre);
+    if (threadIdx.x == 0) {
+        const int d3 = find_bin<SEL_D3>(s_pre, P.rank2[o]);
+        P.thr[o] = sel_unkey((P.key2[o] << 10) | (unsigned int)d3);
+    }
 }
 
 // split_candidate_generator.cpp:59-76 (uniform): one block per feature
@@ -100,45 +273,40 @@ void compute_thresholds(Model &m, const float *X, int N, int F, cudaStream_t s) 
     if (m.cfg.generator_type == GBRL_B200_GEN_UNIFORM) {
         GB_LAUNCH(uniform_thresholds_kernel, F, 256, 0, s, X, ws.thr.as<float>(), N, F, B);
     } else {
-        // exact order statistics of every column: sort a transposed 32-column slab.
-        //   N <= 256K  : one cub::DeviceSegmentedSort call per slab (32 segments) -- a handful of launches per
-        //                slab, which is what matters at RL batch sizes;
-        //   larger N   : one device-wide cub::DeviceRadixSort per column.
-        const bool segmented = N <= 262144;
-        ws.colbuf[0].ensure((size_t)32 * N * sizeof(float));
-        ws.colbuf[1].ensure((size_t)(segmented ? 32 : 1) * N * sizeof(float));
-        size_t tmp = 0;
-        if (segmented) {
-            ws.sort_offsets.ensure(33 * sizeof(int));
-            int h_off[33];
-            for (int i = 0; i <= 32; ++i) h_off[i] = i * N;
-            GB_CUDA(cudaMemcpyAsync(ws.sort_offsets.p, h_off, sizeof(h_off), cudaMemcpyHostToDevice, s));
-            GB_CUDA(cudaStreamSynchronize(s));      // h_off is a stack buffer
-            cub::DeviceSegmentedSort::SortKeys(nullptr, tmp, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), 32 * N, 32,
-                                               ws.sort_offsets.as<int>(), ws.sort_offsets.as<int>() + 1, s);
-        } else {
-            cub::DeviceRadixSort::SortKeys(nullptr, tmp, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), N, 0, 32, s);
-        }
-        ws.sort_tmp.ensure(tmp);
-        for (int f0 = 0; f0 < F; f0 += 32) {
-            int nf = F - f0 < 32 ? F - f0 : 32;
-            GB_LAUNCH(transpose_slab_kernel, ceil_div(N, 32), 256, 0, s, X, ws.colbuf[0].as<float>(), N, F, f0, nf);
-            if (segmented) {
-                size_t t2 = tmp;
-                GB_CUDA(cub::DeviceSegmentedSort::SortKeys(ws.sort_tmp.p, t2, ws.colbuf[0].as<float>(), ws.colbuf[1].as<float>(), nf * N, nf,
-                                                           ws.sort_offsets.as<int>(), ws.sort_offsets.as<int>() + 1, s));
-                g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-                GB_LAUNCH(pick_quantiles_kernel, dim3(ceil_div(B, 256), nf), 256, 0, s, ws.colbuf[1].as<float>(), ws.thr.as<float>(), N, B, f0);
-            } else {
-                for (int c = 0; c < nf; ++c) {
-                    size_t t2 = tmp;
-                    GB_CUDA(cub::DeviceRadixSort::SortKeys(ws.sort_tmp.p, t2, ws.colbuf[0].as<float>() + (size_t)c * N,
-                                                           ws.colbuf[1].as<float>(), N, 0, 32, s));
-                    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
-                    GB_LAUNCH(pick_quantiles_kernel, dim3(ceil_div(B, 256), 1), 256, 0, s, ws.colbuf[1].as<float>(), ws.thr.as<float>(), N, B, f0 + c);
-                }
-            }
-        }
+        // exact order statistics of every column by a three-pass radix multi-select (no sort, no library call)
+        const size_t FB = (size_t)F * B;
+        const size_t bytes = (size_t)F * SEL_D1 * 4 + FB * SEL_D2 * 4 + FB * SEL_D3 * 4 + (size_t)F * SEL_D1 * 2 + FB * 4 * 3 + FB * 8 * 2 + 256;
+        ws.sort_tmp.ensure(bytes);
+        char *p = ws.sort_tmp.as<char>();
+        SelParams P;
+        P.X = X; P.N = N; P.F = F; P.B = B; P.thr = ws.thr.as<float>();
+        P.rank1 = reinterpret_cast<long long *>(p); p += FB * 8;
+        P.rank2 = reinterpret_cast<long long *>(p); p += FB * 8;
+        P.hist1 = reinterpret_cast<unsigned int *>(p); p += (size_t)F * SEL_D1 * 4;
+        P.hist2 = reinterpret_cast<unsigned int *>(p); p += FB * SEL_D2 * 4;
+        P.hist3 = reinterpret_cast<unsigned int *>(p); p += FB * SEL_D3 * 4;
+        P.key2 = reinterpret_cast<unsigned int *>(p); p += FB * 4;
+        P.lead1 = reinterpret_cast<int *>(p); p += FB * 4;
+        P.lead2 = reinterpret_cast<int *>(p); p += FB * 4;
+        P.map1 = reinterpret_cast<uint16_t *>(p);
+        GB_CUDA(cudaMemsetAsync(P.hist1, 0, (size_t)F * SEL_D1 * 4 + FB * SEL_D2 * 4 + FB * SEL_D3 * 4, s));
+        const int slabs = ceil_div(F, 32);
+        // rows per CTA: <= 65535 (16-bit shared counters of pass A), enough CTAs to fill the GPU
+        int ctas = ceil_div(ws.n_sms * 2, slabs);
+        if (ctas < ceil_div(N, 60000)) ctas = ceil_div(N, 60000);
+        if (ctas > ceil_div(N, 64)) ctas = ceil_div(N, 64);
+        if (ctas < 1) ctas = 1;
+        const int rows_per_cta = ceil_div(N, ctas);
+        dim3 grid(ceil_div(N, rows_per_cta), slabs);
+        const size_t sm0 = (size_t)SEL_D1 * 16 * 4, sm1 = (size_t)32 * SEL_D1 * 2, sm2 = sm1 + (size_t)32 * B * 4;
+        ensure_dyn_smem(sel_pass_kernel<0>, sm0); ensure_dyn_smem(sel_pass_kernel<1>, sm1); ensure_dyn_smem(sel_pass_kernel<2>, sm2);
+        GB_LAUNCH(sel_pass_kernel<0>, grid, SEL_THREADS, sm0, s, P, rows_per_cta);
+        GB_LAUNCH(sel_scan1_kernel, F, 256, 0, s, P);
+        GB_LAUNCH(sel_pass_kernel<1>, grid, SEL_THREADS, sm1, s, P, rows_per_cta);
+        GB_LAUNCH(sel_scan2_kernel, (int)FB, 256, 0, s, P);
+        GB_LAUNCH(sel_lead2_kernel, ceil_div((int)FB, 256), 256, 0, s, P);
+        GB_LAUNCH(sel_pass_kernel<2>, grid, SEL_THREADS, sm2, s, P, rows_per_cta);
+        GB_LAUNCH(sel_scan3_kernel, (int)FB, 256, 0, s, P);
     }
     int total = ws.nT * NB * FT;
     GB_LAUNCH(tile_thresholds_kernel, ceil_div(total, 256), 256, 0, s, ws.thr.as<float>(), ws.thrT.as<float>(), F, B, ws.nT);
@@ -199,7 +367,7 @@ bin_kernel(const float *__restrict__ X, const float *__restrict__ thrT, uint16_t
 // the row-major fp32 matrix.  x > thr[f][j]  <=>  code(x) > j, so the comparisons are the reference's.
 __global__ void __launch_bounds__(256)
 bin_featmajor_kernel(const float *__restrict__ X, const float *__restrict__ thrT, uint16_t *__restrict__ codesT, int N, int F,
-                     long long stride, int rows_per_cta) {
+                     long long stride, int rows_per_cta, uint16_t *__restrict__ codes, int tile_lo, int tile_hi) {
     __shared__ float sthr[NB * FT];
     __shared__ uint16_t s_c[FT][36];
     const int tile = blockIdx.y;
@@ -236,6 +404,13 @@ bin_featmajor_kernel(const float *__restrict__ X, const float *__restrict__ thrT
                 if (mslot == 0) c[0] = pos; else if (mslot == 1) c[1] = pos; else if (mslot == 2) c[2] = pos; else c[3] = pos;
             }
         }
+        // the same codes in the tile-major layout of the histogram pass (pre-scaled), for the tiles this rank owns: X is read once
+        if (codes != nullptr && tile >= tile_lo && tile < tile_hi && row < row1) {
+            uint2 w;
+            w.x = (c[0] << CODE_SHIFT) | (c[1] << (16 + CODE_SHIFT));
+            w.y = (c[2] << CODE_SHIFT) | (c[3] << (16 + CODE_SHIFT));
+            *reinterpret_cast<uint2 *>(codes + ((size_t)(tile - tile_lo) * N + row) * FT + g * 4) = w;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) s_c[g * 4 + k][r] = (uint16_t)c[k];
         __syncthreads();
@@ -256,17 +431,20 @@ void bin_features(Model &m, const float *X, int N, int F, cudaStream_t s) {
     ws.codes.ensure((size_t)ntl * N * FT * sizeof(uint16_t));
     if (ntl <= 0 || N == 0) return;
     int rows_per_cta = 1024;
-    dim3 grid(ceil_div(N, rows_per_cta), ntl);
-    GB_LAUNCH(bin_kernel, grid, 256, 0, s, X, ws.thrT.as<float>(), ws.codes.as<uint16_t>(), N, F, ws.tile_lo, rows_per_cta);
     // the feature-major copy pays off once the fp32 matrix no longer sits in L2 (a PPO minibatch does)
     // (GBRL_B200_FEATMAJOR=1 / 0 forces it on / off: the parity tests run both paths on the same small inputs)
     const char *force = getenv("GBRL_B200_FEATMAJOR");
     ws.use_codesT = force ? (force[0] == '1') : ((size_t)N * F * sizeof(float) > ((size_t)48 << 20));
     if (ws.use_codesT) {
+        // one pass over X writes both layouts
         ws.codesT_stride = ((long long)N + 7) & ~7ll;
         ws.codesT.ensure((size_t)F * ws.codesT_stride * sizeof(uint16_t) + 64);
         dim3 grid_t(ceil_div(N, rows_per_cta), ws.nT);
-        GB_LAUNCH(bin_featmajor_kernel, grid_t, 256, 0, s, X, ws.thrT.as<float>(), ws.codesT.as<uint16_t>(), N, F, ws.codesT_stride, rows_per_cta);
+        GB_LAUNCH(bin_featmajor_kernel, grid_t, 256, 0, s, X, ws.thrT.as<float>(), ws.codesT.as<uint16_t>(), N, F, ws.codesT_stride, rows_per_cta,
+                  ws.codes.as<uint16_t>(), ws.tile_lo, ws.tile_hi);
+    } else {
+        dim3 grid(ceil_div(N, rows_per_cta), ntl);
+        GB_LAUNCH(bin_kernel, grid, 256, 0, s, X, ws.thrT.as<float>(), ws.codes.as<uint16_t>(), N, F, ws.tile_lo, rows_per_cta);
     }
 }
 
