@@ -4,6 +4,7 @@
 // error conditions for the calls on the hot path; the device work is delegated to the kernels in this
 // directory.  There is no CPU path: every entry point requires a CUDA device.
 #include "engine.cuh"
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include <string.h>
 #include <algorithm>
 #include <numeric>
@@ -330,7 +331,12 @@ static float do_fit(Model &m, const float *obs, int obs_dev, const float *target
 }
 
 // ---------------------------------------------------------------- profiling
+static const char *const PROF_NAMES[P_NCAT] = {"gbrl_b200/candidates", "gbrl_b200/binning", "gbrl_b200/preprocess", "gbrl_b200/histogram",
+                                               "gbrl_b200/exchange", "gbrl_b200/scan", "gbrl_b200/select_replay", "gbrl_b200/plan_decide",
+                                               "gbrl_b200/partition", "gbrl_b200/finalize", "gbrl_b200/predict"};
+
 ProfScope::ProfScope(Model &m_, int cat_, cudaStream_t s_) : m(m_), cat(cat_), s(s_), on(m_.profile) {
+    nvtxRangePushA(PROF_NAMES[cat]);          // one NVTX range per kernel class (shows up in nsys / ncu --nvtx timelines)
     if (!on) return;
     if (m.prof_used + 2 > m.prof_events.size()) {
         for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); m.prof_events.push_back(e); }
@@ -341,6 +347,7 @@ ProfScope::ProfScope(Model &m_, int cat_, cudaStream_t s_) : m(m_), cat(cat_), s
     cudaEventRecord(m.prof_events[idx], s);
 }
 ProfScope::~ProfScope() {
+    nvtxRangePop();
     if (!on) return;
     cudaEventRecord(m.prof_events[idx + 1], s);
     m.prof_launches.push_back(g_kernel_launches.load() - l0);

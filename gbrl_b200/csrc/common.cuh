@@ -19,7 +19,7 @@ constexpr int FLUSH_ITEMS = 8;    // a CTA flushes its shared-memory histogram t
 constexpr int MAX_DEPTH_SUPPORTED = 12;
 constexpr int MAX_OPTS = 64;
 constexpr int HIST_THREADS = 512;
-constexpr int CODE_SHIFT = 6;       // the code matrix stores code << 6 (byte offset of a histogram row / 2)
+constexpr int CODE_SHIFT = 7;       // the code matrix stores code << 7 = byte offset of the code's row in a shared histogram plane
 constexpr int SCAN_THREADS = 256;
 
 // ---------------------------------------------------------------- errors

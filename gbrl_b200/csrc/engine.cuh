@@ -98,6 +98,7 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     bool use_codesT = false;
     int codes_rows = 0;             // rows of the code matrix (tile stride); >= N when a tree is grown on a mini-batch
     int row_offset = 0;             // first row of the current mini-batch inside the code matrix
+    DevBuf bgq;                          // build_grads as fixed point, split (lo 18 bits, hi): what the histogram atomics add
     DevBuf codes, thr, thrT, bg, order[2], nid, rflag, chunk_sums, hist[2], scores, cand_flags;
     int chunk_cap = 0;                   // capacity of chunk_sums (entries); entry [chunk_cap] is the partition's done counter
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;

@@ -56,7 +56,7 @@ void launch_plan_level(Model &m, int level, cudaStream_t s) {
 // ---------------------------------------------------------------- the histogram kernel
 // dynamic shared memory: (1 + 2*ND) planes of (NB+1)*FT int32; row 0 of every plane is a dump row for code 0
 // (x <= every threshold: right of no candidate), which keeps the inner loop branch-free.
-// The code matrix stores code*64 (u16), so byte offset of (code, feature fs) inside a plane = stored*2 + fs*4.
+// The code matrix stores code*128 (u16) = the byte offset of the code's row inside a plane; + fs*4 for the feature.
 constexpr int HPLANE = (NB + 1) * FT;          // ints per plane
 
 __device__ __forceinline__ void red_shared(unsigned int addr, int v) {
@@ -136,7 +136,7 @@ hist_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, co
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const unsigned int cs = __byte_perm(upper[k] ? b[s].y : b[s].x, 0u, psel[k]);   // code * 64, zero-extended
-                    const unsigned int addr = lbase[k] + cs * 2u;
+                    const unsigned int addr = lbase[k] + cs;
                     red_shared(addr, 1);
                     red_shared_off<PB>(addr, lo[0]);
                     red_shared_off<2 * PB>(addr, hi[0]);
@@ -205,25 +205,24 @@ constexpr int HS_FLUSH_ITEMS = 32;   // hi planes: 32 items x 2048 rows x 2^14 =
 __device__ __forceinline__ void cp_async_16(unsigned int dst, const void *src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_4(unsigned int dst, const void *src, int src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async_8(unsigned int dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int ND, int NWARPS, int NST>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
-hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__ bg, const int *__restrict__ order,
+hist_stream_kernel(const uint16_t *__restrict__ codes, const int2 *__restrict__ bgq, const int *__restrict__ order,
                    const Item *__restrict__ items, const Ctl *__restrict__ ctl, long long *__restrict__ hist, int codes_rows,
                    int row_offset, int D, int d0, int nT_local, int tile_lo, int nT_total, int write_count) {
     extern __shared__ int sh[];
     constexpr int W = 1 + 2 * ND;
     constexpr int PB = HPLANE * 4;               // plane size in bytes
     constexpr int NTHREADS = NWARPS * 32;
-    constexpr int RING_GRAD = HS_STAGE_ROWS * 64;              // a ring stage: 16 rows x 64 B of codes, then 16 x ND gradients
-    constexpr int RING_STAGE = RING_GRAD + HS_STAGE_ROWS * 4 * ND;
+    constexpr int RING_GRAD = HS_STAGE_ROWS * 64;              // a ring stage: 16 rows x 64 B of codes, then 16 x ND fixed-point gradients (lo, hi)
+    constexpr int RING_STAGE = RING_GRAD + HS_STAGE_ROWS * 8 * ND;
     const int n_items = ctl->n_items;
-    const float scale = exp2f((float)ctl->qexp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rl = (lane >> 3) & 3, g = lane & 7;
     const int HS = 1 + D;
@@ -245,21 +244,23 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__
     }
     __syncthreads();
 
-    // flush: (bin, feature) e -> global [slot][tile][bin][feature][1+D]; shared row = bin + 1
-    auto flush = [&](const Item &it) {
+    // flush: (bin, feature) e -> global [slot][tile][bin][feature][1+D]; shared row = bin + 1.  The level buffer is zeroed
+    // before the launch, so a (node, tile) pair whose items all belong to this CTA is written with plain stores; pairs
+    // that are shared with a neighbouring CTA (or flushed more than once) are added with REDG.64.
+    auto flush = [&](const Item &it, bool excl) {
         long long *hb = hist + ((size_t)it.slot * nT_total + (tile_lo + it.tile)) * (size_t)(NB * FT) * HS;
         for (int e = threadIdx.x; e < NB * FT; e += NTHREADS) {
             const int se = e + FT;
             const int cnt = sh[se];
             if (cnt != 0) {
-                if (write_count) red_add64(hb + (size_t)e * HS, (long long)cnt);
+                if (write_count) { if (excl) hb[(size_t)e * HS] = (long long)cnt; else red_add64(hb + (size_t)e * HS, (long long)cnt); }
                 sh[se] = 0;
 #pragma unroll
                 for (int dd = 0; dd < ND; ++dd) {
                     const unsigned int l = (unsigned int)sh[(1 + 2 * dd) * HPLANE + se];
                     const int h = sh[(2 + 2 * dd) * HPLANE + se];
                     const long long tot = ((long long)h << LO_BITS) + (long long)l;
-                    if (tot != 0) red_add64(hb + (size_t)e * HS + 1 + d0 + dd, tot);
+                    if (tot != 0) { if (excl) hb[(size_t)e * HS + 1 + d0 + dd] = tot; else red_add64(hb + (size_t)e * HS + 1 + d0 + dd, tot); }
                     sh[(1 + 2 * dd) * HPLANE + se] = 0;
                     sh[(2 + 2 * dd) * HPLANE + se] = 0;
                 }
@@ -320,8 +321,8 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__
                 if (lane < 16) {
 #pragma unroll
                     for (int dd = 0; dd < ND; ++dd)
-                        cp_async_4(dst + (unsigned int)(RING_GRAD + (lane * ND + dd) * 4), bg + (size_t)(mine >= 0 ? mine : 0) * D + d0 + dd,
-                                   mine >= 0 ? 4 : 0);
+                        cp_async_8(dst + (unsigned int)(RING_GRAD + (lane * ND + dd) * 8), bgq + (size_t)(mine >= 0 ? mine : 0) * D + d0 + dd,
+                                   mine >= 0 ? 8 : 0);
                 }
             } else vbits &= ~(1u << (t & 31));
         }
@@ -332,6 +333,9 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__
     for (int t = 0; t < NST - 1; ++t) issue(t);
     int since_flush = 0, since_fold = 0;
     Item prev = items[i0];
+    // is the current (node, tile) pair exclusively this CTA's?  (its first item is inside the CTA's range; cleared by a forced flush)
+    bool pair_excl = true;
+    if (i0 > 0) { const Item pv = items[i0 - 1]; pair_excl = pv.slot != prev.slot || pv.tile != prev.tile; }
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
         issue(t + NST - 1);
@@ -346,17 +350,12 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b.x), "=r"(b.y) : "r"(src + (unsigned int)(r * 64 + g * 8)));
                 int lo[ND], hi[ND];
 #pragma unroll
-                for (int dd = 0; dd < ND; ++dd) {
-                    float gv;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gv) : "r"(src + (unsigned int)(RING_GRAD + (r * ND + dd) * 4)));
-                    const long long q = __float2ll_rn(gv * scale);
-                    lo[dd] = (int)(q & ((1ll << LO_BITS) - 1));
-                    hi[dd] = (int)(q >> LO_BITS);
-                }
+                for (int dd = 0; dd < ND; ++dd)       // (lo, hi) of the fixed-point gradient, converted once per tree (preprocess.cu)
+                    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(lo[dd]), "=r"(hi[dd]) : "r"(src + (unsigned int)(RING_GRAD + (r * ND + dd) * 8)));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const unsigned int cs = __byte_perm(upper[k] ? b.y : b.x, 0u, psel[k]);   // code * 64, zero-extended
-                    const unsigned int addr = lbase[k] + cs * 2u;
+                    const unsigned int cs = __byte_perm(upper[k] ? b.y : b.x, 0u, psel[k]);   // code * 128, zero-extended
+                    const unsigned int addr = lbase[k] + cs;
                     red_shared(addr, 1);
                     red_shared_off<PB>(addr, lo[0]);
                     red_shared_off<2 * PB>(addr, hi[0]);
@@ -368,17 +367,19 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__
         if ((t & 3) == 3) {                       // item boundary (CTA-uniform decisions: they depend on the item list only)
             ++since_flush; ++since_fold;
             const int nx = (t >> 2) + 1;
-            bool do_flush = false;
+            bool pair_ends = false, forced = false;
             Item nxt = prev;
             if (nx < n_my) {
                 nxt = items[i0 + nx];
-                do_flush = nxt.slot != prev.slot || nxt.tile != prev.tile || since_flush >= HS_FLUSH_ITEMS;
+                pair_ends = nxt.slot != prev.slot || nxt.tile != prev.tile;
+                forced = !pair_ends && since_flush >= HS_FLUSH_ITEMS;
             }
-            if (do_flush) {
+            if (pair_ends || forced) {
                 __syncthreads();
-                flush(prev);
+                flush(prev, pair_excl && pair_ends);
                 __syncthreads();
                 since_flush = 0; since_fold = 0;
+                pair_excl = pair_ends;            // a new pair starts inside the range; a forced flush leaves the pair shared with itself
             } else if (since_fold >= HS_FOLD_ITEMS && nx < n_my) {
                 __syncthreads();
                 fold();
@@ -390,15 +391,19 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const float *__restrict__
     }
     cp_async_wait<0>();
     __syncthreads();
-    flush(prev);
+    {
+        bool last_inside = true;                  // does the pair end with this CTA's last item?
+        if (i1 < n_items) { const Item nx = items[i1]; last_inside = nx.slot != prev.slot || nx.tile != prev.tile; }
+        flush(prev, pair_excl && last_inside);
+    }
 }
 
 template <int ND, int NWARPS, int NST>
 static void launch_hist_stream(Model &m, int d0, int write_count, long long *hist, int n_sms, cudaStream_t s) {
     Workspace &ws = m.ws;
-    const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int) + (size_t)NWARPS * NST * HS_STAGE_ROWS * (64 + 4 * ND);   // planes + rings
+    const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int) + (size_t)NWARPS * NST * HS_STAGE_ROWS * (64 + 8 * ND);   // planes + rings
     ensure_dyn_smem(hist_stream_kernel<ND, NWARPS, NST>, smem);
-    GB_LAUNCH((hist_stream_kernel<ND, NWARPS, NST>), n_sms, NWARPS * 32, smem, s, ws.codes.as<uint16_t>(), ws.bg.as<float>(),
+    GB_LAUNCH((hist_stream_kernel<ND, NWARPS, NST>), n_sms, NWARPS * 32, smem, s, ws.codes.as<uint16_t>(), ws.bgq.as<int2>(),
               ws.order[0].as<int>(), ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
               ws.tile_hi - ws.tile_lo, ws.tile_lo, ws.nT, write_count);
 }

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) predict_kernel(PredictParams P) {
 // The split parameters and leaf values of a chunk are contiguous in the reference's SoA layout (types.h:279-304), so one
 // elected thread brings them into shared memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), double
 // buffered one chunk ahead: the ensemble is read from L2 once per 64 observations instead of once per warp and tree.
-constexpr int PT_SAMPLES = 64, PT_SUB = 2, PT_WARPS = 16, PT_CONS = PT_SUB, PT_PROD = PT_WARPS - PT_CONS;
+constexpr int PT_SAMPLES = 64, PT_SUB = 2, PT_WARPS = 32, PT_CONS = PT_SUB, PT_PROD = PT_WARPS - PT_CONS;
 constexpr int PT_XS = PT_SAMPLES + 1;          // row stride of the transposed observation tile (bank == lane)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(PT_WARPS * 32, 1)
 predict_tiles_kernel(PredictParams P, TileLayout L, int TC, int n_trees_total, int n_leaves_total, long long val_capacity_floats) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_opt_of_dim[DM];
+    __shared__ float s_lr[DM];          // per output: the learning rate of its optimizer when every scheduler is constant
+    __shared__ int s_all_const;
     __shared__ int s_voff[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s0 = blockIdx.x * PT_SAMPLES;
@@ -156,6 +158,12 @@ predict_tiles_kernel(PredictParams P, TileLayout L, int TC, int n_trees_total, i
         for (int o = 0; o < P.n_opts; ++o)
             if ((int)threadIdx.x >= P.opts[o].start_idx && (int)threadIdx.x < P.opts[o].stop_idx) o_of = o;
         s_opt_of_dim[threadIdx.x] = o_of;
+        s_lr[threadIdx.x] = o_of >= 0 ? P.opts[o_of].init_lr : 0.0f;       // an output without optimizer is never updated: x = 0
+    }
+    if (threadIdx.x == 0) {
+        int ac = 1;
+        for (int o = 0; o < P.n_opts; ++o) ac &= (P.opts[o].sched == GBRL_B200_SCHED_CONST);
+        s_all_const = ac;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // observations, transposed: xT[f][sample]
@@ -196,6 +204,7 @@ predict_tiles_kernel(PredictParams P, TileLayout L, int TC, int n_trees_total, i
         for (int d = 0; d < DM; ++d) theta[d] = (d < D && i < P.N) ? (P.add_bias ? P.bias[d] : P.preds[(size_t)i * D + d]) : 0.0f;
     }
     uint32_t phase[2] = {0u, 0u};
+    const bool all_const = s_all_const != 0;          // published by the __syncthreads() above
 #pragma unroll 1
     for (int c = 0; c <= n_chunks; ++c) {
         const int b = c & 1;
@@ -217,26 +226,31 @@ predict_tiles_kernel(PredictParams P, TileLayout L, int TC, int n_trees_total, i
                 const float *val = reinterpret_cast<const float *>(st + L.val) + s_voff[b];
                 float *E = reinterpret_cast<float *>(smem + L.elems[b]);
                 const int lbase = ti[0];
-                for (int task = warp - PT_CONS; task < tcnt * PT_SUB; task += PT_PROD) {
-                    const int j = task / PT_SUB, sub = task - j * PT_SUB;
+                // a producer warp takes whole trees: the split parameters are read once for both sub-tiles
+                for (int j = warp - PT_CONS; j < tcnt; j += PT_PROD) {
                     const int t = t0 + j;
-                    float *e = E + ((size_t)(j * PT_SUB + sub) * DM) * 32 + lane;
                     if (t < P.start_tree || t >= P.stop_tree) continue;
                     const int dj = dep[j];
-                    int li = 0;
-                    for (int k = 0; k < dj; ++k) {                                           // predictor.cpp:248-252
-                        const int f = fi[j * md + k];
-                        li |= (xT[f * PT_XS + sub * 32 + lane] > fv[j * md + k] ? 1 : 0) << (dj - 1 - k);
+                    int li0 = 0, li1 = 0;
+                    for (int k = 0; k < dj; ++k) {                                           // predictor.cpp:248-252, most significant bit first
+                        const float *xr = xT + fi[j * md + k] * PT_XS + lane;
+                        const float th = fv[j * md + k];
+                        li0 = (li0 << 1) | (xr[0] > th ? 1 : 0);
+                        li1 = (li1 << 1) | (xr[32] > th ? 1 : 0);
                     }
-                    const float *v = val + (size_t)(ti[j] - lbase + li) * D;
+                    const float *vb = val + (size_t)(ti[j] - lbase) * D;
+                    float *e = E + ((size_t)(j * PT_SUB) * DM) * 32 + lane;
 #pragma unroll
                     for (int d = 0; d < DM; ++d) {
-                        float x = 0.0f;
+                        float x0 = 0.0f, x1 = 0.0f;
                         if (d < D) {
-                            const int o = s_opt_of_dim[d];
-                            if (o >= 0) x = sched_lr(P.opts[o], t) * v[d];                   // optimizer.cpp:110-118: lr * value ...
+                            float lr = s_lr[d];                                              // optimizer.cpp:110-118: lr * value ...
+                            if (!all_const) { const int o = s_opt_of_dim[d]; lr = o >= 0 ? sched_lr(P.opts[o], t) : 0.0f; }
+                            x0 = lr * vb[(size_t)li0 * D + d];
+                            x1 = lr * vb[(size_t)li1 * D + d];
                         }
-                        e[d * 32] = x;
+                        e[d * 32] = x0;
+                        e[(DM + d) * 32] = x1;
                     }
                 }
             }
@@ -269,8 +283,8 @@ static bool launch_predict_tiles(Model &m, const PredictParams &P, cudaStream_t 
     const Ensemble &e = m.ens;
     const int md = P.md > 0 ? P.md : 1;
     // trees per chunk: the leaf values of a chunk (<= TC * 2^md * D floats) must fit a 32 KB stage
-    int TC = 64;
-    while (TC > 4 && (long long)TC * (1ll << md) * P.D * 4 > 32768) TC >>= 1;
+    int TC = 60;                                      // 2 trees per producer warp and chunk; a multiple of 4 (16-byte aligned bulk copies)
+    while (TC > 4 && (long long)TC * (1ll << md) * P.D * 4 > 32768) TC = (TC / 2) & ~3;
     if ((long long)TC * (1ll << md) * P.D * 4 > 32768) return false;
     const int val_bytes = TC * (1 << md) * P.D * 4 + 32;
     const TileLayout L = tile_layout(P.F, md, DM, TC, val_bytes);

@@ -555,6 +555,14 @@ __global__ void max_only_kernel(const float *g, Ctl *ctl, long long n_elements, 
     if ((threadIdx.x & 31) == 0) atomicMax(which == 0 ? &ctl->max_abs_bg : &ctl->max_abs_raw, __float_as_uint(mx));
 }
 
+__global__ void __launch_bounds__(256) quantize_bg_kernel(const float *__restrict__ bg, int2 *__restrict__ q, const Ctl *__restrict__ ctl, long long ne) {
+    const float scale = exp2f((float)ctl->qexp);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ne; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = __float2ll_rn(bg[i] * scale);
+        q[i] = make_int2((int)(v & ((1ll << LO_BITS) - 1)), (int)(v >> LO_BITS));
+    }
+}
+
 // q = rint(g * 2^qexp) must satisfy |q| < 2^(Q_BITS-1)
 __global__ void qexp_kernel(Ctl *ctl, int which) {
     const float mx = __uint_as_float(which == 0 ? ctl->max_abs_bg : ctl->max_abs_raw);
@@ -611,6 +619,9 @@ void build_grads(Model &m, const float *grads, int N, cudaStream_t s) {
         GB_LAUNCH(max_only_kernel, grid, 256, 0, s, ws.bg.as<float>(), ctl, ne, 0);
     }
     GB_LAUNCH(qexp_kernel, 1, 1, 0, s, ctl, 0);
+    // the fixed-point form the histogram pass adds (q = rint(g * 2^qexp) = hi * 2^18 + lo), converted once per tree
+    ws.bgq.ensure((size_t)(ne > 0 ? ne : 1) * sizeof(int2));
+    if (ne > 0) GB_LAUNCH(quantize_bg_kernel, grid, 256, 0, s, ws.bg.as<float>(), ws.bgq.as<int2>(), ctl, ne);
 }
 
 void raw_grad_scale(Model &m, const float *grads, int N, cudaStream_t s) {

@@ -74,3 +74,15 @@ def test_product_path_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert "oracle" not in txt.lower(), "%s mentions the oracle" % fn
+
+
+def test_reference_side_cpp_backend_compiles_and_links():
+    """INTEGRATION.md section 2 is code: integration/b200_backend.h (written against the reference's types.h) was compiled and
+    linked against libgbrl_b200.so by `make -C oracle backend_check`; the resulting object loads and exports its probe."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libb200_backend_check.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libb200_backend_check.so not built (reference headers not mounted)")
+    from gbrl_b200 import _capi
+    _capi.lib()
+    L = C.CDLL(path)
+    assert hasattr(L, "gbrl_b200_backend_check")

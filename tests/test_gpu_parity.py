@@ -167,7 +167,12 @@ def test_candidates_match_oracle_bitwise():
     _, thr = o.o.root_scores(X, grads)
     g.step(X, grads)
     got = g.m.get_candidates()
-    assert np.array_equal(thr.view(np.uint32), got.view(np.uint32))
+    # bit for bit, except the sign of a zero threshold: -0.0 and +0.0 compare equal, so which of the two a sort leaves at a given
+    # rank is an artefact of the sort (std::sort in the reference, qsort in the oracle, a radix select here) and no comparison
+    # x > threshold can tell them apart
+    nz = (thr != 0) | (got != 0)
+    assert np.array_equal(thr.view(np.uint32)[nz], got.view(np.uint32)[nz])
+    assert np.array_equal(thr, got)
     o.step(X, grads)
     compare_ensembles(o.ensemble(), g.ensemble(), "ties")
 
