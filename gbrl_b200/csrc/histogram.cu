@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(1024) plan_level_kernel(NodeArrays na, Ctl *ct
 
 // rows per work item: the streaming kernel wants NWARPS * 64 (two 32-row blocks per warp), the per-item kernel 8192
 int hist_item_rows(const Model &m) {
-    if (m.cfg.hist_variant != 0) return ITEM_ROWS;
-    return m.cfg.output_dim == 1 ? 32 * 64 : 24 * 64;
+    if (m.cfg.hist_variant == 1) return ITEM_ROWS;
+    return (m.cfg.output_dim == 1 && m.cfg.hist_variant == 0) ? 32 * 64 : 24 * 64;
 }
 
 PlanParams plan_params(const Model &m) {
@@ -300,6 +300,7 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const int2 *__restrict__ 
         const int k = it.k0 + ((blk & 1) * NWARPS + warp) * 32 + lane;
         return k < it.k1 ? order[k] : -1;
     };
+    int slot_issue = 0, slot_use = 0;             // ring slots of the stage being issued / consumed (t % NST, kept incrementally)
     auto issue = [&](int t) {
         if (t < T) {
             if ((t & 1) == 0) {                   // first half of a block: rotate the prefetched row ids
@@ -311,7 +312,7 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const int2 *__restrict__ 
             if (__any_sync(0xffffffffu, mine >= 0)) {
                 vbits |= 1u << (t & 31);
                 const uint16_t *ctile = codes + ((size_t)tile_i * codes_rows + row_offset) * FT;
-                const unsigned int dst = ring + (unsigned int)((t % NST) * RING_STAGE);
+                const unsigned int dst = ring + (unsigned int)(slot_issue * RING_STAGE);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int r = j * 8 + (lane >> 2), q = lane & 3;            // row in stage, 16-byte quarter
@@ -326,6 +327,7 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const int2 *__restrict__ 
                 }
             } else vbits &= ~(1u << (t & 31));
         }
+        slot_issue = slot_issue + 1 == NST ? 0 : slot_issue + 1;      // ring slot of the next stage (no modulo in the loop)
         cp_async_commit();
     };
     rows_n = block_rows(0, tile_n);
@@ -342,7 +344,7 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const int2 *__restrict__ 
         cp_async_wait<NST - 1>();
         __syncwarp();
         if ((vbits >> (t & 31)) & 1u) {
-            const unsigned int src = ring + (unsigned int)((t % NST) * RING_STAGE);
+            const unsigned int src = ring + (unsigned int)(slot_use * RING_STAGE);
 #pragma unroll
             for (int ss = 0; ss < 4; ++ss) {
                 const int r = ss * 4 + rl;
@@ -364,6 +366,7 @@ hist_stream_kernel(const uint16_t *__restrict__ codes, const int2 *__restrict__ 
             }
         }
         __syncwarp();                             // the stage buffer is refilled NST - 1 iterations later by other lanes
+        slot_use = slot_use + 1 == NST ? 0 : slot_use + 1;
         if ((t & 3) == 3) {                       // item boundary (CTA-uniform decisions: they depend on the item list only)
             ++since_flush; ++since_fold;
             const int nx = (t >> 2) + 1;
@@ -429,11 +432,11 @@ void launch_histogram(Model &m, int level, cudaStream_t s) {
     while (d0 < D) {
         const int nd = (D - d0 >= 3) ? 3 : (D - d0);
         const int wc = (d0 == 0);
-        const bool stream = m.cfg.hist_variant == 0;
+        const bool stream = m.cfg.hist_variant != 1;      // 0: 32 warps per CTA where output_dim == 1; 2: 24 warps (more registers per thread)
         if (stream) {
             // two output dimensions per launch at most: the ring needs the shared memory a third pair of planes would take
             if (nd >= 2) { launch_hist_stream<2, 24, 2>(m, d0, wc, hist, n_sms, s); d0 += 2; }
-            else if (D == 1) { launch_hist_stream<1, 32, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }
+            else if (D == 1 && m.cfg.hist_variant == 0) { launch_hist_stream<1, 32, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }
             else { launch_hist_stream<1, 24, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }      // same item size as the ND = 2 launches
             continue;
         }

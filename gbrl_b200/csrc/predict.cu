@@ -232,14 +232,40 @@ predict_tiles_kernel(PredictParams P, TileLayout L, int TC, int n_trees_total, i
                     if (t < P.start_tree || t >= P.stop_tree) continue;
                     const int dj = dep[j];
                     int li0 = 0, li1 = 0;
-                    for (int k = 0; k < dj; ++k) {                                           // predictor.cpp:248-252, most significant bit first
-                        const float *xr = xT + fi[j * md + k] * PT_XS + lane;
-                        const float th = fv[j * md + k];
-                        li0 = (li0 << 1) | (xr[0] > th ? 1 : 0);
-                        li1 = (li1 << 1) | (xr[32] > th ? 1 : 0);
+                    if ((md & 1) == 0) {
+                        // even max_depth: the tree's (feature, threshold) rows are 8-byte aligned -> two levels per broadcast LDS.64
+                        const int2 *fi2 = reinterpret_cast<const int2 *>(fi + j * md);
+                        const float2 *fv2 = reinterpret_cast<const float2 *>(fv + j * md);
+                        for (int k = 0; k < dj; k += 2) {                                    // predictor.cpp:248-252, most significant bit first
+                            const int2 f2 = fi2[k >> 1];
+                            const float2 t2 = fv2[k >> 1];
+                            const float *xa = xT + f2.x * PT_XS + lane;
+                            li0 = (li0 << 1) | (xa[0] > t2.x ? 1 : 0);
+                            li1 = (li1 << 1) | (xa[32] > t2.x ? 1 : 0);
+                            if (k + 1 < dj) {
+                                const float *xb = xT + f2.y * PT_XS + lane;
+                                li0 = (li0 << 1) | (xb[0] > t2.y ? 1 : 0);
+                                li1 = (li1 << 1) | (xb[32] > t2.y ? 1 : 0);
+                            }
+                        }
+                    } else {
+                        for (int k = 0; k < dj; ++k) {
+                            const float *xr = xT + fi[j * md + k] * PT_XS + lane;
+                            const float th = fv[j * md + k];
+                            li0 = (li0 << 1) | (xr[0] > th ? 1 : 0);
+                            li1 = (li1 << 1) | (xr[32] > th ? 1 : 0);
+                        }
                     }
                     const float *vb = val + (size_t)(ti[j] - lbase) * D;
                     float *e = E + ((size_t)(j * PT_SUB) * DM) * 32 + lane;
+                    if (DM == 2 && D == 2 && all_const && (reinterpret_cast<uintptr_t>(vb) & 7) == 0) {
+                        // both outputs of a leaf with one 8-byte gather per sub-tile
+                        const float2 v0 = *reinterpret_cast<const float2 *>(vb + (size_t)li0 * 2);
+                        const float2 v1 = *reinterpret_cast<const float2 *>(vb + (size_t)li1 * 2);
+                        e[0] = s_lr[0] * v0.x; e[32] = s_lr[1] * v0.y;
+                        e[2 * 32] = s_lr[0] * v1.x; e[3 * 32] = s_lr[1] * v1.y;
+                        continue;
+                    }
 #pragma unroll
                     for (int d = 0; d < DM; ++d) {
                         float x0 = 0.0f, x1 = 0.0f;

@@ -43,4 +43,58 @@ struct WideParams {
 
 void launch_replay_wide(Model &m, const ReplayParams &R, const StreamParams &S, cudaStream_t s);
 
+#if defined(__CUDACC__)
+// word offset of every item's side-bit plane (8-word groups); items that do not fit -> direct.  One CTA of BT threads.
+template <int BT>
+__device__ __forceinline__ void replay_plan_body(const ReplayParams &P, NodeArrays na, const StreamParams &S) {
+    __shared__ int s_scan[BT];
+    __shared__ long long s_carry;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n_items; i0 += BT) {
+        const int it = i0 + threadIdx.x;
+        int words = 0, md = 1;
+        if (it < n_items) {
+            const ReplayItem item = P.items[it];
+            if (item.cand >= 0 || S.wide) { words = ((na.seg_len[item.node] + 255) >> 8) << 3; md = 0; }   // 8-word groups
+        }
+        s_scan[threadIdx.x] = words;
+        __syncthreads();
+        for (int o = 1; o < BT; o <<= 1) {
+            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const long long carry = s_carry;
+        const long long excl = carry + s_scan[threadIdx.x] - words;
+        if (it < n_items) {
+            if (md == 0 && excl + words > S.cap_words) md = 2;
+            // direct items keep their (unused) slot in the prefix so that the prefix stays monotone
+            S.woff[it] = (int)min(excl, S.cap_words);
+            S.mode[it] = md;
+            S.nright[it] = 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == BT - 1) s_carry = carry + s_scan[BT - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S.woff[n_items] = (int)min(s_carry, S.cap_words);
+}
+
+// order-space copy of build_grads for the rows of every node that has replay items (grid-stride)
+__device__ __forceinline__ void replay_gather_body(const ReplayParams &P, NodeArrays na, const StreamParams &S) {
+    if (P.ctl->n_replay <= 0) return;
+    const int D = P.D;
+    const bool all = S.oblivious != 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S.N; k += gridDim.x * blockDim.x) {
+        const int row = P.order[k];
+        if (!all && na.rep_count[S.nid[row]] <= 0) continue;
+        for (int d = 0; d < D; ++d) S.G[(size_t)k * D + d] = P.bg[(size_t)row * D + d];
+    }
+}
+#endif
+
+
 }  // namespace gb

@@ -13,8 +13,11 @@
 // Cosine needs a second round (tabs + walk) for the mat_vec_dot_sum chains once the side means are known.
 #include "replay.cuh"
 #include "chain.cuh"
+#include <cooperative_groups.h>
 
 namespace gb {
+
+namespace cg = cooperative_groups;
 
 constexpr int GROUP_ROWS = 256;
 constexpr float TAG_EMPTY = -1.0f;     // tag of a group in which the chain has no element: applicable to any running sum
@@ -28,7 +31,7 @@ __device__ __forceinline__ double shfl_xor_d(double v, int m) {
 // A warp owns a contiguous range of 8-word groups (256 rows each) of the planes: the item of the first group is
 // found by one binary search, after that the item index only moves forward.
 template <int D>
-__global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+__device__ __forceinline__ void wide_bits_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd) {
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
     if (n_items <= 0) return;
     const int lane = threadIdx.x & 31;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArra
 
 // one CTA per item: pred[group][chain] = sum of bsum over the earlier groups of the item
 template <int D>
-__global__ void __launch_bounds__(256) wide_prefix_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+__device__ __forceinline__ void wide_prefix_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd) {
     __shared__ double s_tot[256];
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
     const int t = threadIdx.x;
@@ -203,7 +206,7 @@ __device__ __forceinline__ void chain_elems(const float (&v)[8 * D], unsigned in
 
 // one warp per group: summaries of all chains of the group for the predicted binade
 template <int D, int PASS>
-__global__ void __launch_bounds__(256) wide_tabs_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+__device__ __forceinline__ void wide_tabs_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd) {
     constexpr int NCH = PASS == 0 ? 2 * D : 2;
     constexpr int KE = PASS == 0 ? 8 : 8 * D;
     const int n_items = min(P.ctl->n_replay, S.replay_cap);
@@ -304,7 +307,7 @@ __device__ __forceinline__ int compose_window(float &acc, const int4 q, float tg
 
 // one CTA per item, warp c walks chain c; then the item's score (L2, or Cosine after PASS 1) / the side means (Cosine, PASS 0)
 template <int D, int PASS>
-__global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd, Ctl *ctl_stats) {
+__device__ __forceinline__ void wide_walk_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd, Ctl *ctl_stats) {
     constexpr int NCH = PASS == 0 ? 2 * D : 2;
     constexpr int KE = PASS == 0 ? 8 : 8 * D;
     __shared__ float s_sum[2 * D];
@@ -412,19 +415,49 @@ __global__ void __launch_bounds__(32 * 2 * D) wide_walk_kernel(ReplayParams P, N
     }
 }
 
+// ---------------------------------------------------------------- one cooperative launch for the whole replay tier
+// Most levels have no replay item at all (C2: 134 of 1449 nodes), and seven launches that find nothing to do still cost
+// ~30 us per level.  All stages run inside ONE cooperative kernel separated by grid-wide barriers: the plan is made by
+// CTA 0, every CTA then reads the item count and an empty level costs one launch and one barrier.
+template <int D>
+__global__ void __launch_bounds__(256) wide_replay_coop_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd, Ctl *ctl_stats, int cosine) {
+    cg::grid_group grid = cg::this_grid();
+    if (blockIdx.x == 0) replay_plan_body<256>(P, na, S);
+    grid.sync();
+    if (P.ctl->n_replay <= 0) return;              // uniform over the grid
+    replay_gather_body(P, na, S);
+    grid.sync();
+    wide_bits_body<D>(P, na, S, Wd);
+    grid.sync();
+    wide_prefix_body<D>(P, na, S, Wd);
+    grid.sync();
+    wide_tabs_body<D, 0>(P, na, S, Wd);
+    grid.sync();
+    wide_walk_body<D, 0>(P, na, S, Wd, ctl_stats);
+    if (cosine) {
+        grid.sync();
+        wide_tabs_body<D, 1>(P, na, S, Wd);
+        grid.sync();
+        wide_walk_body<D, 1>(P, na, S, Wd, ctl_stats);
+    }
+}
+
 template <int D>
 static void launch_wide_d(Model &m, const ReplayParams &R, const StreamParams &S, const WideParams &Wd, cudaStream_t s) {
     Workspace &ws = m.ws;
     Ctl *ctl = ws.ctl.as<Ctl>();
-    const int grid = ws.n_sms * 8;
-    GB_LAUNCH((wide_bits_kernel<D>), grid, 256, 0, s, R, ws.na, S, Wd);
-    GB_LAUNCH((wide_prefix_kernel<D>), ws.n_sms * 4, 256, 0, s, R, ws.na, S, Wd);
-    GB_LAUNCH((wide_tabs_kernel<D, 0>), grid, 256, 0, s, R, ws.na, S, Wd);
-    GB_LAUNCH((wide_walk_kernel<D, 0>), ws.n_sms * 8, 32 * 2 * D, 0, s, R, ws.na, S, Wd, ctl);
-    if (m.cfg.split_score_func != GBRL_B200_SCORE_L2) {
-        GB_LAUNCH((wide_tabs_kernel<D, 1>), grid, 256, 0, s, R, ws.na, S, Wd);
-        GB_LAUNCH((wide_walk_kernel<D, 1>), ws.n_sms * 8, 32 * 2 * D, 0, s, R, ws.na, S, Wd, ctl);
+    static int occ_cache[64] = {0};                 // co-resident CTAs per SM, per device
+    int &occ = occ_cache[m.device & 63];
+    if (!occ) {
+        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wide_replay_coop_kernel<D>, 256, 0));
+        if (occ < 1) occ = 1;
+        if (occ > 8) occ = 8;
     }
+    ReplayParams r = R; StreamParams st = S; WideParams wd = Wd; NodeArrays na = ws.na;
+    int cosine = m.cfg.split_score_func != GBRL_B200_SCORE_L2 ? 1 : 0;
+    void *args[] = {&r, &na, &st, &wd, &ctl, &cosine};
+    GB_CUDA(cudaLaunchCooperativeKernel((void *)wide_replay_coop_kernel<D>, dim3(ws.n_sms * occ), dim3(256), args, 0, s));
+    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 void launch_replay_wide(Model &m, const ReplayParams &R, const StreamParams &S, cudaStream_t s) {

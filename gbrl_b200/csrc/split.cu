@@ -920,53 +920,9 @@ __global__ void __launch_bounds__(512, 1) replay_par_kernel(ReplayParams P, Node
 //   replay_bits_kernel    side bit (x > threshold, node.cpp:339) of every (item, row), 32 rows per word, + right counts
 //   replay_stream_kernel  the chains (chain.cuh) over the streams; same arithmetic as replay_par_kernel
 
-__global__ void __launch_bounds__(1024) replay_plan_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
-    __shared__ int s_scan[1024];
-    __shared__ long long s_carry;
-    const int n_items = min(P.ctl->n_replay, S.replay_cap);
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n_items; i0 += 1024) {
-        const int it = i0 + threadIdx.x;
-        int words = 0, md = 1;
-        if (it < n_items) {
-            const ReplayItem item = P.items[it];
-            if (item.cand >= 0 || S.wide) { words = ((na.seg_len[item.node] + 255) >> 8) << 3; md = 0; }   // 8-word groups
-        }
-        s_scan[threadIdx.x] = words;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
-            __syncthreads();
-            s_scan[threadIdx.x] += v;
-            __syncthreads();
-        }
-        const long long carry = s_carry;
-        const long long excl = carry + s_scan[threadIdx.x] - words;
-        if (it < n_items) {
-            if (md == 0 && excl + words > S.cap_words) md = 2;
-            // direct items keep their (unused) slot in the prefix so that the prefix stays monotone
-            S.woff[it] = (int)min(excl, S.cap_words);
-            S.mode[it] = md;
-            S.nright[it] = 0;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + s_scan[1023];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) S.woff[n_items] = (int)min(s_carry, S.cap_words);
-}
+__global__ void __launch_bounds__(1024) replay_plan_kernel(ReplayParams P, NodeArrays na, StreamParams S) { replay_plan_body<1024>(P, na, S); }
 
-__global__ void __launch_bounds__(256) replay_gather_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
-    if (P.ctl->n_replay <= 0) return;
-    const int D = P.D;
-    const bool all = S.oblivious != 0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S.N; k += gridDim.x * blockDim.x) {
-        const int row = P.order[k];
-        if (!all && na.rep_count[S.nid[row]] <= 0) continue;
-        for (int d = 0; d < D; ++d) S.G[(size_t)k * D + d] = P.bg[(size_t)row * D + d];
-    }
-}
+__global__ void __launch_bounds__(256) replay_gather_kernel(ReplayParams P, NodeArrays na, StreamParams S) { replay_gather_body(P, na, S); }
 
 // one warp per 8-word group (256 rows) of a plane
 __global__ void __launch_bounds__(256) replay_bits_kernel(ReplayParams P, NodeArrays na, StreamParams S) {
@@ -1403,8 +1359,10 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
             S.cap_words = force_direct ? 0 : ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
             S.nid = ws.nid.as<int>();
             S.wide = (D <= 2 && m.cfg.replay_variant == 0) ? 1 : 0;
-            GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
-            GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
+            if (!S.wide) {
+                GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
+                GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
+            }
             if (S.wide) {
                 // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
                 launch_replay_wide(m, R, S, s);
