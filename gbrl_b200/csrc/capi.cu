@@ -113,13 +113,14 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
         // replay streams (split.cu): planes for 64 full-size candidates, i.e. all items of a level unless the near-tie
         // band is unusually crowded (those items are gathered directly by their chain CTA)
         ws.rgrad.ensure(n1 * D * sizeof(float));
-        ws.rbits_words = (long long)((n1 + 255) / 256) * 8 * 64 + 4096;
+        ws.rbits_words = (long long)((n1 + 255) / 256) * 8 * 64 + 4096 + 256 * 2048;      // + the 32-group alignment slack of up to 2048 items
         ws.rbits.ensure((size_t)ws.rbits_words * sizeof(unsigned int));
         ws.rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
         if (D <= 2) {
             ws.rwide_groups = ws.rbits_words / 8 + 1;
             ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)) + sizeof(int)) +
-                            (size_t)ws.replay_cap * 8 * sizeof(float));
+                            (size_t)ws.replay_cap * 8 * sizeof(float) + 64 +
+                            ((size_t)ws.rwide_groups / 32 + 2) * 2 * D * (sizeof(int4) + sizeof(float)));      // + window tables
         }
     }
     // node arrays carved from one allocation

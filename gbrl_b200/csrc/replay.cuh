@@ -38,6 +38,8 @@ struct WideParams {
     float *tag;                // [groups][2D] the binade (inv_u) the summary was computed for, 0 = none
     int *gitem;                // [groups] item of the group
     float *fin;                // [items][8] pass 0 -> pass 1: means (left D, right D), ln, rn
+    int4 *wtab;                // [windows][2D] composite table of a window of 32 groups (replay_wide.cu wide_wtabs_body)
+    float *wtag;               // [windows][2D] its binade, TAG_EMPTY, or 0 = no composite
     long long cap_groups;
 };
 
@@ -58,6 +60,7 @@ __device__ __forceinline__ void replay_plan_body(const ReplayParams &P, NodeArra
         if (it < n_items) {
             const ReplayItem item = P.items[it];
             if (item.cand >= 0 || S.wide) { words = ((na.seg_len[item.node] + 255) >> 8) << 3; md = 0; }   // 8-word groups
+            if (S.wide) words = (words + 255) & ~255;     // planes start on 32-group boundaries (window tables, replay_wide.cu)
         }
         s_scan[threadIdx.x] = words;
         __syncthreads();

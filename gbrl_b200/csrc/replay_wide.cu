@@ -20,6 +20,7 @@ namespace gb {
 namespace cg = cooperative_groups;
 
 constexpr int GROUP_ROWS = 256;
+constexpr int WIN_MIN_GROUPS = 64;     // chains of at least this many groups are walked through window tables first
 constexpr float TAG_EMPTY = -1.0f;     // tag of a group in which the chain has no element: applicable to any running sum
 
 __device__ __forceinline__ double shfl_xor_d(double v, int m) {
@@ -259,6 +260,72 @@ __device__ __forceinline__ void wide_tabs_body(const ReplayParams &P, NodeArrays
     }
 }
 
+// Second level of the summaries: one warp per (window of 32 groups, chain) composes the window's group tables into ONE table
+// (tables compose associatively, chain.cuh) when all its groups were summarised for the same binade.  The chain warp
+// then walks window tables 32 at a time (1024 groups = 262 144 rows per scan) and descends into a window only where the
+// composite is not applicable to the actual running sum.  Items are laid out on 32-group boundaries (replay_plan_body).
+template <int D, int PASS>
+__device__ __forceinline__ void wide_wtabs_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd) {
+    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    const unsigned int full = 0xffffffffu;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (n_items <= 0) return;
+    if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
+    const int lane = threadIdx.x & 31;
+    const int total_windows = (S.woff[n_items] >> 3) >> 5;
+    const long long units = (long long)total_windows * NCH;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long uidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; uidx < units; uidx += warps) {
+        const int gw = (int)(uidx / NCH), c = (int)(uidx - (long long)gw * NCH);
+        const int it = Wd.gitem[(size_t)gw * 32];
+        if (it < 0) continue;
+        const int n = na.seg_len[P.items[it].node];
+        const int ng = (n + GROUP_ROWS - 1) / GROUP_ROWS;
+        if (ng < WIN_MIN_GROUPS) continue;                                  // short chains are walked at group level only
+        const int lw = gw - ((S.woff[it] >> 3) >> 5);
+        const int cnt = min(32, ng - lw * 32);
+        if (cnt <= 0) continue;
+        int4 q = make_int4(0, 0, 0, 0);
+        float tg = TAG_EMPTY;
+        if (lane < cnt) { q = Wd.tab[((size_t)gw * 32 + lane) * 2 * D + c]; tg = Wd.tag[((size_t)gw * 32 + lane) * 2 * D + c]; }
+        // common binade of the non-empty groups (0: mixed / none -> the window has no composite)
+        const unsigned int tb = __float_as_uint(tg);
+        const bool nonempty = tg != TAG_EMPTY;
+        const unsigned int ne_mask = __ballot_sync(full, nonempty);
+        float wtag = TAG_EMPTY;
+        int4 out = make_int4(0, 0, 0, 0);
+        if (ne_mask) {
+            const unsigned int t0 = __shfl_sync(full, tb, __ffs(ne_mask) - 1);
+            const bool same = !nonempty || tb == t0;
+            wtag = (__all_sync(full, same) && __uint_as_float(t0) != 0.0f) ? __uint_as_float(t0) : 0.0f;
+            if (wtag != 0.0f) {
+                int i0 = nonempty ? q.x : 0, i1 = nonempty ? q.y : 0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int g0 = __shfl_up_sync(full, i0, off), g1 = __shfl_up_sync(full, i1, off);
+                    if (lane >= off) {
+                        const int n0 = g0 + ((g0 & 1) ? i1 : i0);
+                        const int n1 = g1 + (((g1 + 1) & 1) ? i1 : i0);
+                        i0 = n0; i1 = n1;
+                    }
+                }
+                int e0 = __shfl_up_sync(full, i0, 1);
+                if (lane == 0) e0 = 0;
+                // min / max prefix along the even-parity path (the odd path differs by at most 1, as inside a group)
+                long long mn = nonempty ? (long long)e0 + q.z : 0, mx = nonempty ? (long long)e0 + q.w : 0;
+                mn = max(mn, (long long)-seq::BAD); mx = min(mx, (long long)seq::BAD);
+                int mni = (int)mn, mxi = (int)mx;
+                mni = __reduce_min_sync(full, mni); mxi = __reduce_max_sync(full, mxi);
+                // increments beyond +-2^29 cannot be applied inside a binade anyway: refuse the composite instead of overflowing
+                const bool small = abs(q.x) < (1 << 24) && abs(q.y) < (1 << 24);
+                if (!__all_sync(full, small)) wtag = 0.0f;
+                out = make_int4(__shfl_sync(full, i0, 31), __shfl_sync(full, i1, 31), mni - 1, mxi + 1);
+            }
+        }
+        if (lane == 0) { Wd.wtab[(size_t)gw * 2 * D + c] = out; Wd.wtag[(size_t)gw * 2 * D + c] = wtag; }
+    }
+}
+
 // composes the longest applicable prefix of a window of 32 groups (lane = group); returns how many were consumed
 __device__ __forceinline__ int compose_window(float &acc, const int4 q, float tg, bool in_range, int first) {
     const unsigned int full = 0xffffffffu;
@@ -333,38 +400,65 @@ __device__ __forceinline__ void wide_walk_body(const ReplayParams &P, NodeArrays
         if (warp < NCH) {
             const int c = warp;
             float acc = 0.0f;
-            int4 qnx = make_int4(0, 0, 0, 0);              // the next window's summaries / tags, loaded a window ahead
-            float tgnx = 0.0f;
-            if (lane < ng) { qnx = Wd.tab[(base + lane) * 2 * D + c]; tgnx = Wd.tag[(base + lane) * 2 * D + c]; }
+            // group-level walk of the windows [wa, wb) of this chain (window = 32 groups, lane = group)
+            auto walk_groups = [&](int wa, int wb) {
+                int4 qnx = make_int4(0, 0, 0, 0);          // the next window's summaries / tags, loaded a window ahead
+                float tgnx = 0.0f;
+                if (wa * 32 + lane < ng) { qnx = Wd.tab[(base + wa * 32 + lane) * 2 * D + c]; tgnx = Wd.tag[(base + wa * 32 + lane) * 2 * D + c]; }
 #pragma unroll 1
-            for (int w0 = 0; w0 < ng; w0 += 32) {          // window of 32 groups, lane = group
-                const bool in_range = w0 + lane < ng;
-                const int wn = min(32, ng - w0);
-                const int4 q = qnx;
-                const float tg = tgnx;
-                if (w0 + 32 + lane < ng) { qnx = Wd.tab[(base + w0 + 32 + lane) * 2 * D + c]; tgnx = Wd.tag[(base + w0 + 32 + lane) * 2 * D + c]; }
-                int first = 0;
-                float vn[8 * D];                           // rows of the group after a failed one, fetched while that one is advanced
-                unsigned int mbn = 0u;
-                int have = -1;                             // group (window-relative) whose rows vn holds
+                for (int w0 = wa * 32; w0 < ng && w0 < wb * 32; w0 += 32) {
+                    const bool in_range = w0 + lane < ng;
+                    const int wn = min(32, ng - w0);
+                    const int4 q = qnx;
+                    const float tg = tgnx;
+                    if (w0 + 32 + lane < ng && w0 + 32 < wb * 32) { qnx = Wd.tab[(base + w0 + 32 + lane) * 2 * D + c]; tgnx = Wd.tag[(base + w0 + 32 + lane) * 2 * D + c]; }
+                    int first = 0;
+                    float vn[8 * D];                       // rows of the group after a failed one, fetched while that one is advanced
+                    unsigned int mbn = 0u;
+                    int have = -1;                         // group (window-relative) whose rows vn holds
 #pragma unroll 1
-                while (first < wn) {
-                    const int take = compose_window(acc, q, tg, in_range, first);
-                    n_fast += take;
-                    first += take;
-                    if (first >= wn) break;
-                    // this group is in another binade than predicted, or the sum leaves its binade inside it
-                    float v[8 * D], x[KE];
-                    unsigned int mb;
-                    if (have == first) {
+                    while (first < wn) {
+                        const int take = compose_window(acc, q, tg, in_range, first);
+                        n_fast += take;
+                        first += take;
+                        if (first >= wn) break;
+                        // this group is in another binade than predicted, or the sum leaves its binade inside it
+                        float v[8 * D], x[KE];
+                        unsigned int mb;
+                        if (have == first) {
 #pragma unroll
-                        for (int j = 0; j < 8 * D; ++j) v[j] = vn[j];
-                        mb = mbn;
-                    } else group_rows<D>(G, W, n, w0 + first, v, mb);
-                    if (w0 + first + 1 < ng) { group_rows<D>(G, W, n, w0 + first + 1, vn, mbn); have = first + 1; }
-                    chain_elems<D, PASS>(v, mb, c, s_mean, x);
-                    acc = seq::warp_seq_block<KE>(acc, x, s_wbuf[c], n_seq);
-                    ++n_slow; ++first;
+                            for (int j = 0; j < 8 * D; ++j) v[j] = vn[j];
+                            mb = mbn;
+                        } else group_rows<D>(G, W, n, w0 + first, v, mb);
+                        if (w0 + first + 1 < ng) { group_rows<D>(G, W, n, w0 + first + 1, vn, mbn); have = first + 1; }
+                        chain_elems<D, PASS>(v, mb, c, s_mean, x);
+                        acc = seq::warp_seq_block<KE>(acc, x, s_wbuf[c], n_seq);
+                        ++n_slow; ++first;
+                    }
+                }
+            };
+            const int nw = (ng + 31) >> 5;                 // windows of this chain
+            if (ng < WIN_MIN_GROUPS) walk_groups(0, nw);
+            else {
+                // window tables first: 32 windows (1024 groups) per scan; a window whose composite does not apply is walked at group level
+                const size_t wbase = base >> 5;
+#pragma unroll 1
+                for (int s0w = 0; s0w < nw; s0w += 32) {   // super-window, lane = window
+                    const bool in_range = s0w + lane < nw;
+                    const int sn = min(32, nw - s0w);
+                    int4 q = make_int4(0, 0, 0, 0);
+                    float tg = 0.0f;
+                    if (in_range) { q = Wd.wtab[(wbase + s0w + lane) * 2 * D + c]; tg = Wd.wtag[(wbase + s0w + lane) * 2 * D + c]; }
+                    int first = 0;
+#pragma unroll 1
+                    while (first < sn) {
+                        const int take = compose_window(acc, q, tg, in_range, first);
+                        n_fast += take * 32;
+                        first += take;
+                        if (first >= sn) break;
+                        walk_groups(s0w + first, s0w + first + 1);
+                        ++first;
+                    }
                 }
             }
             if (lane == 0) s_sum[c] = acc;
@@ -433,10 +527,14 @@ __global__ void __launch_bounds__(256) wide_replay_coop_kernel(ReplayParams P, N
     grid.sync();
     wide_tabs_body<D, 0>(P, na, S, Wd);
     grid.sync();
+    wide_wtabs_body<D, 0>(P, na, S, Wd);
+    grid.sync();
     wide_walk_body<D, 0>(P, na, S, Wd, ctl_stats);
     if (cosine) {
         grid.sync();
         wide_tabs_body<D, 1>(P, na, S, Wd);
+        grid.sync();
+        wide_wtabs_body<D, 1>(P, na, S, Wd);
         grid.sync();
         wide_walk_body<D, 1>(P, na, S, Wd, ctl_stats);
     }
@@ -470,7 +568,10 @@ void launch_replay_wide(Model &m, const ReplayParams &R, const StreamParams &S, 
     Wd.pred = reinterpret_cast<float *>(p); p += ng * D2 * sizeof(float);
     Wd.tag = reinterpret_cast<float *>(p); p += ng * D2 * sizeof(float);
     Wd.gitem = reinterpret_cast<int *>(p); p += ng * sizeof(int);
-    Wd.fin = reinterpret_cast<float *>(p);
+    Wd.fin = reinterpret_cast<float *>(p); p += (size_t)ws.replay_cap * 8 * sizeof(float);
+    p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15);
+    Wd.wtab = reinterpret_cast<int4 *>(p); p += (ng / 32 + 2) * D2 * sizeof(int4);
+    Wd.wtag = reinterpret_cast<float *>(p);
     Wd.cap_groups = (long long)ng;
     if (ws.D == 1) launch_wide_d<1>(m, R, S, Wd, s);
     else launch_wide_d<2>(m, R, S, Wd, s);
