@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(1024) plan_level_kernel(NodeArrays na, Ctl *ct
 // rows per work item: the streaming kernel wants NWARPS * 64 (two 32-row blocks per warp), the per-item kernel 8192
 int hist_item_rows(const Model &m) {
     if (m.cfg.hist_variant == 1) return ITEM_ROWS;
-    return (m.cfg.output_dim == 1 && m.cfg.hist_variant == 0) ? 32 * 64 : 24 * 64;
+    return (m.cfg.output_dim == 1 && m.cfg.hist_variant == 2) ? 32 * 64 : 24 * 64;
 }
 
 PlanParams plan_params(const Model &m) {
@@ -432,11 +432,11 @@ void launch_histogram(Model &m, int level, cudaStream_t s) {
     while (d0 < D) {
         const int nd = (D - d0 >= 3) ? 3 : (D - d0);
         const int wc = (d0 == 0);
-        const bool stream = m.cfg.hist_variant != 1;      // 0: 32 warps per CTA where output_dim == 1; 2: 24 warps (more registers per thread)
+        const bool stream = m.cfg.hist_variant != 1;      // 0: 24 warps per CTA (more registers per thread; measured faster); 2: 32 warps where output_dim == 1
         if (stream) {
             // two output dimensions per launch at most: the ring needs the shared memory a third pair of planes would take
             if (nd >= 2) { launch_hist_stream<2, 24, 2>(m, d0, wc, hist, n_sms, s); d0 += 2; }
-            else if (D == 1 && m.cfg.hist_variant == 0) { launch_hist_stream<1, 32, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }
+            else if (D == 1 && m.cfg.hist_variant == 2) { launch_hist_stream<1, 32, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }
             else { launch_hist_stream<1, 24, 3>(m, d0, wc, hist, n_sms, s); d0 += 1; }      // same item size as the ND = 2 launches
             continue;
         }

@@ -13,11 +13,8 @@
 // Cosine needs a second round (tabs + walk) for the mat_vec_dot_sum chains once the side means are known.
 #include "replay.cuh"
 #include "chain.cuh"
-#include <cooperative_groups.h>
 
 namespace gb {
-
-namespace cg = cooperative_groups;
 
 constexpr int GROUP_ROWS = 256;
 constexpr int WIN_MIN_GROUPS = 64;     // chains of at least this many groups are walked through window tables first
@@ -205,58 +202,51 @@ __device__ __forceinline__ void chain_elems(const float (&v)[8 * D], unsigned in
     }
 }
 
-// one warp per group: summaries of all chains of the group for the predicted binade
+// summaries of all chains of group g for the predicted binade (one warp)
 template <int D, int PASS>
-__device__ __forceinline__ void wide_tabs_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd) {
+__device__ __forceinline__ void tabs_group(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd, int g) {
     constexpr int NCH = PASS == 0 ? 2 * D : 2;
     constexpr int KE = PASS == 0 ? 8 : 8 * D;
-    const int n_items = min(P.ctl->n_replay, S.replay_cap);
-    if (n_items <= 0) return;
-    if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
     const int lane = threadIdx.x & 31;
-    const int total_groups = S.woff[n_items] >> 3;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total_groups; g += warps) {
-        const int it = Wd.gitem[g];
-        if (it < 0) continue;
-        const ReplayItem item = P.items[it];
-        const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
-        const int lg = g - (S.woff[it] >> 3);
-        float v[8 * D];
-        unsigned int mb;
-        group_rows<D>(S.G + (size_t)s0 * D, S.bits + S.woff[it], n, lg, v, mb);
-        float smean[2 * D];
-        if (PASS == 1) {
+    const int it = Wd.gitem[g];
+    if (it < 0) return;
+    const ReplayItem item = P.items[it];
+    const int s0 = na.seg_start[item.node], n = na.seg_len[item.node];
+    const int lg = g - (S.woff[it] >> 3);
+    float v[8 * D];
+    unsigned int mb;
+    group_rows<D>(S.G + (size_t)s0 * D, S.bits + S.woff[it], n, lg, v, mb);
+    float smean[2 * D];
+    if (PASS == 1) {
 #pragma unroll
-            for (int i = 0; i < 2 * D; ++i) smean[i] = Wd.fin[(size_t)it * 8 + i];
+        for (int i = 0; i < 2 * D; ++i) smean[i] = Wd.fin[(size_t)it * 8 + i];
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        float pr;
+        if (PASS == 0) pr = Wd.pred[(size_t)g * 2 * D + c];
+        else {
+            pr = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) pr += smean[c * D + d] * Wd.pred[(size_t)g * 2 * D + c * D + d];
         }
+        float inv_u, u;
+        const bool ok = seq::epoch_of(pr, inv_u, u);
+        float x[KE];
+        chain_elems<D, PASS>(v, mb, c, smean, x);
+        bool nz = false;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            float pr;
-            if (PASS == 0) pr = Wd.pred[(size_t)g * 2 * D + c];
-            else {
-                pr = 0.0f;
-#pragma unroll
-                for (int d = 0; d < D; ++d) pr += smean[c * D + d] * Wd.pred[(size_t)g * 2 * D + c * D + d];
-            }
-            float inv_u, u;
-            const bool ok = seq::epoch_of(pr, inv_u, u);
-            float x[KE];
-            chain_elems<D, PASS>(v, mb, c, smean, x);
-            bool nz = false;
-#pragma unroll
-            for (int i = 0; i < KE; ++i) nz |= (x[i] != 0.0f) || (x[i] != x[i]);
-            const bool empty = !__any_sync(0xffffffffu, nz);          // the chain has no (non-zero) element in this group
-            float tagv = ok ? inv_u : 0.0f;
-            if (empty) {
-                tagv = TAG_EMPTY;
-                if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(0, 0, 0, 0);
-            } else if (ok) {
-                const seq::Tab tb = seq::warp_summarize<KE>(x, inv_u);
-                if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
-            }
-            if (lane == 0) Wd.tag[(size_t)g * 2 * D + c] = tagv;
+        for (int i = 0; i < KE; ++i) nz |= (x[i] != 0.0f) || (x[i] != x[i]);
+        const bool empty = !__any_sync(0xffffffffu, nz);          // the chain has no (non-zero) element in this group
+        float tagv = ok ? inv_u : 0.0f;
+        if (empty) {
+            tagv = TAG_EMPTY;
+            if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(0, 0, 0, 0);
+        } else if (ok) {
+            const seq::Tab tb = seq::warp_summarize<KE>(x, inv_u);
+            if (lane == 0) Wd.tab[(size_t)g * 2 * D + c] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
         }
+        if (lane == 0) Wd.tag[(size_t)g * 2 * D + c] = tagv;
     }
 }
 
@@ -265,26 +255,18 @@ __device__ __forceinline__ void wide_tabs_body(const ReplayParams &P, NodeArrays
 // then walks window tables 32 at a time (1024 groups = 262 144 rows per scan) and descends into a window only where the
 // composite is not applicable to the actual running sum.  Items are laid out on 32-group boundaries (replay_plan_body).
 template <int D, int PASS>
-__device__ __forceinline__ void wide_wtabs_body(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd) {
-    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+__device__ __forceinline__ void wtabs_window(const ReplayParams &P, NodeArrays na, const StreamParams &S, const WideParams &Wd, int gw, int c) {
     const unsigned int full = 0xffffffffu;
-    const int n_items = min(P.ctl->n_replay, S.replay_cap);
-    if (n_items <= 0) return;
-    if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
     const int lane = threadIdx.x & 31;
-    const int total_windows = (S.woff[n_items] >> 3) >> 5;
-    const long long units = (long long)total_windows * NCH;
-    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long uidx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; uidx < units; uidx += warps) {
-        const int gw = (int)(uidx / NCH), c = (int)(uidx - (long long)gw * NCH);
+    {
         const int it = Wd.gitem[(size_t)gw * 32];
-        if (it < 0) continue;
+        if (it < 0) return;
         const int n = na.seg_len[P.items[it].node];
         const int ng = (n + GROUP_ROWS - 1) / GROUP_ROWS;
-        if (ng < WIN_MIN_GROUPS) continue;                                  // short chains are walked at group level only
+        if (ng < WIN_MIN_GROUPS) return;                                    // short chains are walked at group level only
         const int lw = gw - ((S.woff[it] >> 3) >> 5);
         const int cnt = min(32, ng - lw * 32);
-        if (cnt <= 0) continue;
+        if (cnt <= 0) return;
         int4 q = make_int4(0, 0, 0, 0);
         float tg = TAG_EMPTY;
         if (lane < cnt) { q = Wd.tab[((size_t)gw * 32 + lane) * 2 * D + c]; tg = Wd.tag[((size_t)gw * 32 + lane) * 2 * D + c]; }
@@ -509,53 +491,49 @@ __device__ __forceinline__ void wide_walk_body(const ReplayParams &P, NodeArrays
     }
 }
 
-// ---------------------------------------------------------------- one cooperative launch for the whole replay tier
-// Most levels have no replay item at all (C2: 134 of 1449 nodes), and seven launches that find nothing to do still cost
-// ~30 us per level.  All stages run inside ONE cooperative kernel separated by grid-wide barriers: the plan is made by
-// CTA 0, every CTA then reads the item count and an empty level costs one launch and one barrier.
+// ---------------------------------------------------------------- kernels
+// (One cooperative launch with grid-wide barriers between the stages was measured too: C2 select_replay 0.59 -> 0.96 ms --
+//  a barrier over n_sms x occupancy CTAs costs more than the back-to-back launches it replaces.  profiles/README.md.)
 template <int D>
-__global__ void __launch_bounds__(256) wide_replay_coop_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd, Ctl *ctl_stats, int cosine) {
-    cg::grid_group grid = cg::this_grid();
-    if (blockIdx.x == 0) replay_plan_body<256>(P, na, S);
-    grid.sync();
-    if (P.ctl->n_replay <= 0) return;              // uniform over the grid
-    replay_gather_body(P, na, S);
-    grid.sync();
-    wide_bits_body<D>(P, na, S, Wd);
-    grid.sync();
-    wide_prefix_body<D>(P, na, S, Wd);
-    grid.sync();
-    wide_tabs_body<D, 0>(P, na, S, Wd);
-    grid.sync();
-    wide_wtabs_body<D, 0>(P, na, S, Wd);
-    grid.sync();
-    wide_walk_body<D, 0>(P, na, S, Wd, ctl_stats);
-    if (cosine) {
-        grid.sync();
-        wide_tabs_body<D, 1>(P, na, S, Wd);
-        grid.sync();
-        wide_wtabs_body<D, 1>(P, na, S, Wd);
-        grid.sync();
-        wide_walk_body<D, 1>(P, na, S, Wd, ctl_stats);
+__global__ void __launch_bounds__(256) wide_bits_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) { wide_bits_body<D>(P, na, S, Wd); }
+template <int D>
+__global__ void __launch_bounds__(256) wide_prefix_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) { wide_prefix_body<D>(P, na, S, Wd); }
+
+// one CTA per window of 32 groups: 8 warps x 4 groups of summaries, then one warp per chain composes the window's table
+template <int D, int PASS>
+__global__ void __launch_bounds__(256) wide_tabs_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd) {
+    constexpr int NCH = PASS == 0 ? 2 * D : 2;
+    const int n_items = min(P.ctl->n_replay, S.replay_cap);
+    if (n_items <= 0) return;
+    if (PASS == 1 && P.score_func == GBRL_B200_SCORE_L2) return;
+    const int warp = threadIdx.x >> 5;
+    const int total_windows = (S.woff[n_items] >> 3) >> 5;      // planes are padded to whole windows (replay_plan_body)
+    for (int gw = blockIdx.x; gw < total_windows; gw += gridDim.x) {
+#pragma unroll 1
+        for (int gi = warp; gi < 32; gi += 8) tabs_group<D, PASS>(P, na, S, Wd, gw * 32 + gi);
+        __syncthreads();                                        // the window's group tables are visible to the CTA
+        if (warp < NCH) wtabs_window<D, PASS>(P, na, S, Wd, gw, warp);
     }
+}
+
+template <int D, int PASS>
+__global__ void __launch_bounds__(256) wide_walk_kernel(ReplayParams P, NodeArrays na, StreamParams S, WideParams Wd, Ctl *ctl_stats) {
+    wide_walk_body<D, PASS>(P, na, S, Wd, ctl_stats);
 }
 
 template <int D>
 static void launch_wide_d(Model &m, const ReplayParams &R, const StreamParams &S, const WideParams &Wd, cudaStream_t s) {
     Workspace &ws = m.ws;
     Ctl *ctl = ws.ctl.as<Ctl>();
-    static int occ_cache[64] = {0};                 // co-resident CTAs per SM, per device
-    int &occ = occ_cache[m.device & 63];
-    if (!occ) {
-        GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wide_replay_coop_kernel<D>, 256, 0));
-        if (occ < 1) occ = 1;
-        if (occ > 8) occ = 8;
+    const int grid = ws.n_sms * 8;
+    GB_LAUNCH((wide_bits_kernel<D>), grid, 256, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_prefix_kernel<D>), ws.n_sms, 256, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_tabs_kernel<D, 0>), grid, 256, 0, s, R, ws.na, S, Wd);
+    GB_LAUNCH((wide_walk_kernel<D, 0>), ws.n_sms * 2, 256, 0, s, R, ws.na, S, Wd, ctl);
+    if (m.cfg.split_score_func != GBRL_B200_SCORE_L2) {
+        GB_LAUNCH((wide_tabs_kernel<D, 1>), grid, 256, 0, s, R, ws.na, S, Wd);
+        GB_LAUNCH((wide_walk_kernel<D, 1>), ws.n_sms * 2, 256, 0, s, R, ws.na, S, Wd, ctl);
     }
-    ReplayParams r = R; StreamParams st = S; WideParams wd = Wd; NodeArrays na = ws.na;
-    int cosine = m.cfg.split_score_func != GBRL_B200_SCORE_L2 ? 1 : 0;
-    void *args[] = {&r, &na, &st, &wd, &ctl, &cosine};
-    GB_CUDA(cudaLaunchCooperativeKernel((void *)wide_replay_coop_kernel<D>, dim3(ws.n_sms * occ), dim3(256), args, 0, s));
-    g_kernel_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
 void launch_replay_wide(Model &m, const ReplayParams &R, const StreamParams &S, cudaStream_t s) {

@@ -1359,10 +1359,8 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
             S.cap_words = force_direct ? 0 : ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
             S.nid = ws.nid.as<int>();
             S.wide = (D <= 2 && m.cfg.replay_variant == 0) ? 1 : 0;
-            if (!S.wide) {
-                GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
-                GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
-            }
+            GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
+            GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
             if (S.wide) {
                 // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
                 launch_replay_wide(m, R, S, s);

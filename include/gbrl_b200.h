@@ -57,7 +57,8 @@ typedef struct {
                                arg-max only */
     float band_kappa;       /* band = kappa * 2^-24 * sqrt(n_node) * |score|; <=0 -> default 6 */
     int use_subtraction;    /* 1: histogram only the smaller child, derive the sibling from the parent */
-    int hist_variant;       /* 0: streaming histogram kernel (cp.async row ring, carried shared histogram); 1: per-item kernel */
+    int hist_variant;       /* 0: streaming histogram kernel (cp.async row ring, carried shared histogram); 1: per-item kernel;
+                               2: streaming kernel with 32-warp CTAs for output_dim == 1 (measured slower than the 24-warp default) */
     int replay_variant;     /* 0: replay chains spread over the whole GPU where output_dim <= 2; 1: one CTA per replay item */
 } gbrl_b200_config;
 
