@@ -545,13 +545,13 @@ def bench_fit(wl, args, K, W, rank, world, local, with_e2e=True, with_exact=True
             "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
                        "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"],
                        "chain_blocks_fast": stats["chain_blocks_fast"], "chain_blocks_slow": stats["chain_blocks_slow"],
-                       "chain_lanes_seq": stats["chain_lanes_seq"]}}
+                       "chain_lanes_seq": stats["chain_lanes_seq"], "flips": stats["replay_flips"]}}
 
 
 def compact(d):
     """The part of a workload's line that is kept under extra_workloads."""
     keep = ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches",
-            "kernel_ms_per_step", "ensemble_sha", "tree_walks_per_s", "issue_bound", "exact_tier_only")
+            "kernel_ms_per_step", "ensemble_sha", "tree_walks_per_s", "issue_bound", "exact_tier_only", "replay")
     return {k: d[k] for k in keep if k in d and d[k] is not None}
 
 

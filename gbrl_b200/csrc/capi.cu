@@ -154,7 +154,7 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
     m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
     m.hist_rows = h.stat_hist_rows;
-    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow; m.chain_seq = h.stat_chain_seq; m.chain_err = h.stat_chain_err;
+    m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow; m.chain_seq = h.stat_chain_seq; m.replay_flips = h.stat_replay_flips;
     m.max_noise = __builtin_bit_cast(float, h.stat_max_noise);
 }
 
@@ -631,7 +631,7 @@ int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
     o->n_leaves = m.ens.n_leaves; o->iteration = m.iteration;
     o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
     o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated; o->max_noise_ratio = m.max_noise;
-    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow; o->chain_lanes_seq = m.chain_seq; o->chain_errors = m.chain_err;
+    o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow; o->chain_lanes_seq = m.chain_seq; o->replay_flips = m.replay_flips;
     API_END
 }
 

@@ -64,7 +64,7 @@ struct Ctl {
     unsigned int stat_max_noise;   // float bits: max over replayed candidates of |replayed - exact| / (2^-24 sqrt(n) |score|)
     long long stat_replay_items, stat_replay_nodes, stat_nodes_evaluated, stat_replay_overflow, stat_hist_rows;
     long long stat_chain_fast, stat_chain_slow, stat_chain_seq;   // chain groups applied from their record / run sequentially; lanes run sequentially
-    long long stat_chain_err;   // internal inconsistencies of the chain evaluator (must stay 0; directly after the three counters above)
+    long long stat_replay_flips;   // split decisions in which the replayed arg-max differs from the exact-tier arg-max
 };
 
 // per-node arrays, heap indexed, MAXN = 2^(max_depth+1)-1 entries each
@@ -140,7 +140,7 @@ struct Model {
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
     // statistics
-    long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0, chain_fast = 0, chain_slow = 0, chain_seq = 0, chain_err = 0;
+    long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0, chain_fast = 0, chain_slow = 0, chain_seq = 0, replay_flips = 0;
     bool have_candidates = false;
     long long hist_rows = 0;          // rows scanned by the histogram kernel (read back from Ctl)
     float max_noise = 0.0f;           // see Ctl::stat_max_noise

@@ -1209,7 +1209,10 @@ __device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) 
             if (better(og, oi, bg_, bi)) { bg_ = og; bi = oi; }
         }
         bg_ = __shfl_sync(0xffffffffu, bg_, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
-        if (bi != INT_MAX) { g = bg_; c = bi; }
+        if (bi != INT_MAX) {
+            if (lane == 0 && bi != c) atomicAdd((unsigned long long *)&P.ctl->stat_replay_flips, 1ull);
+            g = bg_; c = bi;
+        }
     }
     // fitter.cpp:357: split iff best_score >= 0 (and the node could be split at all)
     const bool split = (c >= 0) && (g >= 0.0f);
@@ -1244,7 +1247,10 @@ __device__ void decide_oblivious_body(const DecideParams &P, NodeArrays na) {
                 s = s * P.fw[P.rev_map[cand / P.B]];
                 if (s > -INFINITY && better(s, cand, bg_, bi)) { bg_ = s; bi = cand; }
             }
-            if (bi != INT_MAX) c = bi;
+            if (bi != INT_MAX) {
+                if (bi != c) atomicAdd((unsigned long long *)&P.ctl->stat_replay_flips, 1ull);
+                c = bi;
+            }
         }
         s_cand = c;
         P.ctl->obl_depth = (c >= 0) ? P.level + 1 : P.level;

@@ -393,7 +393,7 @@ class GBRL:
         return {"kernel_launches": md.kernel_launches, "replay_items": md.replay_items, "replay_nodes": md.replay_nodes,
                 "replay_overflow": md.replay_overflow, "nodes_evaluated": md.nodes_evaluated, "max_noise_ratio": float(md.max_noise_ratio),
                 "n_trees": md.n_trees, "n_leaves": md.n_leaves, "chain_blocks_fast": md.chain_blocks_fast,
-                "chain_blocks_slow": md.chain_blocks_slow, "chain_lanes_seq": md.chain_lanes_seq, "chain_errors": md.chain_errors}
+                "chain_blocks_slow": md.chain_blocks_slow, "chain_lanes_seq": md.chain_lanes_seq, "replay_flips": md.replay_flips}
 
     def get_ensemble_data(self):
         """binding.cpp:330-390: dict of owning NumPy arrays in the reference layout."""

@@ -77,7 +77,7 @@ typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine 
     long long chain_blocks_fast; /* replay sub-blocks evaluated by the parallel chain evaluator (csrc/chain.cuh) */
     long long chain_blocks_slow; /* replay sub-blocks advanced piecewise (a binade change inside the block) */
     long long chain_lanes_seq;   /* lanes (R rows each) of those blocks that were run as a plain sequential float chain */
-    long long chain_errors;      /* reserved (always 0) */
+    long long replay_flips;      /* split decisions (greedy: nodes, oblivious: levels) in which the near-tie replay changed the exact-tier winner */
 } gbrl_b200_metadata;
 
 const char *gbrl_b200_last_error(void);

@@ -31,6 +31,23 @@ for (n, f, d, depth, score, grow) in ((60000, 96, 2, 5, "cosine", "greedy"), (50
         sharded.step(X, None, g)
     a, b = single.get_ensemble_data(), sharded.get_ensemble_data()
     ok = ok and all(np.array_equal(a[k], b[k]) for k in ("tree_indices", "depths", "feature_indices", "feature_values", "values", "edge_weights"))
+# fit(shuffle=True) with mini-batches: the ranks must draw the SAME permutation (shared seed, capi.cu) -> identical ensembles
+import hashlib  # noqa: E402
+n, f, d = 40000, 40, 1
+X, y = synth(n, f, d, 11)
+m = configure(GBRL(input_dim=f, output_dim=d, policy_dim=d, max_depth=4, n_bins=64, split_score_func="cosine", generator_type="quantile",
+                   batch_size=10000, grow_policy="oblivious", ref_threads=1, device="cuda:%d" % local), f, d)
+m.init_distributed()
+m.fit(X, None, y, 2, True, "MultiRMSE")
+e = m.get_ensemble_data()
+h = hashlib.sha256(b"".join(np.ascontiguousarray(e[k]).tobytes() for k in ("feature_indices", "feature_values", "values"))).digest()[:8]
+mine = torch.tensor([int.from_bytes(h, "little", signed=True)], device="cuda", dtype=torch.int64)
+allh = [torch.zeros_like(mine) for _ in range(world)]
+dist.all_gather(allh, mine)
+same = all(int(t.item()) == int(allh[0].item()) for t in allh)
+if not same:
+    print("rank %d: shuffled fit differs across ranks" % rank)
+ok = ok and same and e["values"].shape[0] > 0
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t)
 if rank == 0 and int(t.item()) == world:
