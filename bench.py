@@ -545,7 +545,8 @@ def bench_fit(wl, args, K, W, rank, world, local, with_e2e=True, with_exact=True
             "replay": {"nodes": stats["replay_nodes"], "items": stats["replay_items"], "overflow": stats["replay_overflow"],
                        "nodes_evaluated": stats["nodes_evaluated"], "max_noise_ratio": stats["max_noise_ratio"],
                        "chain_blocks_fast": stats["chain_blocks_fast"], "chain_blocks_slow": stats["chain_blocks_slow"],
-                       "chain_lanes_seq": stats["chain_lanes_seq"], "flips": stats["replay_flips"]}}
+                       "chain_lanes_seq": stats["chain_lanes_seq"], "flips": stats["replay_flips"],
+                       "speculative_trees": stats["spec_trees"], "levels_rolled_back": stats["spec_rollbacks"]}}
 
 
 def compact(d):
@@ -568,7 +569,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no extra_workloads)")
     ap.add_argument("--no-replay", action="store_true", help="exact-arithmetic arg-max only (see DESIGN.md, near-tie replay)")
     ap.add_argument("--hist-variant", type=int, default=0, help="0 streaming histogram kernel (default), 1 per-item kernel")
-    ap.add_argument("--replay-variant", type=int, default=0, help="0 GPU-wide replay chains where output_dim <= 2 (default), 1 one CTA per replay item")
+    ap.add_argument("--replay-variant", type=int, default=0, help="bit 0: 0 GPU-wide replay chains where output_dim <= 2 (default), 1 one CTA per replay item; bit 1: 0 speculative levels (default), 1 every level waits for its replay")
     ap.add_argument("--kappa", type=float, default=0.0, help="near-tie band width in noise units (0 = engine default)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU work for --impl reference")

@@ -23,7 +23,7 @@ class Metadata(C.Structure):
         "batch_size", "split_score_func", "generator_type", "grow_policy", "verbose", "n_num_features",
         "n_cat_features", "n_trees", "n_leaves", "iteration")] + [(n, C.c_longlong) for n in (
             "kernel_launches", "replay_items", "replay_nodes", "replay_overflow", "nodes_evaluated")] + [("max_noise_ratio", C.c_float)] + [
-                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow", "chain_lanes_seq", "replay_flips")]
+                (n, C.c_longlong) for n in ("chain_blocks_fast", "chain_blocks_slow", "chain_lanes_seq", "replay_flips", "spec_trees", "spec_rollbacks")]
 
 
 # every symbol include/gbrl_b200.h declares (tests check that the library exports all of them)

@@ -78,6 +78,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     ws.tile_hi = (int)((long long)ws.nT * (tg + 1) / gt);
     const size_t n1 = (size_t)(N > 0 ? N : 1);
     ws.order[0].ensure(n1 * sizeof(int)); ws.order[1].ensure(n1 * sizeof(int));
+    ws.order_p[0] = ws.order[0].as<int>(); ws.order_p[1] = ws.order[1].as<int>();
     ws.nid.ensure(n1 * sizeof(int)); ws.rflag.ensure(n1 * sizeof(uint16_t) + 16);
     {   // chunk totals / prefixes of the partition + its "CTAs done" counter (kept zero between launches)
         const int cap = ceil_div((int)n1, 2048) + 1;
@@ -90,6 +91,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     const int lv = md > 0 ? md - 1 : 0;
     const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + D) * sizeof(long long);
     ws.hist[0].ensure(slot_bytes << lv); ws.hist[1].ensure(slot_bytes << lv);
+    ws.hist_p[0] = ws.hist[0].as<long long>(); ws.hist_p[1] = ws.hist[1].as<long long>();
     const size_t C = (size_t)F * B;
     ws.scores.ensure((C << lv) * sizeof(float));
     ws.cand_flags.ensure(C << lv);
@@ -107,20 +109,54 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     ws.items.ensure((size_t)ws.items_cap * sizeof(Item));
     ws.replay_cap = 1 << 18;
     if ((size_t)ws.replay_cap < 4 * ((size_t)1 << md)) ws.replay_cap = 4 << md;
-    ws.replay.ensure((size_t)ws.replay_cap * (sizeof(ReplayItem) + sizeof(int)));
-    ws.replay_scores.ensure((size_t)ws.replay_cap * sizeof(float));
-    if (m.cfg.tie_replay && D <= 4) {
-        // replay streams (split.cu): planes for 64 full-size candidates, i.e. all items of a level unless the near-tie
-        // band is unusually crowded (those items are gathered directly by their chain CTA)
-        ws.rgrad.ensure(n1 * D * sizeof(float));
-        ws.rbits_words = (long long)((n1 + 255) / 256) * 8 * 64 + 4096 + 256 * 2048;      // + the 32-group alignment slack of up to 2048 items
-        ws.rbits.ensure((size_t)ws.rbits_words * sizeof(unsigned int));
-        ws.rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
-        if (D <= 2) {
-            ws.rwide_groups = ws.rbits_words / 8 + 1;
-            ws.rwide.ensure((size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)) + sizeof(int)) +
-                            (size_t)ws.replay_cap * 8 * sizeof(float) + 64 +
-                            ((size_t)ws.rwide_groups / 32 + 2) * 2 * D * (sizeof(int4) + sizeof(float)));      // + window tables
+    ws.rbits_words = (long long)((n1 + 255) / 256) * 8 * 64 + 4096 + 256 * 2048;      // + the 32-group alignment slack of up to 2048 items
+    ws.rwide_groups = ws.rbits_words / 8 + 1;
+    const size_t rwide_bytes = (size_t)ws.rwide_groups * ((size_t)2 * D * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)) + sizeof(int)) +
+                               (size_t)ws.replay_cap * 8 * sizeof(float) + 64 +
+                               ((size_t)ws.rwide_groups / 32 + 2) * 2 * D * (sizeof(int4) + sizeof(float));      // + window tables
+    auto ensure_replay = [&](DevBuf &replay, DevBuf &scores, DevBuf &rgrad, DevBuf &rbits, DevBuf &rmeta, DevBuf &rwide) {
+        replay.ensure((size_t)ws.replay_cap * (sizeof(ReplayItem) + sizeof(int)));
+        scores.ensure((size_t)2 * ws.replay_cap * sizeof(float));      // replayed scores, then the exact-tier scores of the same items
+        if (m.cfg.tie_replay && D <= 4) {
+            // replay streams (split.cu): planes for 64 full-size candidates, i.e. all items of a level unless the near-tie
+            // band is unusually crowded (those items are gathered directly by their chain CTA)
+            rgrad.ensure(n1 * D * sizeof(float));
+            rbits.ensure((size_t)ws.rbits_words * sizeof(unsigned int));
+            rmeta.ensure(((size_t)3 * ws.replay_cap + 2) * sizeof(int));
+            if (D <= 2) rwide.ensure(rwide_bytes);
+        }
+    };
+    ensure_replay(ws.replay, ws.replay_scores, ws.rgrad, ws.rbits, ws.rmeta, ws.rwide);
+    // Speculative levels (tree.cu): every level keeps its own replay buffers, row order and histograms, so that the chains of a
+    // level can be walked while the deeper levels are grown, and a level can be returned to.  GBRL_B200_SPEC=0 turns it off.
+    {
+        static const bool env_off = getenv("GBRL_B200_SPEC") != nullptr && getenv("GBRL_B200_SPEC")[0] == '0';
+        size_t extra = 0;
+        if (md > 0) {
+            const size_t per_slot = (size_t)ws.replay_cap * 20 + n1 * D * 4 + (size_t)ws.rbits_words * 4 + (D <= 2 ? rwide_bytes : 0);
+            extra = (size_t)md * per_slot + (slot_bytes << md) + (size_t)(md + 1) * n1 * 4;
+        }
+        ws.spec = m.cfg.tie_replay && md > 0 && !(m.cfg.replay_variant & 2) && !env_off && extra <= ((size_t)24 << 30);
+        if (ws.spec) {
+            for (int l = 0; l < md; ++l) {
+                ReplaySlot &sl = ws.slots[l];
+                ensure_replay(sl.replay, sl.replay_scores, sl.rgrad, sl.rbits, sl.rmeta, sl.rwide);
+                sl.ctl_snap.ensure(sizeof(Ctl));
+                ws.hist_lv[l].ensure(slot_bytes << l);
+                ws.order_lv[l].ensure(n1 * sizeof(int));
+                if (!sl.stream) {
+                    int lo = 0, hi = 0;
+                    GB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority: the side work never delays the tree
+                    GB_CUDA(cudaStreamCreateWithPriority(&sl.stream, cudaStreamNonBlocking, lo));
+                    GB_CUDA(cudaEventCreateWithFlags(&sl.ev_sel, cudaEventDisableTiming));
+                    GB_CUDA(cudaEventCreateWithFlags(&sl.ev_dec, cudaEventDisableTiming));
+                    GB_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+                }
+            }
+            ws.order_lv[md].ensure(n1 * sizeof(int));
+            ws.state_snap.ensure((size_t)ws.MAXN * sizeof(int));
+            ws.spec_flag.ensure(sizeof(unsigned int));
+            if (!ws.h_spec_flag) GB_CUDA(cudaMallocHost(&ws.h_spec_flag, sizeof(unsigned int)));
         }
     }
     // node arrays carved from one allocation
@@ -334,7 +370,7 @@ static float do_fit(Model &m, const float *obs, int obs_dev, const float *target
 // ---------------------------------------------------------------- profiling
 static const char *const PROF_NAMES[P_NCAT] = {"gbrl_b200/candidates", "gbrl_b200/binning", "gbrl_b200/preprocess", "gbrl_b200/histogram",
                                                "gbrl_b200/exchange", "gbrl_b200/scan", "gbrl_b200/select_replay", "gbrl_b200/plan_decide",
-                                               "gbrl_b200/partition", "gbrl_b200/finalize", "gbrl_b200/predict"};
+                                               "gbrl_b200/partition", "gbrl_b200/finalize", "gbrl_b200/predict", "gbrl_b200/spec_wait"};
 
 ProfScope::ProfScope(Model &m_, int cat_, cudaStream_t s_) : m(m_), cat(cat_), s(s_), on(m_.profile) {
     nvtxRangePushA(PROF_NAMES[cat]);          // one NVTX range per kernel class (shows up in nsys / ncu --nvtx timelines)
@@ -451,6 +487,14 @@ int gbrl_b200_create(const gbrl_b200_config *cfg, gbrl_b200_model **out) {
 void gbrl_b200_destroy(gbrl_b200_model *h) {
     if (!h) return;
     try { gb::dist_shutdown(h->m); } catch (...) {}
+    cudaSetDevice(h->m.device);
+    for (auto &sl : h->m.ws.slots) {
+        if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+        if (sl.ev_sel) cudaEventDestroy(sl.ev_sel);
+        if (sl.ev_dec) cudaEventDestroy(sl.ev_dec);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (h->m.ws.h_spec_flag) cudaFreeHost(h->m.ws.h_spec_flag);
     delete h;
 }
 
@@ -632,6 +676,7 @@ int gbrl_b200_get_metadata(gbrl_b200_model *h, gbrl_b200_metadata *o) {
     o->kernel_launches = gb::g_kernel_launches.load(); o->replay_items = m.replay_items; o->replay_nodes = m.replay_nodes;
     o->replay_overflow = m.replay_overflow; o->nodes_evaluated = m.nodes_evaluated; o->max_noise_ratio = m.max_noise;
     o->chain_blocks_fast = m.chain_fast; o->chain_blocks_slow = m.chain_slow; o->chain_lanes_seq = m.chain_seq; o->replay_flips = m.replay_flips;
+    o->spec_trees = m.spec_trees; o->spec_rollbacks = m.spec_rollbacks;
     API_END
 }
 

@@ -89,6 +89,16 @@ struct Ensemble {            // reference layout, types.h:279-304 (numerical fea
     long long n_leaves_ub = 0;   // host-side upper bound of n_leaves while trees are grown without a host sync
 };
 
+// Per-level buffers of a SPECULATIVE near-tie replay (tree.cu grow_tree): the level's replay items, side-bit planes, group
+// summaries and replayed scores live here while the chains are walked on `stream`, concurrently with the deeper levels
+// of the tree that the main stream grows on the exact-tier winners.
+struct ReplaySlot {
+    DevBuf replay, replay_scores, rgrad, rbits, rmeta, rwide, ctl_snap;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_sel = nullptr, ev_dec = nullptr, ev_done = nullptr;
+    bool pending = false;
+};
+
 struct Workspace {           // sized for (N, F, D, depth); reused across calls with the same shape
     int N = 0, F = 0, nT = 0, D = 0, depth = 0, MAXN = 0, B = 0;
     int tile_lo = 0, tile_hi = 0;   // feature tiles owned by this rank [tile_lo, tile_hi)
@@ -111,12 +121,22 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     DevBuf sort_offsets;
     DevBuf xstage, gstage, tstage, preds_full, grads_fit, loss_parts, pstage, pred_partials;
     NodeArrays na{};
+    // current / next row order and the histogram buffer of (level & 1): ws.order[] / ws.hist[], or -- while a tree is grown
+    // speculatively -- the per-level buffers below (a rollback needs the order and the histograms of the level it returns to)
+    int *order_p[2] = {nullptr, nullptr};
+    long long *hist_p[2] = {nullptr, nullptr};
+    bool spec = false;                   // speculative replay enabled for this workspace shape
+    bool count_stats = true;             // false while a rolled-back level is decided a second time
+    DevBuf order_lv[MAX_DEPTH_SUPPORTED + 1], hist_lv[MAX_DEPTH_SUPPORTED];
+    ReplaySlot slots[MAX_DEPTH_SUPPORTED];
+    DevBuf state_snap, spec_flag;        // node states of every level before its decision; lowest level whose decision the replay changed
+    unsigned int *h_spec_flag = nullptr; // pinned host copy of spec_flag
     size_t sort_tmp_bytes = 0;
     int replay_cap = 0, items_cap = 0;
 };
 
 // per-kernel-class device timing (CUDA events on the launching stream), enabled by gbrl_b200_profile()
-enum ProfCat : int { P_CAND = 0, P_BIN, P_PRE, P_HIST, P_ALLREDUCE, P_SCAN, P_SELECT, P_DECIDE, P_PART, P_FIN, P_PRED, P_NCAT };
+enum ProfCat : int { P_CAND = 0, P_BIN, P_PRE, P_HIST, P_ALLREDUCE, P_SCAN, P_SELECT, P_DECIDE, P_PART, P_FIN, P_PRED, P_SPEC, P_NCAT };
 
 struct FitSession {          // state of fit_begin / fit_iterate / fit_end (fitter.cpp:117-261)
     bool active = false, incremental = true;
@@ -141,6 +161,7 @@ struct Model {
     int rank = 0, world = 1;
     // statistics
     long long replay_items = 0, replay_nodes = 0, replay_overflow = 0, nodes_evaluated = 0, chain_fast = 0, chain_slow = 0, chain_seq = 0, replay_flips = 0;
+    long long spec_trees = 0, spec_rollbacks = 0;   // trees grown speculatively / levels that had to be rolled back
     bool have_candidates = false;
     long long hist_rows = 0;          // rows scanned by the histogram kernel (read back from Ctl)
     float max_noise = 0.0f;           // see Ctl::stat_max_noise
@@ -183,8 +204,10 @@ int hist_item_rows(const Model &m);
 void launch_histogram(Model &m, int level, cudaStream_t s);
 // split.cu
 void launch_scan(Model &m, int level, cudaStream_t s);
-void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s);
-void launch_decide(Model &m, int level, cudaStream_t s);
+void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s, ReplaySlot *slot = nullptr);
+void launch_decide(Model &m, int level, cudaStream_t s, bool use_replay = true);
+void launch_verify(Model &m, int level, cudaStream_t s, ReplaySlot &slot);      // speculative level: replayed decision vs the one taken
+void launch_rollback(Model &m, int level, cudaStream_t s);
 // partition.cu
 void launch_partition(Model &m, const float *X, int level, int cur, cudaStream_t s);
 // tree.cu

@@ -407,7 +407,7 @@ static void launch_hist_stream(Model &m, int d0, int write_count, long long *his
     const size_t smem = (size_t)(1 + 2 * ND) * HPLANE * sizeof(int) + (size_t)NWARPS * NST * HS_STAGE_ROWS * (64 + 8 * ND);   // planes + rings
     ensure_dyn_smem(hist_stream_kernel<ND, NWARPS, NST>, smem);
     GB_LAUNCH((hist_stream_kernel<ND, NWARPS, NST>), n_sms, NWARPS * 32, smem, s, ws.codes.as<uint16_t>(), ws.bgq.as<int2>(),
-              ws.order[0].as<int>(), ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
+              ws.order_p[0], ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
               ws.tile_hi - ws.tile_lo, ws.tile_lo, ws.nT, write_count);
 }
 
@@ -418,7 +418,7 @@ static void launch_hist_nd(Model &m, int d0, int write_count, long long *hist, i
     ensure_dyn_smem(hist_kernel<ND>, smem);
     const int ctas_per_sm = ND == 1 ? 2 : 1;
     GB_LAUNCH(hist_kernel<ND>, n_sms * ctas_per_sm, HIST_THREADS, smem, s, ws.codes.as<uint16_t>(), ws.bg.as<float>(),
-              ws.order[0].as<int>(), ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
+              ws.order_p[0], ws.items.as<Item>(), ws.ctl.as<Ctl>(), hist, ws.codes_rows, ws.row_offset, ws.D, d0,
               ws.tile_hi - ws.tile_lo, ws.tile_lo, ws.nT, write_count);
 }
 
@@ -426,7 +426,7 @@ static void launch_hist_nd(Model &m, int d0, int write_count, long long *hist, i
 void launch_histogram(Model &m, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
     const int n_sms = ws.n_sms;
-    long long *hist = ws.hist[level & 1].as<long long>();
+    long long *hist = ws.hist_p[level & 1];
     const int D = ws.D;
     int d0 = 0;
     while (d0 < D) {

@@ -107,7 +107,7 @@ part_scatter_kernel(const int *__restrict__ order_in, int *__restrict__ order_ou
     }
 }
 
-// after this call ws.order[0] is the new current order
+// after this call ws.order_p[0] is the new current order
 void launch_partition(Model &m, const float *X, int level, int cur, cudaStream_t s) {
     (void)level; (void)cur;
     Workspace &ws = m.ws;
@@ -116,12 +116,11 @@ void launch_partition(Model &m, const float *X, int level, int cur, cudaStream_t
     const int n_chunks = ceil_div(N, PART_CHUNK);
     // ws.rflag holds the packed u16 (flag, in-chunk prefix) per position; chunk_sums[n_chunks] is the done counter (zero between launches)
     GB_LAUNCH(part_flag_scan_kernel, n_chunks, 256, 0, s, X, ws.F, ws.use_codesT ? ws.codesT.as<uint16_t>() : nullptr, ws.codesT_stride,
-              ws.row_offset, ws.order[0].as<int>(), ws.nid.as<int>(), ws.na, ws.rflag.as<uint16_t>(), ws.chunk_sums.as<int>(),
+              ws.row_offset, ws.order_p[0], ws.nid.as<int>(), ws.na, ws.rflag.as<uint16_t>(), ws.chunk_sums.as<int>(),
               ws.chunk_sums.as<int>() + ws.chunk_cap, N, n_chunks);
-    GB_LAUNCH(part_scatter_kernel, ceil_div(N, 256), 256, 0, s, ws.order[0].as<int>(), ws.order[1].as<int>(), ws.nid.as<int>(),
+    GB_LAUNCH(part_scatter_kernel, ceil_div(N, 256), 256, 0, s, ws.order_p[0], ws.order_p[1], ws.nid.as<int>(),
               ws.rflag.as<uint16_t>(), ws.chunk_sums.as<int>(), ws.na, N);
-    std::swap(ws.order[0].p, ws.order[1].p);
-    std::swap(ws.order[0].bytes, ws.order[1].bytes);
+    std::swap(ws.order_p[0], ws.order_p[1]);
 }
 
 }  // namespace gb

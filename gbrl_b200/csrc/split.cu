@@ -257,6 +257,7 @@ struct SelectParams {
     const uint8_t *cand_flags;
     const float2 *tile_best;
     ReplayItem *replay;
+    float *replay_exact;      // exact-tier score of every replay item (0 for parent items): calibration statistic of the band
     Ctl *ctl;
 };
 
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(1024) select_greedy_kernel(SelectParams P, Nod
         } else {
             s_begin = beg;
             na.rep_begin[h] = beg; na.rep_count[h] = n_items; na.band[h] = band;
-            if (P.level > 0) { P.replay[beg].node = h; P.replay[beg].cand = -1; s_w = 1; }
+            if (P.level > 0) { P.replay[beg].node = h; P.replay[beg].cand = -1; P.replay_exact[beg] = 0.0f; s_w = 1; }
             atomicAdd((unsigned long long *)&P.ctl->stat_replay_nodes, 1ull);
             atomicAdd((unsigned long long *)&P.ctl->stat_replay_items, (unsigned long long)n_items);
         }
@@ -334,6 +335,7 @@ __global__ void __launch_bounds__(1024) select_greedy_kernel(SelectParams P, Nod
             const int w = atomicAdd(&s_w, 1);
             P.replay[s_begin + w].node = h;
             P.replay[s_begin + w].cand = i;
+            P.replay_exact[s_begin + w] = sc[i];
         }
     }
 }
@@ -1133,8 +1135,13 @@ struct DecideParams {
     const ReplayItem *replay;
     const float *replay_scores;
     const int *obl_cands;
-    const float *scores;      // exact-tier scores [slot][C]
-    Ctl *ctl;
+    const float *replay_exact;   // exact-tier scores of the replay items (select_greedy_kernel)
+    Ctl *ctl;                    // decisions: the live control block; verification of a speculative level: its snapshot
+    Ctl *ctl_stats;              // the live control block (statistics)
+    const int *state_snap;       // verification: node states before the level's decision
+    int use_replay;              // 0: speculative decision on the exact-tier winner (the replay of this level is still running)
+    int count_stats;             // 0: this level was counted already (second decision of a rolled-back level)
+    int force_flip;              // tests (GBRL_B200_SPEC_FORCE_FLIP=1): speculate on a WRONG candidate wherever there is a choice
 };
 
 // suffix sum over codes > j of feature f in the node's histogram (one warp)
@@ -1178,12 +1185,12 @@ __device__ void apply_split(NodeArrays na, const DecideParams &P, int h, int can
     __syncwarp();
 }
 
-// greedy: one warp per node of the level
-__device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) {
-    const int h = level_base(P.level) + p, lane = threadIdx.x & 31;
-    if (na.state[h] != NODE_OPEN) return;
-    float g = na.best_gain[h];
-    int c = na.best_idx[h];
+// greedy, one warp: the decision of node h in the reference's arithmetic -- arg-max over the replayed candidates where the node
+// has replay items, the exact-tier winner otherwise.  Same value in every lane.
+__device__ void final_choice_greedy(const DecideParams &P, NodeArrays na, int p, int h, float &g, int &c) {
+    const int lane = threadIdx.x & 31;
+    g = na.best_gain[h];
+    c = na.best_idx[h];
     const int rc = na.rep_count[h];
     if (rc > 0) {
         // final arg-max over the replayed candidates, in the reference's arithmetic
@@ -1199,9 +1206,9 @@ __device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) 
             if (gain > -INFINITY && better(gain, cand, bg_, bi)) { bg_ = gain; bi = cand; }
             // calibration statistic of the band: observed rounding noise of the reference's sum, in units of
             // 2^-24 * sqrt(n) * |score*w|  (exact-tier score*w = stored gain + exact parent)
-            const float sw_exact = P.scores[(size_t)p * P.C + cand] + na.parent_score[h];
+            const float sw_exact = P.replay_exact[i] + na.parent_score[h];
             const float unit = U24 * sqrtf((float)na.seg_len[h]) * fabsf(sw_exact);
-            if (unit > 0.0f && gain > -INFINITY) atomicMax(&P.ctl->stat_max_noise, __float_as_uint(fabsf(sw - sw_exact) / unit));
+            if (unit > 0.0f && gain > -INFINITY && P.count_stats) atomicMax(&P.ctl_stats->stat_max_noise, __float_as_uint(fabsf(sw - sw_exact) / unit));
         }
         for (int o = 16; o > 0; o >>= 1) {
             const float og = __shfl_down_sync(0xffffffffu, bg_, o);
@@ -1210,8 +1217,28 @@ __device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) 
         }
         bg_ = __shfl_sync(0xffffffffu, bg_, 0); bi = __shfl_sync(0xffffffffu, bi, 0);
         if (bi != INT_MAX) {
-            if (lane == 0 && bi != c) atomicAdd((unsigned long long *)&P.ctl->stat_replay_flips, 1ull);
+            if (lane == 0 && bi != c && P.count_stats) atomicAdd((unsigned long long *)&P.ctl_stats->stat_replay_flips, 1ull);
             g = bg_; c = bi;
+        }
+    }
+    (void)p;
+}
+
+// greedy: one warp per node of the level
+__device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) {
+    const int h = level_base(P.level) + p, lane = threadIdx.x & 31;
+    if (na.state[h] != NODE_OPEN) return;
+    float g; int c;
+    if (P.use_replay) final_choice_greedy(P, na, p, h, g, c);
+    else {
+        g = na.best_gain[h]; c = na.best_idx[h];
+        if (P.force_flip && na.rep_count[h] > 0) {
+            // tests: take the first other candidate of the replay list, so that the verification has to roll this level back
+            const int rb = na.rep_begin[h], rc = na.rep_count[h];
+            for (int i = rb; i < rb + rc; ++i) {
+                const int cand = P.replay[i].cand;
+                if (cand >= 0 && cand != c) { c = cand; g = 0.0f; break; }
+            }
         }
     }
     // fitter.cpp:357: split iff best_score >= 0 (and the node could be split at all)
@@ -1230,26 +1257,40 @@ __device__ void decide_greedy_node(const DecideParams &P, NodeArrays na, int p) 
     }
 }
 
+// oblivious, one thread: the level's candidate in the reference's arithmetic (fitter.cpp:427-445)
+__device__ int final_choice_oblivious(const DecideParams &P) {
+    int c = P.ctl->obl_best_idx;
+    const int nrep = P.ctl->obl_has_replay;
+    if (c >= 0 && nrep > 1) {
+        float bg_ = -INFINITY; int bi = INT_MAX;
+        for (int w = 0; w < nrep; ++w) {
+            const int cand = P.obl_cands[w];
+            float s = 0.0f;
+            for (int p = 0; p < P.nn; ++p) s += P.replay_scores[(size_t)w * P.nn + p];
+            s = s * P.fw[P.rev_map[cand / P.B]];
+            if (s > -INFINITY && better(s, cand, bg_, bi)) { bg_ = s; bi = cand; }
+        }
+        if (bi != INT_MAX) {
+            if (bi != c && P.count_stats) atomicAdd((unsigned long long *)&P.ctl_stats->stat_replay_flips, 1ull);
+            c = bi;
+        }
+    }
+    return c;
+}
+
 // oblivious: one CTA, warp w handles nodes w, w + #warps, ...
 __device__ void decide_oblivious_body(const DecideParams &P, NodeArrays na) {
     __shared__ int s_cand;
     const int base = level_base(P.level);
     if (na.state[base] != NODE_OPEN) return;
     if (threadIdx.x == 0) {
-        int c = P.ctl->obl_best_idx;
-        const int nrep = P.ctl->obl_has_replay;
-        if (c >= 0 && nrep > 1) {
-            float bg_ = -INFINITY; int bi = INT_MAX;
-            for (int w = 0; w < nrep; ++w) {
-                const int cand = P.obl_cands[w];
-                float s = 0.0f;
-                for (int p = 0; p < P.nn; ++p) s += P.replay_scores[(size_t)w * P.nn + p];
-                s = s * P.fw[P.rev_map[cand / P.B]];
-                if (s > -INFINITY && better(s, cand, bg_, bi)) { bg_ = s; bi = cand; }
-            }
-            if (bi != INT_MAX) {
-                if (bi != c) atomicAdd((unsigned long long *)&P.ctl->stat_replay_flips, 1ull);
-                c = bi;
+        int c;
+        if (P.use_replay) c = final_choice_oblivious(P);
+        else {
+            c = P.ctl->obl_best_idx;
+            if (P.force_flip && c >= 0 && P.ctl->obl_has_replay > 1) {
+                for (int w = 0; w < P.ctl->obl_has_replay; ++w)
+                    if (P.obl_cands[w] != c) { c = P.obl_cands[w]; break; }
             }
         }
         s_cand = c;
@@ -1283,6 +1324,47 @@ __global__ void __launch_bounds__(1024) decide_plan_kernel(DecideParams P, NodeA
                         Q.row_group, Q.item_rows_max);
 }
 
+// Verification of a speculative level (side stream, after the level's replay): the decision in the reference's arithmetic
+// against the one the tree was grown on.  The lowest level with a difference is where grow_tree returns to.
+__global__ void __launch_bounds__(1024) verify_kernel(DecideParams P, NodeArrays na, int oblivious, unsigned int *flip_level) {
+    const int base = level_base(P.level);
+    if (oblivious) {
+        if (threadIdx.x != 0 || P.state_snap[base] != NODE_OPEN) return;      // the tree had stopped before this level
+        const int c = final_choice_oblivious(P);
+        const int taken = na.state[base] == NODE_SPLIT ? na.split_f[base] * P.B + na.split_j[base] : -1;
+        if (c != taken) atomicMin(flip_level, (unsigned int)P.level);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    for (int p = threadIdx.x >> 5; p < P.nn; p += (int)(blockDim.x >> 5)) {
+        const int h = base + p;
+        if (P.state_snap[h] != NODE_OPEN) continue;
+        float g; int c;
+        final_choice_greedy(P, na, p, h, g, c);
+        const bool split = (c >= 0) && (g >= 0.0f);
+        const bool split_taken = na.state[h] == NODE_SPLIT;
+        const int taken = na.split_f[h] * P.B + na.split_j[h];
+        if (lane == 0 && (split != split_taken || (split && c != taken))) atomicMin(flip_level, (unsigned int)P.level);
+    }
+}
+
+// Return to the state before the decision of level L: node states of that level from their snapshot, deeper nodes gone, every
+// row back in its ancestor at level L (the row ORDER and the histograms of level L are still in their per-level buffers).
+__global__ void __launch_bounds__(256) rollback_kernel(NodeArrays na, const int *state_snap, int *nid, int N, int MAXN, int L, unsigned int *flip_level) {
+    const int lo = level_base(L), hi = level_base(L + 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *flip_level = 0xffffffffu;
+    if (i < MAXN) {
+        if (i >= hi) na.state[i] = NODE_NONE;
+        else if (i >= lo) na.state[i] = state_snap[i];
+    }
+    if (i < N) {
+        int h = nid[i];
+        while (h >= hi) h = (h - 1) >> 1;
+        nid[i] = h;
+    }
+}
+
 // ---------------------------------------------------------------- launchers
 template <int DM>
 static void launch_scan_dm(const ScanParams &P, const NodeArrays &na, int grid, cudaStream_t s) {
@@ -1295,8 +1377,8 @@ void launch_scan(Model &m, int level, cudaStream_t s) {
     P.level = level; P.nT = ws.nT; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = ws.F * ws.B;
     P.score_func = m.cfg.split_score_func; P.oblivious = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
     P.min_data = m.cfg.min_data_in_leaf; P.max_depth = m.cfg.max_depth; P.use_subtraction = m.cfg.use_subtraction;
-    P.hist_cur = ws.hist[level & 1].as<long long>();
-    P.hist_par = ws.hist[(level + 1) & 1].as<long long>();
+    P.hist_cur = ws.hist_p[level & 1];
+    P.hist_par = ws.hist_p[(level + 1) & 1];
     P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
     P.scores = ws.scores.as<float>(); P.cand_flags = ws.cand_flags.as<uint8_t>();
     P.tile_best = ws.tile_best.as<float2>(); P.ctl = ws.ctl.as<Ctl>();
@@ -1319,7 +1401,9 @@ static void launch_stream(const ReplayParams &R, const NodeArrays &na, const Str
     GB_LAUNCH((replay_stream_kernel<DCT>), n_sms * 2, 512, smem, s, R, na, S, ctl);
 }
 
-void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s) {
+// slot != nullptr: speculative level.  The caller has bound the slot's buffers into the workspace (tree.cu SlotBind); the selection
+// runs on `s`, the replay of the selected items on the slot's side stream, against a snapshot of the control block.
+void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t s, ReplaySlot *slot) {
     Workspace &ws = m.ws;
     const bool obl = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
     const int C = ws.F * ws.B, nn = 1 << level;
@@ -1334,7 +1418,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         P.level = level; P.nT = ws.nT; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = C; P.tie_replay = m.cfg.tie_replay;
         P.replay_cap = ws.replay_cap; P.kappa = kappa; P.scores = ws.scores.as<float>();
         P.cand_flags = ws.cand_flags.as<uint8_t>(); P.tile_best = ws.tile_best.as<float2>();
-        P.replay = ws.replay.as<ReplayItem>(); P.ctl = ctl;
+        P.replay = ws.replay.as<ReplayItem>(); P.replay_exact = ws.replay_scores.as<float>() + ws.replay_cap; P.ctl = ctl;
         GB_LAUNCH(select_greedy_kernel, nn, 1024, 0, s, P, ws.na);
     } else {
         OblParams P;
@@ -1346,68 +1430,109 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         GB_LAUNCH(obl_reduce_kernel, P.nblocks, 256, 0, s, P, ws.na);
         GB_LAUNCH(obl_select_kernel, 1, 256, 0, s, P, ws.na);
     }
-    if (m.cfg.tie_replay) {
-        ReplayParams R;
-        R.F = ws.F; R.B = ws.B; R.D = ws.D; R.score_func = m.cfg.split_score_func; R.min_data = m.cfg.min_data_in_leaf;
-        R.X = X; R.codesT = ws.use_codesT ? ws.codesT.as<uint16_t>() : nullptr; R.codesT_stride = ws.codesT_stride; R.row_offset = ws.row_offset;
-        R.bg = ws.bg.as<float>(); R.order = ws.order[0].as<int>(); R.thr = ws.thr.as<float>();
-        R.items = ws.replay.as<ReplayItem>(); R.out = ws.replay_scores.as<float>(); R.ctl = ctl;
-        // rows per thread per stage: 8 (1024-row stages) for D == 1 down to 1 for wide outputs, so that a stage's
-        // gradients fit in registers while they are in flight and two stages fit in shared memory
-        const int D = ws.D;
-        if (D <= 4) {
-            // bit-exact parallel chains (chain.cuh) over streams prepared by the whole GPU
-            StreamParams S;
-            S.G = ws.rgrad.as<float>(); S.bits = ws.rbits.as<unsigned int>(); S.woff = ws.rmeta.as<int>();
-            S.mode = S.woff + ws.replay_cap + 1; S.nright = S.mode + ws.replay_cap;
-            // GBRL_B200_REPLAY_DIRECT=1 (tests): no plane fits, every item takes the direct-gather kernel
-            static const bool force_direct = getenv("GBRL_B200_REPLAY_DIRECT") != nullptr && getenv("GBRL_B200_REPLAY_DIRECT")[0] == '1';
-            S.cap_words = force_direct ? 0 : ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N; S.oblivious = obl ? 1 : 0;
-            S.nid = ws.nid.as<int>();
-            S.wide = (D <= 2 && m.cfg.replay_variant == 0) ? 1 : 0;
-            GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, s, R, ws.na, S);
-            GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
-            if (S.wide) {
-                // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
-                launch_replay_wide(m, R, S, s);
-                if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-                else GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-                return;
-            }
-            GB_LAUNCH(replay_bits_kernel, ws.n_sms * 8, 256, 0, s, R, ws.na, S);
-            if (D <= 1) {
-                launch_stream<1>(R, ws.na, S, ctl, ws.n_sms, s);
-                GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-            } else if (D == 2) {
-                launch_stream<2>(R, ws.na, S, ctl, ws.n_sms, s);
-                GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-            } else if (D == 3) {
-                launch_stream<3>(R, ws.na, S, ctl, ws.n_sms, s);
-                GB_LAUNCH((replay_par_kernel<3>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-            } else {
-                launch_stream<4>(R, ws.na, S, ctl, ws.n_sms, s);
-                GB_LAUNCH((replay_par_kernel<4>), ws.n_sms * 2, 512, 0, s, R, ws.na, ctl, S.mode, ws.replay_cap);
-            }
-        } else {
-            // wide outputs: one lane per output dimension runs its chain sequentially (parallel over D instead of over rows)
-            const int T = 128;
-            const size_t smem = ((size_t)2 * T * D + 2 * D) * sizeof(float) + (size_t)2 * (T / 32) * sizeof(unsigned int);
-            if (smem > 48 * 1024) ensure_dyn_smem(replay_kernel<1, 128>, smem);
-            GB_LAUNCH((replay_kernel<1, 128>), ws.n_sms * 4, 128, smem, s, R, ws.na);
+    if (!m.cfg.tie_replay) return;
+    const Ctl *rctl = ctl;         // what the replay kernels read the item count from
+    cudaStream_t rs = s;           // the stream they run on
+    if (slot) {
+        GB_CUDA(cudaMemcpyAsync(slot->ctl_snap.p, ctl, sizeof(Ctl), cudaMemcpyDeviceToDevice, s));
+        GB_CUDA(cudaEventRecord(slot->ev_sel, s));
+        GB_CUDA(cudaStreamWaitEvent(slot->stream, slot->ev_sel, 0));
+        rctl = slot->ctl_snap.as<Ctl>();
+        rs = slot->stream;
+        slot->pending = true;
+    }
+    ReplayParams R;
+    R.F = ws.F; R.B = ws.B; R.D = ws.D; R.score_func = m.cfg.split_score_func; R.min_data = m.cfg.min_data_in_leaf;
+    R.X = X; R.codesT = ws.use_codesT ? ws.codesT.as<uint16_t>() : nullptr; R.codesT_stride = ws.codesT_stride; R.row_offset = ws.row_offset;
+    R.bg = ws.bg.as<float>(); R.order = ws.order_p[0]; R.thr = ws.thr.as<float>();
+    R.items = ws.replay.as<ReplayItem>(); R.out = ws.replay_scores.as<float>(); R.ctl = rctl;
+    // rows per thread per stage: 8 (1024-row stages) for D == 1 down to 1 for wide outputs, so that a stage's
+    // gradients fit in registers while they are in flight and two stages fit in shared memory
+    const int D = ws.D;
+    if (D <= 4) {
+        // bit-exact parallel chains (chain.cuh) over streams prepared by the whole GPU
+        StreamParams S;
+        S.G = ws.rgrad.as<float>(); S.bits = ws.rbits.as<unsigned int>(); S.woff = ws.rmeta.as<int>();
+        S.mode = S.woff + ws.replay_cap + 1; S.nright = S.mode + ws.replay_cap;
+        // GBRL_B200_REPLAY_DIRECT=1 (tests): no plane fits, every item takes the direct-gather kernel
+        static const bool force_direct = getenv("GBRL_B200_REPLAY_DIRECT") != nullptr && getenv("GBRL_B200_REPLAY_DIRECT")[0] == '1';
+        S.cap_words = force_direct ? 0 : ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N;
+        // a speculative level gathers every row: `nid` moves on with the deeper levels while this level is replayed
+        S.oblivious = (obl || slot) ? 1 : 0;
+        S.nid = ws.nid.as<int>();
+        S.wide = (D <= 2 && (m.cfg.replay_variant & 1) == 0) ? 1 : 0;
+        GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, rs, R, ws.na, S);
+        GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, rs, R, ws.na, S);
+        if (S.wide) {
+            // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
+            launch_replay_wide(m, R, S, rs);
+            if (D <= 1) GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
+            else GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
+            return;
         }
+        GB_LAUNCH(replay_bits_kernel, ws.n_sms * 8, 256, 0, rs, R, ws.na, S);
+        if (D <= 1) {
+            launch_stream<1>(R, ws.na, S, ctl, ws.n_sms, rs);
+            GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
+        } else if (D == 2) {
+            launch_stream<2>(R, ws.na, S, ctl, ws.n_sms, rs);
+            GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
+        } else if (D == 3) {
+            launch_stream<3>(R, ws.na, S, ctl, ws.n_sms, rs);
+            GB_LAUNCH((replay_par_kernel<3>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
+        } else {
+            launch_stream<4>(R, ws.na, S, ctl, ws.n_sms, rs);
+            GB_LAUNCH((replay_par_kernel<4>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
+        }
+    } else {
+        // wide outputs: one lane per output dimension runs its chain sequentially (parallel over D instead of over rows)
+        const int T = 128;
+        const size_t smem = ((size_t)2 * T * D + 2 * D) * sizeof(float) + (size_t)2 * (T / 32) * sizeof(unsigned int);
+        if (smem > 48 * 1024) ensure_dyn_smem(replay_kernel<1, 128>, smem);
+        GB_LAUNCH((replay_kernel<1, 128>), ws.n_sms * 4, 128, smem, rs, R, ws.na);
     }
 }
 
-void launch_decide(Model &m, int level, cudaStream_t s) {
+static DecideParams decide_params(Model &m, int level) {
     Workspace &ws = m.ws;
     DecideParams P;
     P.level = level; P.nT = ws.nT; P.F = ws.F; P.B = ws.B; P.D = ws.D; P.C = ws.F * ws.B; P.max_depth = m.cfg.max_depth;
     P.nn = 1 << level;
-    P.hist_cur = ws.hist[level & 1].as<long long>(); P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
+    P.hist_cur = ws.hist_p[level & 1]; P.thr = ws.thr.as<float>(); P.fw = m.feature_weights.as<float>();
     P.rev_map = m.rev_num_map.as<int>(); P.replay = ws.replay.as<ReplayItem>(); P.replay_scores = ws.replay_scores.as<float>();
-    P.obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap); P.ctl = ws.ctl.as<Ctl>();
-    P.scores = ws.scores.as<float>();
-    GB_LAUNCH(decide_plan_kernel, 1, 1024, 0, s, P, ws.na, plan_params(m), m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? 1 : 0);
+    P.replay_exact = ws.replay_scores.as<float>() + ws.replay_cap;
+    P.obl_cands = reinterpret_cast<int *>(ws.replay.as<ReplayItem>() + ws.replay_cap);
+    P.ctl = ws.ctl.as<Ctl>(); P.ctl_stats = ws.ctl.as<Ctl>();
+    P.state_snap = ws.state_snap.as<int>();
+    P.use_replay = 1; P.count_stats = ws.count_stats ? 1 : 0; P.force_flip = 0;
+    return P;
+}
+
+// use_replay == false: speculative decision (the slot of the level is bound into the workspace)
+void launch_decide(Model &m, int level, cudaStream_t s, bool use_replay) {
+    static const bool force_flip = getenv("GBRL_B200_SPEC_FORCE_FLIP") != nullptr && getenv("GBRL_B200_SPEC_FORCE_FLIP")[0] == '1';
+    DecideParams P = decide_params(m, level);
+    P.use_replay = use_replay ? 1 : 0;
+    P.force_flip = (!use_replay && force_flip) ? 1 : 0;
+    GB_LAUNCH(decide_plan_kernel, 1, 1024, 0, s, P, m.ws.na, plan_params(m), m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? 1 : 0);
+}
+
+// after launch_decide of a speculative level (slot bound): the side stream waits for the decision, then compares
+void launch_verify(Model &m, int level, cudaStream_t s, ReplaySlot &slot) {
+    DecideParams P = decide_params(m, level);
+    P.ctl = slot.ctl_snap.as<Ctl>();
+    GB_CUDA(cudaEventRecord(slot.ev_dec, s));
+    GB_CUDA(cudaStreamWaitEvent(slot.stream, slot.ev_dec, 0));
+    GB_LAUNCH(verify_kernel, 1, 1024, 0, slot.stream, P, m.ws.na, m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? 1 : 0,
+              m.ws.spec_flag.as<unsigned int>());
+    GB_CUDA(cudaEventRecord(slot.ev_done, slot.stream));
+}
+
+void launch_rollback(Model &m, int level, cudaStream_t s) {
+    Workspace &ws = m.ws;
+    const int n = ws.N > ws.MAXN ? ws.N : ws.MAXN;
+    GB_LAUNCH(rollback_kernel, ceil_div(n, 256), 256, 0, s, ws.na, ws.state_snap.as<int>(), ws.nid.as<int>(), ws.N, ws.MAXN, level,
+              ws.spec_flag.as<unsigned int>());
 }
 
 }  // namespace gb

@@ -10,6 +10,7 @@
 //   leaf value             fitter.cpp:545-582          mean of the RAW gradients of the leaf's samples, 0 if none;
 //                          a depth-0 leaf never matches (passed=false, :559-564) and keeps value 0
 #include "engine.cuh"
+#include <utility>
 
 namespace gb {
 
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) root_totals_kernel(const float *__restric
 
 void launch_init_tree(Model &m, int N, cudaStream_t s) {
     Workspace &ws = m.ws;
-    if (N > 0) GB_LAUNCH(init_rows_kernel, ceil_div(N, 256), 256, 0, s, ws.order[0].as<int>(), ws.nid.as<int>(), N);
+    if (N > 0) GB_LAUNCH(init_rows_kernel, ceil_div(N, 256), 256, 0, s, ws.order_p[0], ws.nid.as<int>(), N);
     GB_LAUNCH(init_nodes_kernel, 1, 256, 0, s, ws.na, ws.ctl.as<Ctl>(), ws.MAXN, N, ws.D, m.cfg.max_depth,
               m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS);
     if (N > 0) {
@@ -264,7 +265,7 @@ void launch_finalize_tree(Model &m, const float *raw_grads, int N, int cur, cuda
     if (N > 0) {
         int grid = ceil_div(N, 256);
         if (grid > 2368) grid = 2368;
-        GB_LAUNCH(leaf_sums_kernel, grid, 256, 0, s, raw_grads, ws.order[0].as<int>(), ws.nid.as<int>(), ws.na, ctl,
+        GB_LAUNCH(leaf_sums_kernel, grid, 256, 0, s, raw_grads, ws.order_p[0], ws.nid.as<int>(), ws.na, ctl,
                   ws.loss_parts.as<long long>(), N, D);
     }
     GB_LAUNCH(leaf_values_kernel, ceil_div((1 << md) * D, 256), 256, 0, s, ws.loss_parts.as<long long>(), ctl, E, ws.na, D, md, obl ? 1 : 0, ws.MAXN);
@@ -272,24 +273,88 @@ void launch_finalize_tree(Model &m, const float *raw_grads, int N, int cur, cuda
 }
 
 // ---------------------------------------------------------------- one tree
+// Speculative levels (ws.spec).  The near-tie replay (split.cu) re-scores a handful of candidates per level in the reference's
+// sequential fp32 arithmetic; its chains are latency-bound walks of single warps, and they change the exact-tier decision
+// rarely (C2: 0 of 85 replayed nodes, C3: 6 of 104 levels, C5: 3 of 313 nodes; profiles/README.md).  So the tree keeps growing
+// on the exact-tier winners while every level's replay runs on its own low-priority side stream, against per-level buffers
+// (replay items, planes, summaries; the level's row order and histograms are kept too).  A verification kernel behind each
+// replay compares the decision in the reference's arithmetic with the one taken and records the lowest level that differs.
+// At the end of the tree the host reads that one word: none -> the tree IS the reference's tree; level L -> node states and
+// row -> node ids are returned to level L (rollback_kernel; order and histograms of L are still there), L is decided again
+// with its replay on the critical path, and the levels below L are grown speculatively again.  L strictly increases, so
+// a tree costs at most max_depth returns; the result never depends on speculation.
+namespace {
+struct SlotBind {            // swaps a slot's replay buffers into the workspace for the launches of one level
+    Workspace &ws; ReplaySlot *sl;
+    static void sw(DevBuf &a, DevBuf &b) { std::swap(a.p, b.p); std::swap(a.bytes, b.bytes); }
+    void swap_all() {
+        sw(ws.replay, sl->replay); sw(ws.replay_scores, sl->replay_scores); sw(ws.rgrad, sl->rgrad);
+        sw(ws.rbits, sl->rbits); sw(ws.rmeta, sl->rmeta); sw(ws.rwide, sl->rwide);
+    }
+    SlotBind(Workspace &w, ReplaySlot *s) : ws(w), sl(s) { if (sl) swap_all(); }
+    ~SlotBind() { if (sl) swap_all(); }
+};
+}  // namespace
+
 void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, cudaStream_t s) {
     (void)F;
     Workspace &ws = m.ws;
     const int md = m.cfg.max_depth;
     ensure_ensemble_capacity(m, 1, s);
+    const bool spec = ws.spec && md > 0 && N > 0;
+    if (spec) {
+        ws.order_p[0] = ws.order_lv[0].as<int>(); ws.order_p[1] = ws.order_lv[1].as<int>();
+        GB_CUDA(cudaMemsetAsync(ws.spec_flag.p, 0xff, sizeof(unsigned int), s));
+        m.spec_trees += 1;
+    } else {
+        ws.order_p[0] = ws.order[0].as<int>(); ws.order_p[1] = ws.order[1].as<int>();
+        ws.hist_p[0] = ws.hist[0].as<long long>(); ws.hist_p[1] = ws.hist[1].as<long long>();
+    }
+    ws.count_stats = true;
     { ProfScope ps(m, P_PRE, s); raw_grad_scale(m, raw_grads, N, s); launch_init_tree(m, N, s); }
     const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + ws.D) * sizeof(long long);
     if (md > 0) { ProfScope ps(m, P_DECIDE, s); launch_plan_level(m, 0, s); }
-    for (int level = 0; level < md; ++level) {
-        { ProfScope ps(m, P_DECIDE, s); GB_CUDA(cudaMemsetAsync(ws.hist[level & 1].p, 0, slot_bytes << level, s)); }
-        { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
-        if (m.world > 1) { ProfScope ps(m, P_ALLREDUCE, s);
-            dist_allreduce_hist(m, ws.hist[level & 1].as<long long>(), (slot_bytes << level) / sizeof(long long), s); }
-        { ProfScope ps(m, P_SCAN, s); launch_scan(m, level, s); }
-        { ProfScope ps(m, P_SELECT, s); launch_select_and_replay(m, X, level, s); }
-        { ProfScope ps(m, P_DECIDE, s); launch_decide(m, level, s); }
-        { ProfScope ps(m, P_PART, s); launch_partition(m, X, level, 0, s); }
+    int start = 0, sync_level = -1;      // sync_level: the level that is decided with its replay on the critical path (after a return)
+    for (;;) {
+        for (int level = start; level < md; ++level) {
+            if (spec) {
+                ws.hist_p[level & 1] = ws.hist_lv[level].as<long long>();
+                ws.order_p[0] = ws.order_lv[level].as<int>(); ws.order_p[1] = ws.order_lv[level + 1].as<int>();
+            }
+            if (level != sync_level) {         // the histograms of a level that is returned to are still in place
+                { ProfScope ps(m, P_DECIDE, s); GB_CUDA(cudaMemsetAsync(ws.hist_p[level & 1], 0, slot_bytes << level, s)); }
+                { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
+                if (m.world > 1) { ProfScope ps(m, P_ALLREDUCE, s);
+                    dist_allreduce_hist(m, ws.hist_p[level & 1], (slot_bytes << level) / sizeof(long long), s); }
+            }
+            { ProfScope ps(m, P_SCAN, s); launch_scan(m, level, s); }
+            ReplaySlot *slot = (spec && level != sync_level) ? &ws.slots[level] : nullptr;
+            SlotBind bind(ws, slot);
+            ws.count_stats = level != sync_level;
+            { ProfScope ps(m, P_SELECT, s); launch_select_and_replay(m, X, level, s, slot); }
+            { ProfScope ps(m, P_DECIDE, s);
+              if (spec) GB_CUDA(cudaMemcpyAsync(ws.state_snap.as<int>() + level_base(level), ws.na.state + level_base(level),
+                                                sizeof(int) << level, cudaMemcpyDeviceToDevice, s));
+              launch_decide(m, level, s, slot == nullptr);
+              if (slot) launch_verify(m, level, s, *slot); }
+            { ProfScope ps(m, P_PART, s); launch_partition(m, X, level, 0, s); }
+        }
+        if (!spec) break;
+        unsigned int flip;
+        { ProfScope ps(m, P_SPEC, s);
+          for (int l = 0; l < md; ++l)
+              if (ws.slots[l].pending) { GB_CUDA(cudaStreamWaitEvent(s, ws.slots[l].ev_done, 0)); ws.slots[l].pending = false; }
+          GB_CUDA(cudaMemcpyAsync(ws.h_spec_flag, ws.spec_flag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s)); }
+        GB_CUDA(cudaStreamSynchronize(s));
+        flip = *ws.h_spec_flag;
+        if (flip >= (unsigned int)md) break;
+        // the replay changed the decision of level `flip`: return to it
+        m.spec_rollbacks += 1;
+        { ProfScope ps(m, P_SPEC, s); launch_rollback(m, (int)flip, s); }
+        start = sync_level = (int)flip;
+        if (start > 0) ws.hist_p[(start + 1) & 1] = ws.hist_lv[start - 1].as<long long>();      // the parent level of the derived nodes
     }
+    ws.count_stats = true;
     { ProfScope ps(m, P_FIN, s); launch_finalize_tree(m, raw_grads, N, 0, s); }
     m.ens.n_trees += 1;   // host mirror; the exact n_leaves is read back by the caller (sync_ctl)
     m.ens.n_leaves_ub = (m.ens.n_leaves_ub > m.ens.n_leaves ? m.ens.n_leaves_ub : m.ens.n_leaves) + (1ll << md);

@@ -239,7 +239,7 @@ class GBRL:
         return float(loss.value)
 
     PROFILE_CLASSES = ("candidates", "binning", "preprocess", "histogram", "allreduce", "scan", "select_replay",
-                       "plan_decide", "partition", "finalize", "predict")
+                       "plan_decide", "partition", "finalize", "predict", "spec_wait")
 
     def profile(self, enable=True):
         _capi.check(self._lib.gbrl_b200_profile(self._h, 1 if enable else 0))
@@ -393,7 +393,8 @@ class GBRL:
         return {"kernel_launches": md.kernel_launches, "replay_items": md.replay_items, "replay_nodes": md.replay_nodes,
                 "replay_overflow": md.replay_overflow, "nodes_evaluated": md.nodes_evaluated, "max_noise_ratio": float(md.max_noise_ratio),
                 "n_trees": md.n_trees, "n_leaves": md.n_leaves, "chain_blocks_fast": md.chain_blocks_fast,
-                "chain_blocks_slow": md.chain_blocks_slow, "chain_lanes_seq": md.chain_lanes_seq, "replay_flips": md.replay_flips}
+                "chain_blocks_slow": md.chain_blocks_slow, "chain_lanes_seq": md.chain_lanes_seq, "replay_flips": md.replay_flips,
+                "spec_trees": md.spec_trees, "spec_rollbacks": md.spec_rollbacks}
 
     def get_ensemble_data(self):
         """binding.cpp:330-390: dict of owning NumPy arrays in the reference layout."""

@@ -59,7 +59,10 @@ typedef struct {
     int use_subtraction;    /* 1: histogram only the smaller child, derive the sibling from the parent */
     int hist_variant;       /* 0: streaming histogram kernel (cp.async row ring, carried shared histogram); 1: per-item kernel;
                                2: streaming kernel with 32-warp CTAs for output_dim == 1 (measured slower than the 24-warp default) */
-    int replay_variant;     /* 0: replay chains spread over the whole GPU where output_dim <= 2; 1: one CTA per replay item */
+    int replay_variant;     /* bit 0: 0 = replay chains spread over the whole GPU where output_dim <= 2, 1 = one CTA per replay item;
+                               bit 1: 0 = speculative levels (the tree keeps growing on the exact-tier winners while the chains of a
+                               level are walked on a side stream; a level whose decision the replay changes is rolled back),
+                               1 = every level waits for its replay */
 } gbrl_b200_config;
 
 typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine statistics */
@@ -78,6 +81,8 @@ typedef struct {           /* mirrors binding.cpp:309-328 get_metadata + engine 
     long long chain_blocks_slow; /* replay sub-blocks advanced piecewise (a binade change inside the block) */
     long long chain_lanes_seq;   /* lanes (R rows each) of those blocks that were run as a plain sequential float chain */
     long long replay_flips;      /* split decisions (greedy: nodes, oblivious: levels) in which the near-tie replay changed the exact-tier winner */
+    long long spec_trees;        /* trees grown with the replay chains off the critical path (speculative levels, see replay_variant) */
+    long long spec_rollbacks;    /* levels of those trees that were decided a second time because the replay changed their decision */
 } gbrl_b200_metadata;
 
 const char *gbrl_b200_last_error(void);

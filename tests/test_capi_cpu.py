@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_struct_layout_matches_header():
     from gbrl_b200 import _capi
     assert C.sizeof(_capi.Config) == 19 * 4
-    assert C.sizeof(_capi.Metadata) == 17 * 4 + 4 + 5 * 8 + 8 + 4 * 8   # 4 bytes padding before the int64 block, float + padding, 4 x int64
+    assert C.sizeof(_capi.Metadata) == 17 * 4 + 4 + 5 * 8 + 8 + 6 * 8   # 4 bytes padding before the int64 block, float + padding, 6 x int64
 
 
 def test_no_cpu_fallback():
