@@ -536,7 +536,7 @@ def bench_fit(wl, args, K, W, rank, world, local, with_e2e=True, with_exact=True
     return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 scores / int64 fixed-point sums",
             "data": "synthetic",
-            "config": {"workload": workload_name(wl), "parallelism": "histogram sharded over %d rank(s): feature tiles x row chunks, one exchange of the owned int64 slices per level" % world,
+            "config": {"workload": workload_name(wl), "parallelism": "histogram sharded over %d rank(s): feature tiles x row chunks, one int64 all-reduce of the level buffer per level" % world,
                        "l2": "inputs larger than L2 (code matrix %.0f MB + fp32 matrix %.0f MB per level pass)" % (
                            c["n"] * c["f"] * 2 / 1e6, c["n"] * c["f"] * 4 / 1e6),
                        "tie_replay": not args.no_replay, "ref_threads": cores},

@@ -1142,6 +1142,7 @@ struct DecideParams {
     int use_replay;              // 0: speculative decision on the exact-tier winner (the replay of this level is still running)
     int count_stats;             // 0: this level was counted already (second decision of a rolled-back level)
     int force_flip;              // tests (GBRL_B200_SPEC_FORCE_FLIP=1): speculate on a WRONG candidate wherever there is a choice
+    const unsigned int *abort_flag;   // speculative tree: lowest level known to need a second decision (0xffffffff: none)
 };
 
 // suffix sum over codes > j of feature f in the node's histogram (one warp)
@@ -1313,7 +1314,13 @@ __device__ void decide_oblivious_body(const DecideParams &P, NodeArrays na) {
 // One CTA: the split decisions of level `level` (fitter.cpp:338-371 / 448-477), then -- the children's segments and states
 // being known -- the histogram work items of level + 1 (plan.cuh).  One launch instead of three per level.
 __global__ void __launch_bounds__(1024) decide_plan_kernel(DecideParams P, NodeArrays na, PlanParams Q, int oblivious) {
-    if (oblivious) decide_oblivious_body(P, na);
+    // A speculative tree that is already known to return to a shallower level stops deciding: the nodes of this level stay
+    // open, no child is created, and every later kernel of the tree finds nothing to do.
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = (P.abort_flag != nullptr && *(volatile const unsigned int *)P.abort_flag < (unsigned int)P.level) ? 1 : 0;
+    __syncthreads();
+    if (s_abort) { /* nothing */ }
+    else if (oblivious) decide_oblivious_body(P, na);
     else {
         for (int p = threadIdx.x >> 5; p < P.nn; p += (int)(blockDim.x >> 5)) decide_greedy_node(P, na, p);
     }
@@ -1505,6 +1512,7 @@ static DecideParams decide_params(Model &m, int level) {
     P.ctl = ws.ctl.as<Ctl>(); P.ctl_stats = ws.ctl.as<Ctl>();
     P.state_snap = ws.state_snap.as<int>();
     P.use_replay = 1; P.count_stats = ws.count_stats ? 1 : 0; P.force_flip = 0;
+    P.abort_flag = nullptr;
     return P;
 }
 
@@ -1514,6 +1522,7 @@ void launch_decide(Model &m, int level, cudaStream_t s, bool use_replay) {
     DecideParams P = decide_params(m, level);
     P.use_replay = use_replay ? 1 : 0;
     P.force_flip = (!use_replay && force_flip) ? 1 : 0;
+    if (!use_replay) P.abort_flag = m.ws.spec_flag.as<unsigned int>();
     GB_LAUNCH(decide_plan_kernel, 1, 1024, 0, s, P, m.ws.na, plan_params(m), m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS ? 1 : 0);
 }
 

@@ -9,7 +9,11 @@ cap() {   # name, workload, kernel regex, skip, count
 cap hist_c2 c2 hist_stream 6 3
 cap walk_c2 c2 "wide_walk_kernel" 2 3
 cap dwalk_c2 c2 wide_dense_walk 1 2
+cap part_c2 c2 "part_" 12 2
+cap scan_c2 c2 "scan_kernel" 8 2
 cap tabs_c3 c3 "wide_tabs_kernel" 4 2
 cap hist_c3 c3 hist_stream 8 2
 cap bits_c3 c3 wide_bits 3 2
+cap hist_c5 c5 hist_stream 6 2
 cap predict_c4 c4 predict_tiles 1 1
+cap sel_c2 c2 "sel_pass_kernel" 0 3
