@@ -29,6 +29,8 @@ namespace gb {
 // X is read three times (coalesced 128-byte row segments); only a few per cent of the elements reach passes B / C.
 constexpr int SEL_D1 = 2048, SEL_D2 = 2048, SEL_D3 = 1024;
 constexpr int SEL_THREADS = 512;
+constexpr int SEL_MAP_STRIDE = SEL_D1 + 2;     // u16 per lane row of the digit-1 map: +1 word rotates the banks from lane to lane (ncu r02:
+                                               // 1.2e8 bank conflicts of 1.6e8 wavefronts without it -- all lanes probe similar digits)
 
 __device__ __forceinline__ uint32_t sel_key(float v) {
     const uint32_t u = __float_as_uint(v);
@@ -66,19 +68,20 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) sel_pass_kernel(SelParams P, i
     const int col = slab * 32 + lane;
     const bool has_col = col < P.F;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(P.N, r0 + rows_per_cta);
-    uint16_t *smap = reinterpret_cast<uint16_t *>(sm);                       // PASS >= 1: [32][SEL_D1] u16
-    unsigned int *skey = sm + 32 * SEL_D1 / 2;                               // PASS 2:    [32][B] sorted 22-bit prefixes
+    uint16_t *smap = reinterpret_cast<uint16_t *>(sm);                       // PASS >= 1: [32][SEL_MAP_STRIDE] u16
+    unsigned int *skey = sm + 32 * SEL_MAP_STRIDE / 2;                       // PASS 2:    [32][B + 1] sorted 22-bit prefixes
+    const int kstride = P.B + 1;
     if (PASS == 0) {
         for (int i = threadIdx.x; i < SEL_D1 * 16; i += SEL_THREADS) sm[i] = 0u;
     } else {
         for (int i = threadIdx.x; i < 32 * SEL_D1; i += SEL_THREADS) {
             const int c = i / SEL_D1, d = i - c * SEL_D1;
-            smap[i] = (slab * 32 + c < P.F) ? P.map1[(size_t)(slab * 32 + c) * SEL_D1 + d] : (uint16_t)0xffff;
+            smap[c * SEL_MAP_STRIDE + d] = (slab * 32 + c < P.F) ? P.map1[(size_t)(slab * 32 + c) * SEL_D1 + d] : (uint16_t)0xffff;
         }
         if (PASS == 2) {
             for (int i = threadIdx.x; i < 32 * P.B; i += SEL_THREADS) {
                 const int c = i / P.B, b = i - c * P.B;
-                skey[i] = (slab * 32 + c < P.F) ? P.key2[(size_t)(slab * 32 + c) * P.B + b] : 0xffffffffu;
+                skey[c * kstride + b] = (slab * 32 + c < P.F) ? P.key2[(size_t)(slab * 32 + c) * P.B + b] : 0xffffffffu;
             }
         }
     }
@@ -99,14 +102,14 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) sel_pass_kernel(SelParams P, i
             if (PASS == 0) {
                 atomicAdd(&sm[d1 * 16 + (lane >> 1)], (lane & 1) ? 0x10000u : 1u);
             } else {
-                const unsigned int ld = smap[lane * SEL_D1 + d1];
+                const unsigned int ld = smap[lane * SEL_MAP_STRIDE + d1];
                 if (ld == 0xffffu) continue;
                 if (PASS == 1) {
                     atomicAdd(&P.hist2[((size_t)col * P.B + ld) * SEL_D2 + ((k >> 10) & 0x7ffu)], 1u);
                 } else {
                     // first target whose 22-bit prefix equals this element's (targets ascending): lower bound from the digit-1 leader on
                     const uint32_t pre = k >> 10;
-                    const unsigned int *kc = skey + lane * P.B;
+                    const unsigned int *kc = skey + lane * kstride;
                     int lo = (int)ld, hi = P.B;
                     while (lo < hi) { const int mid = (lo + hi) >> 1; if (kc[mid] < pre) lo = mid + 1; else hi = mid; }
                     if (lo < P.B && kc[lo] == pre) atomicAdd(&P.hist3[((size_t)col * P.B + lo) * SEL_D3 + (k & 0x3ffu)], 1u);
@@ -298,7 +301,7 @@ void compute_thresholds(Model &m, const float *X, int N, int F, cudaStream_t s) 
         if (ctas < 1) ctas = 1;
         const int rows_per_cta = ceil_div(N, ctas);
         dim3 grid(ceil_div(N, rows_per_cta), slabs);
-        const size_t sm0 = (size_t)SEL_D1 * 16 * 4, sm1 = (size_t)32 * SEL_D1 * 2, sm2 = sm1 + (size_t)32 * B * 4;
+        const size_t sm0 = (size_t)SEL_D1 * 16 * 4, sm1 = (size_t)32 * SEL_MAP_STRIDE * 2, sm2 = sm1 + (size_t)32 * (B + 1) * 4;
         ensure_dyn_smem(sel_pass_kernel<0>, sm0); ensure_dyn_smem(sel_pass_kernel<1>, sm1); ensure_dyn_smem(sel_pass_kernel<2>, sm2);
         GB_LAUNCH(sel_pass_kernel<0>, grid, SEL_THREADS, sm0, s, P, rows_per_cta);
         GB_LAUNCH(sel_scan1_kernel, F, 256, 0, s, P);

@@ -37,6 +37,12 @@ void ensure_dyn_smem_impl(const void *func, size_t bytes) {
     done[key] = bytes;
 }
 
+int replay_grid_mult(bool side_stream) {
+    static const int env = getenv("GBRL_B200_SIDE_GRID") ? atoi(getenv("GBRL_B200_SIDE_GRID")) : 0;
+    if (!side_stream) return 8;
+    return env > 0 ? env : 32;
+}
+
 // ---------------------------------------------------------------- DevBuf
 void DevBuf::ensure(size_t n, bool keep, cudaStream_t s) {
     if (n <= bytes && p) return;

@@ -66,6 +66,11 @@ __host__ __device__ inline int level_of(int h) {
 }
 __host__ __device__ inline int level_base(int l) { return (1 << l) - 1; }
 
+// CTAs per SM of the grid-stride replay kernels (gather / side bits / summaries).  On a side stream (speculative levels) they are
+// launched as MANY SHORT CTAs: stream priorities act when a CTA is dispatched, so the shorter the side CTAs live, the sooner
+// a histogram or partition launch of the main stream gets its SMs.  GBRL_B200_SIDE_GRID overrides (tuning).
+int replay_grid_mult(bool side_stream);
+
 #if defined(__CUDACC__)
 __device__ __forceinline__ float warp_bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ int warp_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }

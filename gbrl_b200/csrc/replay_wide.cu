@@ -525,7 +525,7 @@ template <int D>
 static void launch_wide_d(Model &m, const ReplayParams &R, const StreamParams &S, const WideParams &Wd, cudaStream_t s) {
     Workspace &ws = m.ws;
     Ctl *ctl = ws.ctl.as<Ctl>();
-    const int grid = ws.n_sms * 8;
+    const int grid = ws.n_sms * replay_grid_mult(R.ctl != ws.ctl.as<Ctl>());      // side stream <=> the control block is a snapshot
     GB_LAUNCH((wide_bits_kernel<D>), grid, 256, 0, s, R, ws.na, S, Wd);
     GB_LAUNCH((wide_prefix_kernel<D>), ws.n_sms, 256, 0, s, R, ws.na, S, Wd);
     GB_LAUNCH((wide_tabs_kernel<D, 0>), grid, 256, 0, s, R, ws.na, S, Wd);

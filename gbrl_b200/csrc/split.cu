@@ -391,18 +391,33 @@ __global__ void __launch_bounds__(256) obl_reduce_kernel(OblParams P, NodeArrays
     if (threadIdx.x == 0) P.blk_best[blockIdx.x] = make_float2(s_gain[0], __int_as_float(s_idx[0]));
 }
 
-__global__ void __launch_bounds__(256) obl_select_kernel(OblParams P, NodeArrays na) {
+__global__ void __launch_bounds__(1024) obl_select_kernel(OblParams P, NodeArrays na) {
     __shared__ float s_best, s_band;
     __shared__ int s_besti, s_count, s_w, s_ok;
+    __shared__ float r_g[32];
+    __shared__ int r_i[32];
     const int base = level_base(P.level);
     if (na.state[base] != NODE_OPEN) return;    // tree already stopped
-    if (threadIdx.x == 0) {
+    {
+        // arg-max over the per-block bests (lowest candidate index on ties)
         float g = -INFINITY; int bi = INT_MAX;
-        for (int b = 0; b < P.nblocks; ++b) {
+        for (int b = threadIdx.x; b < P.nblocks; b += blockDim.x) {
             const float2 v = P.blk_best[b];
             const int i = __float_as_int(v.y);
             if (v.x > -INFINITY && better(v.x, i, g, bi)) { g = v.x; bi = i; }
         }
+        for (int off = 16; off > 0; off >>= 1) {
+            const float og = __shfl_down_sync(0xffffffffu, g, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+            if (better(og, oi, g, bi)) { g = og; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { r_g[threadIdx.x >> 5] = g; r_i[threadIdx.x >> 5] = bi; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float g = r_g[0]; int bi = r_i[0];
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); ++w2)
+            if (better(r_g[w2], r_i[w2], g, bi)) { g = r_g[w2]; bi = r_i[w2]; }
         s_best = g; s_besti = (bi == INT_MAX) ? -1 : bi; s_count = 0; s_w = 0; s_ok = 0;
         P.ctl->obl_best = g; P.ctl->obl_best_idx = s_besti; P.ctl->obl_has_replay = 0;
         atomicAdd((unsigned long long *)&P.ctl->stat_nodes_evaluated, (unsigned long long)P.nn);
@@ -1435,7 +1450,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         P.rev_map = m.rev_num_map.as<int>(); P.obl_tot = ws.obl_tot.as<float>(); P.obl_nb = ws.obl_tot.as<float>() + C;
         P.blk_best = ws.tile_best.as<float2>(); P.replay = ws.replay.as<ReplayItem>(); P.obl_cands = obl_cands; P.ctl = ctl;
         GB_LAUNCH(obl_reduce_kernel, P.nblocks, 256, 0, s, P, ws.na);
-        GB_LAUNCH(obl_select_kernel, 1, 256, 0, s, P, ws.na);
+        GB_LAUNCH(obl_select_kernel, 1, 1024, 0, s, P, ws.na);
     }
     if (!m.cfg.tie_replay) return;
     const Ctl *rctl = ctl;         // what the replay kernels read the item count from
@@ -1469,7 +1484,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         S.nid = ws.nid.as<int>();
         S.wide = (D <= 2 && (m.cfg.replay_variant & 1) == 0) ? 1 : 0;
         GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, rs, R, ws.na, S);
-        GB_LAUNCH(replay_gather_kernel, ws.n_sms * 8, 256, 0, rs, R, ws.na, S);
+        GB_LAUNCH(replay_gather_kernel, ws.n_sms * replay_grid_mult(slot != nullptr), 256, 0, rs, R, ws.na, S);
         if (S.wide) {
             // chains spread over the whole GPU (replay_wide.cu); items whose plane did not fit are gathered directly
             launch_replay_wide(m, R, S, rs);
@@ -1477,7 +1492,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
             else GB_LAUNCH((replay_par_kernel<2>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
             return;
         }
-        GB_LAUNCH(replay_bits_kernel, ws.n_sms * 8, 256, 0, rs, R, ws.na, S);
+        GB_LAUNCH(replay_bits_kernel, ws.n_sms * replay_grid_mult(slot != nullptr), 256, 0, rs, R, ws.na, S);
         if (D <= 1) {
             launch_stream<1>(R, ws.na, S, ctl, ws.n_sms, rs);
             GB_LAUNCH((replay_par_kernel<1>), ws.n_sms * 2, 512, 0, rs, R, ws.na, ctl, S.mode, ws.replay_cap);
