@@ -66,9 +66,10 @@ __host__ __device__ inline int level_of(int h) {
 }
 __host__ __device__ inline int level_base(int l) { return (1 << l) - 1; }
 
-// CTAs per SM of the grid-stride replay kernels (gather / side bits / summaries).  On a side stream (speculative levels) they are
-// launched as MANY SHORT CTAs: stream priorities act when a CTA is dispatched, so the shorter the side CTAs live, the sooner
-// a histogram or partition launch of the main stream gets its SMs.  GBRL_B200_SIDE_GRID overrides (tuning).
+// CTAs per SM of the grid-stride replay kernels (gather / side bits / summaries).  GBRL_B200_SIDE_GRID overrides it for the
+// launches on a side stream (speculative levels): stream priorities act when a CTA is dispatched, so shorter-lived side CTAs
+// could give way to the main stream sooner -- measured, it makes no difference (the histogram kernel shares issue slots, not
+// dispatch order, with the replay).
 int replay_grid_mult(bool side_stream);
 
 #if defined(__CUDACC__)
