@@ -227,8 +227,19 @@ struct DenseWide {
     long long n_elements; int D, T, mode;
     double *bsum; float *pred; int4 *tab; float *tag;      // [chains][gmax]
     int gmax;
+    // memoised sequential evaluation of the RISKY groups (see wide_dense_cand_kernel)
+    int *ridx;             // [chains][gmax] row of the group in `cand`, -1: none
+    int *rlist;            // [rcap] group (chain * gmax + g) of every row
+    int *rcount;           // rows handed out
+    float *cand;           // [rcap][2 * DW_K] chain value after the group for the start  pred + (k - DW_K) * ulp(pred)
+    int rcap;
 };
 constexpr float DW_EMPTY = -1.0f;
+constexpr int DW_K = 1024;             // candidate starts on each side of the predicted running sum
+
+// the k-th candidate start of a group whose predicted running sum is `pred` (ulp `u` of its binade); used by the
+// simulation and by the walk, which only accepts a candidate that equals its running sum BIT FOR BIT
+__device__ __forceinline__ float dw_candidate(float pred, float u, int k) { return pred + (float)k * u; }
 
 struct DenseChain { long long first, cnt; int ng; };
 __device__ __forceinline__ DenseChain dense_chain_of(const DenseWide &P, int chain) {
@@ -337,14 +348,65 @@ __global__ void __launch_bounds__(256) wide_dense_tabs_kernel(DenseWide P) {
         float inv_u, uu;
         const bool ok = seq::epoch_of(P.pred[(size_t)chain * P.gmax + g], inv_u, uu);
         float tagv = ok ? inv_u : 0.0f;
+        int row = -1;
         if (!__any_sync(0xffffffffu, nz)) {
             tagv = DW_EMPTY;
             if (lane == 0) P.tab[(size_t)chain * P.gmax + g] = make_int4(0, 0, 0, 0);
         } else if (ok) {
             const seq::Tab tb = seq::warp_summarize<8>(x, inv_u);
-            if (lane == 0) P.tab[(size_t)chain * P.gmax + g] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+            if (lane == 0) {
+                P.tab[(size_t)chain * P.gmax + g] = make_int4(tb.a0, tb.a1, tb.mn, tb.mx);
+                // risky: the summary does not hold for every running sum within DW_K ulps of the prediction (the sum passes a
+                // power of two inside the group, or close to it) -> its outcome is memoised for the candidate starts instead
+                const float pr = P.pred[(size_t)chain * P.gmax + g];
+                const long long mm = (long long)(pr * inv_u);
+                const long long lo = (1 << 23) + seq::MARGIN + DW_K, hi = (1 << 24) - seq::MARGIN - DW_K;
+                const bool safe = mm > 0 ? (mm + tb.mn > lo && mm + tb.mx < hi) : (mm + tb.mx < -lo && mm + tb.mn > -hi);
+                if (!safe && P.rcap > 0) {
+                    const int r = atomicAdd(P.rcount, 1);
+                    if (r < P.rcap) { row = r; P.rlist[r] = (int)((size_t)chain * P.gmax + g); }
+                }
+            }
         }
-        if (lane == 0) P.tag[(size_t)chain * P.gmax + g] = tagv;
+        if (lane == 0) { P.tag[(size_t)chain * P.gmax + g] = tagv; P.ridx[(size_t)chain * P.gmax + g] = row; }
+    }
+}
+
+// Memoised sequential evaluation: for every risky group, the plain float chain over its 256 elements from each of the 2 * DW_K
+// candidate starts around the predicted running sum -- embarrassingly parallel (one lane per candidate, elements broadcast from
+// shared memory), ~0.5 M dependent adds per group.  The walk then replaces the 256 dependent adds of such a group by ONE lookup
+// when its running sum is one of the candidates; by construction the stored value is what the sequential chain yields from
+// exactly that start, so nothing about binades or rounding has to hold for it to be right.
+__global__ void __launch_bounds__(256) wide_dense_cand_kernel(DenseWide P) {
+    __shared__ __align__(16) float s_x[256];
+    const int n_rows = min(*P.rcount, P.rcap);
+    for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
+        const int cg = P.rlist[r];
+        const int chain = cg / P.gmax, g = cg - chain * P.gmax;
+        const DenseChain c = dense_chain_of(P, chain);
+        {
+            const long long j = (long long)g * 256 + threadIdx.x;
+            float v = 0.0f;
+            if (j < c.cnt) { v = P.mat[c.first + j * P.D]; if (P.mode == 1) v = v * v; }
+            __syncthreads();
+            s_x[threadIdx.x] = v;
+            __syncthreads();
+        }
+        const float pr = P.pred[cg];
+        float inv_u, u;
+        seq::epoch_of(pr, inv_u, u);               // risky groups always have a binade (wide_dense_tabs_kernel)
+        float acc[2 * DW_K / 256];
+#pragma unroll
+        for (int q = 0; q < 2 * DW_K / 256; ++q) acc[q] = dw_candidate(pr, u, (int)threadIdx.x + q * 256 - DW_K);
+        const float4 *xs = reinterpret_cast<const float4 *>(s_x);
+#pragma unroll 4
+        for (int i = 0; i < 64; ++i) {
+            const float4 e = xs[i];
+#pragma unroll
+            for (int q = 0; q < 2 * DW_K / 256; ++q) { acc[q] = acc[q] + e.x; acc[q] = acc[q] + e.y; acc[q] = acc[q] + e.z; acc[q] = acc[q] + e.w; }
+        }
+#pragma unroll
+        for (int q = 0; q < 2 * DW_K / 256; ++q) P.cand[(size_t)r * 2 * DW_K + threadIdx.x + q * 256] = acc[q];
     }
 }
 
@@ -357,8 +419,9 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
     float acc = 0.0f;
     int n_fast = 0, n_slow = 0, n_seq = 0;
     int4 qnx = make_int4(0, 0, 0, 0);
-    float tgnx = 0.0f;
-    if (lane < c.ng) { qnx = P.tab[base + lane]; tgnx = P.tag[base + lane]; }
+    float tgnx = 0.0f, prnx = 0.0f;
+    int rinx = -1;
+    if (lane < c.ng) { qnx = P.tab[base + lane]; tgnx = P.tag[base + lane]; rinx = P.ridx[base + lane]; prnx = P.pred[base + lane]; }
     float pa[8], pb[8];                                   // rows of two groups fetched ahead of need
     int ha = -1, hb = -1;                                 // which groups they are
 #pragma unroll 1
@@ -366,8 +429,13 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
         const bool in_range = w0 + lane < c.ng;
         const int wn = min(32, c.ng - w0);
         const int4 q = qnx;
-        const float tg = tgnx;
-        if (w0 + 32 + lane < c.ng) { qnx = P.tab[base + w0 + 32 + lane]; tgnx = P.tag[base + w0 + 32 + lane]; }
+        const float tg = tgnx, prw = prnx;
+        const int riw = rinx;
+        rinx = -1;
+        if (w0 + 32 + lane < c.ng) {
+            qnx = P.tab[base + w0 + 32 + lane]; tgnx = P.tag[base + w0 + 32 + lane];
+            rinx = P.ridx[base + w0 + 32 + lane]; prnx = P.pred[base + w0 + 32 + lane];
+        }
         int first = 0;
 #pragma unroll 1
         while (first < wn) {
@@ -414,6 +482,23 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
             // rows of the failed group; the two groups after it are fetched now (a sum that hovers around a power of two
             // fails group after group, and a lone warp has nothing else to hide the load latency behind)
             const int gq = w0 + first;
+            {
+                // memoised outcome of this group for the candidate start that IS the running sum, if there is one
+                const int row = __shfl_sync(full, riw, first);
+                const float pr = __shfl_sync(full, prw, first);
+                float pinv, pu;
+                if (row >= 0 && seq::epoch_of(pr, pinv, pu)) {
+                    const float kf = rintf((acc - pr) * pinv);
+                    if (fabsf(kf) < (float)DW_K) {
+                        const int k = (int)kf;
+                        if (dw_candidate(pr, pu, k) == acc) {
+                            acc = __ldcg(P.cand + (size_t)row * 2 * DW_K + (k + DW_K));
+                            ++n_fast; ++first;
+                            continue;
+                        }
+                    }
+                }
+            }
             float x[8];
             if (ha == gq) {
 #pragma unroll
@@ -462,12 +547,21 @@ static void launch_ref_chain(Model *m, float *mat, const float *mean, float *par
     const long long longest = (ne - (long long)(T - 1) * ept + D - 1) / D + 1;      // the last thread takes the remainder
     P.gmax = (int)((longest + 255) / 256) + 1;
     const size_t per = (size_t)T * D * P.gmax;
-    scratch.ensure(per * (sizeof(double) + sizeof(int4) + 2 * sizeof(float)));
+    // memo rows: every group may be risky on a short chain; long inputs get a 64 MB budget (groups beyond it run sequentially)
+    size_t rcap = per;
+    if (rcap > ((size_t)64 << 20) / (2 * DW_K * sizeof(float))) rcap = ((size_t)64 << 20) / (2 * DW_K * sizeof(float));
+    scratch.ensure(per * (sizeof(double) + sizeof(int4) + 2 * sizeof(float) + sizeof(int)) + rcap * (sizeof(int) + 2 * DW_K * sizeof(float)) + 64);
     char *p = scratch.as<char>();
     P.tab = reinterpret_cast<int4 *>(p); p += per * sizeof(int4);       // 16-byte entries first (alignment)
     P.bsum = reinterpret_cast<double *>(p); p += per * sizeof(double);
+    P.cand = reinterpret_cast<float *>(p); p += rcap * 2 * DW_K * sizeof(float);
     P.pred = reinterpret_cast<float *>(p); p += per * sizeof(float);
-    P.tag = reinterpret_cast<float *>(p);
+    P.tag = reinterpret_cast<float *>(p); p += per * sizeof(float);
+    P.ridx = reinterpret_cast<int *>(p); p += per * sizeof(int);
+    P.rlist = reinterpret_cast<int *>(p); p += rcap * sizeof(int);
+    P.rcount = reinterpret_cast<int *>(p);
+    P.rcap = (int)rcap;
+    GB_CUDA(cudaMemsetAsync(P.rcount, 0, sizeof(int), s));
     long long units = (long long)per;
     int grid = (int)((units + 7) / 8);
     if (grid > 148 * 16) grid = 148 * 16;
@@ -475,6 +569,7 @@ static void launch_ref_chain(Model *m, float *mat, const float *mean, float *par
     GB_LAUNCH(wide_dense_sums_kernel, grid, 256, 0, s, P);
     GB_LAUNCH(wide_dense_prefix_kernel, T * D, 32, 0, s, P);
     GB_LAUNCH(wide_dense_tabs_kernel, grid, 256, 0, s, P);
+    GB_LAUNCH(wide_dense_cand_kernel, 148 * 4, 256, 0, s, P);
     GB_LAUNCH(wide_dense_walk_kernel, T * D, 32, 0, s, P, stats);
 }
 

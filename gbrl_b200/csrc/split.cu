@@ -258,6 +258,7 @@ struct SelectParams {
     const float2 *tile_best;
     ReplayItem *replay;
     float *replay_exact;      // exact-tier score of every replay item (0 for parent items): calibration statistic of the band
+    int *state_snap;          // speculative trees: node states before the level's decision (nullptr otherwise)
     Ctl *ctl;
 };
 
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(1024) select_greedy_kernel(SelectParams P, Nod
     __shared__ float s_best;
     __shared__ int s_besti, s_count, s_begin, s_w;
     const int p = blockIdx.x, h = level_base(P.level) + p;
+    if (P.state_snap != nullptr && threadIdx.x == 0) P.state_snap[h] = na.state[h];
     if (na.state[h] != NODE_OPEN) return;
     {
         // arg-max over the per-feature bests (lowest candidate index on ties)
@@ -354,6 +356,7 @@ struct OblParams {
     float2 *blk_best;          // [nblocks]
     ReplayItem *replay;
     int *obl_cands;            // candidate list of replay (stored after the items, see launcher)
+    int *state_snap;           // speculative trees: node states before the level's decision (nullptr otherwise)
     Ctl *ctl;
 };
 
@@ -397,6 +400,8 @@ __global__ void __launch_bounds__(1024) obl_select_kernel(OblParams P, NodeArray
     __shared__ float r_g[32];
     __shared__ int r_i[32];
     const int base = level_base(P.level);
+    if (P.state_snap != nullptr)
+        for (int p = threadIdx.x; p < P.nn; p += blockDim.x) P.state_snap[base + p] = na.state[base + p];
     if (na.state[base] != NODE_OPEN) return;    // tree already stopped
     {
         // arg-max over the per-block bests (lowest candidate index on ties)
@@ -1341,6 +1346,7 @@ __global__ void __launch_bounds__(1024) decide_plan_kernel(DecideParams P, NodeA
     }
     __threadfence_block();
     __syncthreads();
+    if (threadIdx.x == 0) P.ctl->n_replay = 0;      // the replay list of the next level starts empty (select_*_kernel appends)
     if (P.level + 1 < P.max_depth)
         plan_level_body(na, P.ctl, Q.items, Q.items_cap, P.level + 1, Q.max_depth, Q.nT_local, Q.use_subtraction, Q.oblivious, Q.row_groups,
                         Q.row_group, Q.item_rows_max);
@@ -1430,7 +1436,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
     const bool obl = m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS;
     const int C = ws.F * ws.B, nn = 1 << level;
     Ctl *ctl = ws.ctl.as<Ctl>();
-    GB_CUDA(cudaMemsetAsync(&ctl->n_replay, 0, sizeof(int), s));
+    // (ctl->n_replay is zero here: init_nodes_kernel for level 0, the decide + plan kernel of the level before otherwise)
     // default band: 6 noise units.  The largest noise ever observed on a replayed candidate is 1.35 units (max_noise_ratio), so two
     // candidates can swap when they are <= 2.7 units apart; the observed spread (sigma ~ 0.35 units) puts 6 units at > 12 sigma.
     const float kappa = m.cfg.band_kappa > 0 ? m.cfg.band_kappa : 6.0f;
@@ -1441,6 +1447,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         P.replay_cap = ws.replay_cap; P.kappa = kappa; P.scores = ws.scores.as<float>();
         P.cand_flags = ws.cand_flags.as<uint8_t>(); P.tile_best = ws.tile_best.as<float2>();
         P.replay = ws.replay.as<ReplayItem>(); P.replay_exact = ws.replay_scores.as<float>() + ws.replay_cap; P.ctl = ctl;
+        P.state_snap = ws.spec ? ws.state_snap.as<int>() : nullptr;
         GB_LAUNCH(select_greedy_kernel, nn, 1024, 0, s, P, ws.na);
     } else {
         OblParams P;
@@ -1449,6 +1456,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         P.scores = ws.scores.as<float>(); P.cand_flags = ws.cand_flags.as<uint8_t>(); P.fw = m.feature_weights.as<float>();
         P.rev_map = m.rev_num_map.as<int>(); P.obl_tot = ws.obl_tot.as<float>(); P.obl_nb = ws.obl_tot.as<float>() + C;
         P.blk_best = ws.tile_best.as<float2>(); P.replay = ws.replay.as<ReplayItem>(); P.obl_cands = obl_cands; P.ctl = ctl;
+        P.state_snap = ws.spec ? ws.state_snap.as<int>() : nullptr;
         GB_LAUNCH(obl_reduce_kernel, P.nblocks, 256, 0, s, P, ws.na);
         GB_LAUNCH(obl_select_kernel, 1, 1024, 0, s, P, ws.na);
     }

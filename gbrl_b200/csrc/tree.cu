@@ -332,9 +332,7 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
             SlotBind bind(ws, slot);
             ws.count_stats = level != sync_level;
             { ProfScope ps(m, P_SELECT, s); launch_select_and_replay(m, X, level, s, slot); }
-            { ProfScope ps(m, P_DECIDE, s);
-              if (spec) GB_CUDA(cudaMemcpyAsync(ws.state_snap.as<int>() + level_base(level), ws.na.state + level_base(level),
-                                                sizeof(int) << level, cudaMemcpyDeviceToDevice, s));
+            { ProfScope ps(m, P_DECIDE, s);      // (the node states of the level were snapshotted by the selection kernel)
               launch_decide(m, level, s, slot == nullptr);
               if (slot) launch_verify(m, level, s, *slot); }
             { ProfScope ps(m, P_PART, s); launch_partition(m, X, level, 0, s); }

@@ -222,6 +222,50 @@ def test_determinism_run_to_run():
     assert np.array_equal(outs[0][1], outs[1][1])
 
 
+@pytest.mark.parametrize("grow,score", [("greedy", "L2"), ("oblivious", "cosine"), ("greedy", "cosine"), ("oblivious", "L2")])
+def test_discrete_features_and_exact_ties(grow, score):
+    """Small-integer features, a constant column and an exact copy of a column: most quantile thresholds are duplicates and many
+    candidates describe the SAME partition, so the arg-max is decided by the reference's rule for exact ties (lowest candidate
+    index, fitter.cpp:338-356 / 427-445) and by the path guard (node.cpp:154-166), not by score differences."""
+    n, f, d = 6000, 9, 2
+    rng = np.random.default_rng(5)
+    X = rng.integers(0, 4, size=(n, f)).astype(np.float32)
+    X[:, 2] = 7.0                         # constant column: n_bins equal thresholds, every candidate has an empty side
+    X[:, 6] = X[:, 1]                     # exact copy: candidates of column 6 tie with those of column 1
+    X[:, 4] = rng.standard_normal(n).astype(np.float32)
+    y = (np.stack([X[:, 1] - X[:, 3], X[:, 4] * (X[:, 0] > 1)], 1) + 0.05 * rng.standard_normal((n, d))).astype(np.float32)
+    kw = dict(input_dim=f, output_dim=d, max_depth=5, n_bins=64, par_th=10, split_score_func=score, generator_type="quantile",
+              batch_size=n, grow_policy=grow)
+    o, g = _pair(**kw)
+    boosting_loop([o, g], X, y, 4)
+    assert g.m.get_stats()["replay_overflow"] == 0
+
+
+def test_targets_with_huge_dynamic_range():
+    """Gradients spanning 12 decades and exactly-zero gradients: the fixed-point scale of the histogram is taken from max |g|, so
+    tiny gradients quantise to 0 in the exact tier -- the replay tier and the leaf values (raw gradients) must still be the reference's."""
+    n, f, d = 5000, 8, 1
+    X, y = synth(n, f, d, 77)
+    y = y.copy()
+    y[::7] *= 1e6
+    y[1::7] *= 1e-6
+    y[2::7] = 0.0
+    kw = dict(input_dim=f, output_dim=d, max_depth=4, n_bins=128, par_th=10, split_score_func="L2", generator_type="quantile",
+              batch_size=n, grow_policy="greedy")
+    o, g = _pair(**kw)
+    n_, d_ = y.shape
+    for it in range(3):                    # leaf values reach 1e5: compare relative to their magnitude
+        po = np.asarray(o.predict(X)).reshape(n_, d_)
+        grad = (po - y).astype(np.float32)
+        o.step(X, grad); g.step(X, grad)
+        eo, eg = o.ensemble(), g.ensemble()
+        for k in ("tree_indices", "depths", "feature_indices", "inequality_directions"):
+            assert np.array_equal(np.asarray(eo[k]).astype(np.int64), np.asarray(eg[k]).astype(np.int64)), (it, k)
+        assert np.array_equal(np.asarray(eo["feature_values"]), np.asarray(eg["feature_values"]))
+        vo, vg = np.asarray(eo["values"], np.float64), np.asarray(eg["values"], np.float64).reshape(np.asarray(eo["values"]).shape)
+        assert np.all(np.abs(vo - vg) <= TOL * np.maximum(1.0, np.abs(vo))), np.abs(vo - vg).max()
+
+
 @pytest.mark.parametrize("n", [1, 2, 37, 300])
 def test_tiny_inputs(n):
     """n_samples below n_bins+1 (quantile ranks collapse), single-sample nodes, empty children."""
