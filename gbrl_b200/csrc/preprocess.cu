@@ -527,6 +527,148 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
     }
 }
 
+
+// ---------------------------------------------------------------- memo walk (mean chains)
+// The mean chain of zero-mean gradients is a random walk: |s| ~ sigma sqrt(k), so the running sum touches a power of two in 40 % of
+// the 256-element groups of a 62 500-element chain and every summary fails there (chains).  What does NOT depend on
+// binades is the plain sequential chain itself, and how far the actual running sum is from its exact-arithmetic prediction is a
+// slow random walk of rounding errors (~0.3 ulp per add: a few ulps per group, tens of ulps per chain).  So EVERY group is
+// evaluated sequentially for 2 * MW_K candidate starts around its predicted incoming sum -- one lane per candidate, all groups of all
+// chains at once: ~1 G independent adds, tens of microseconds for the whole GPU -- and the chain warp only looks its running sum
+// up: one group per ~250 cycles instead of 256 dependent adds.  The segment of the table around the current deviation is fetched
+// MW_PF groups ahead with cp.async, so that the lookup is a shared-memory read.  A start that is not in the table (or not on the
+// candidate grid) falls back to the sequential chain, which is right by definition; a candidate is accepted only when it EQUALS the
+// running sum bit for bit, so the result is the reference's sequential sum whatever the prediction was.
+constexpr int MW_K = 512;             // candidates on each side of the prediction
+constexpr int MW_SEG = 64;            // candidates per prefetched segment
+constexpr int MW_PF = 6;              // groups of lookahead
+
+// candidate spacing of a group: the ulp of the prediction's binade, or half of it when the candidates reach below that binade
+// (sums below the power of two live on the finer grid; on the coarser side every grid point is still a candidate)
+__device__ __forceinline__ bool mw_grid(float pred, float &step, float &inv_step) {
+    float inv_u, u;
+    if (!seq::epoch_of(pred, inv_u, u)) return false;
+    const bool fine = fabsf(pred * inv_u) < 8388608.0f + (float)MW_K;
+    step = fine ? 0.5f * u : u;
+    inv_step = fine ? 2.0f * inv_u : inv_u;
+    return true;
+}
+__device__ __forceinline__ float mw_candidate(float pred, float step, int k) { return pred + (float)k * step; }
+
+// one CTA per group: 2 * MW_K sequential chains over the group's 256 elements (4 per thread, elements broadcast from shared memory)
+__global__ void __launch_bounds__(256) dense_memo_sim_kernel(DenseWide P) {
+    __shared__ __align__(16) float s_x[256];
+    const int n_chains = P.T * P.D;
+    const long long total = (long long)n_chains * P.gmax;
+    for (long long cg = blockIdx.x; cg < total; cg += gridDim.x) {
+        const int chain = (int)(cg / P.gmax), g = (int)(cg - (long long)chain * P.gmax);
+        const DenseChain c = dense_chain_of(P, chain);
+        if (g >= c.ng) continue;                       // uniform over the CTA
+        float step, inv_step;
+        const float pr = P.pred[cg];
+        if (!mw_grid(pr, step, inv_step)) continue;    // no binade (start of the chain, tiny sums): the walk runs these sequentially
+        {
+            const long long j = (long long)g * 256 + threadIdx.x;
+            float v = 0.0f;
+            if (j < c.cnt) v = P.mat[c.first + j * P.D];
+            __syncthreads();
+            s_x[threadIdx.x] = v;
+            __syncthreads();
+        }
+        constexpr int Q = 2 * MW_K / 256;
+        float acc[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) acc[q] = mw_candidate(pr, step, (int)threadIdx.x + q * 256 - MW_K);
+        const float4 *xs = reinterpret_cast<const float4 *>(s_x);
+#pragma unroll 4
+        for (int i = 0; i < 64; ++i) {
+            const float4 e = xs[i];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) { acc[q] = acc[q] + e.x; acc[q] = acc[q] + e.y; acc[q] = acc[q] + e.z; acc[q] = acc[q] + e.w; }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) P.cand[(size_t)cg * 2 * MW_K + threadIdx.x + q * 256] = acc[q];
+    }
+}
+
+__device__ __forceinline__ void mw_cp_async_4(unsigned int dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// one warp per chain
+__global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long long *stats) {
+    __shared__ __align__(16) float s_wbuf[256];
+    __shared__ float s_seg[MW_PF][MW_SEG];
+    __shared__ int s_k0[MW_PF];
+    const unsigned int full = 0xffffffffu;
+    const int chain = blockIdx.x, lane = threadIdx.x;
+    const DenseChain c = dense_chain_of(P, chain);
+    const size_t base = (size_t)chain * P.gmax;
+    float acc = 0.0f;
+    int n_fast = 0, n_slow = 0, n_seq = 0;
+    // segment of group gp around deviation `dev` (absolute, = running sum - prediction of the group the walk is at)
+    auto prefetch = [&](int gp, float dev) {
+        if (gp < c.ng) {
+            const float pr = P.pred[base + gp];
+            float step, inv_step;
+            int k0 = -MW_K;
+            if (mw_grid(pr, step, inv_step)) {
+                const float kc = rintf(dev * inv_step);
+                k0 = (int)fminf(fmaxf(kc - (float)(MW_SEG / 2), (float)-MW_K), (float)(MW_K - MW_SEG));
+            }
+            const float *src = P.cand + (base + gp) * 2 * MW_K + (k0 + MW_K);
+            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(&s_seg[gp % MW_PF][0]);
+            mw_cp_async_4(dst + lane * 4, src + lane);
+            mw_cp_async_4(dst + (lane + 32) * 4, src + lane + 32);
+            if (lane == 0) s_k0[gp % MW_PF] = k0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll 1
+    for (int gp = 0; gp < MW_PF; ++gp) prefetch(gp, 0.0f);
+    float prw = 0.0f;                                        // predictions of the current window of 32 groups (lane = group)
+#pragma unroll 1
+    for (int g = 0; g < c.ng; ++g) {
+        if ((g & 31) == 0) prw = (g + lane < c.ng) ? P.pred[base + g + lane] : 0.0f;
+        const float pr = __shfl_sync(full, prw, g & 31);
+        asm volatile("cp.async.wait_group %0;" ::"n"(MW_PF - 1) : "memory");
+        __syncwarp();
+        float step, inv_step;
+        bool done = false;
+        const float dev = acc - pr;                          // how far the running sum is from the exact-arithmetic prediction
+        if (mw_grid(pr, step, inv_step)) {
+            const float kf = rintf(dev * inv_step);
+            if (fabsf(kf) < (float)MW_K) {
+                const int k = (int)kf;
+                if (mw_candidate(pr, step, k) == acc) {
+                    const int idx = k - s_k0[g % MW_PF];
+                    if (idx >= 0 && idx < MW_SEG) acc = s_seg[g % MW_PF][idx];
+                    else acc = __ldcg(P.cand + (base + g) * 2 * MW_K + (k + MW_K));
+                    done = true;
+                    ++n_fast;
+                }
+            }
+        }
+        if (!done) {
+            float x[8];
+            dense_group(P, c, g, x);
+            acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
+            ++n_slow;
+        }
+        __syncwarp();
+        prefetch(g + MW_PF, dev);           // the deviation drifts by a few ulps per group: centre the segment of g + MW_PF on it
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+        P.partial[chain] = acc;
+        if (stats) {
+            atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_fast);
+            atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_slow);
+            atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_seq);
+        }
+    }
+}
+
 constexpr size_t DC_SMEM = (size_t)3 * DC_THREADS * 8 * sizeof(float);
 
 template <int D>
@@ -547,6 +689,24 @@ static void launch_ref_chain(Model *m, float *mat, const float *mean, float *par
     const long long longest = (ne - (long long)(T - 1) * ept + D - 1) / D + 1;      // the last thread takes the remainder
     P.gmax = (int)((longest + 255) / 256) + 1;
     const size_t per = (size_t)T * D * P.gmax;
+    if (mode == 0 && per * 2 * MW_K * sizeof(float) <= ((size_t)1 << 30)) {
+        // mean chains: memoised sequential evaluation of every group + a walk that only looks up (dense_memo_*_kernel)
+        scratch.ensure(per * (sizeof(double) + sizeof(float) + 2 * MW_K * sizeof(float)) + 64);
+        char *q = scratch.as<char>();
+        P.bsum = reinterpret_cast<double *>(q); q += per * sizeof(double);
+        P.cand = reinterpret_cast<float *>(q); q += per * 2 * MW_K * sizeof(float);
+        P.pred = reinterpret_cast<float *>(q);
+        P.tab = nullptr; P.tag = nullptr; P.ridx = nullptr; P.rlist = nullptr; P.rcount = nullptr; P.rcap = 0;
+        long long un = (long long)per;
+        int gr = (int)((un + 7) / 8);
+        if (gr > 148 * 16) gr = 148 * 16;
+        if (gr < 1) gr = 1;
+        GB_LAUNCH(wide_dense_sums_kernel, gr, 256, 0, s, P);
+        GB_LAUNCH(wide_dense_prefix_kernel, T * D, 32, 0, s, P);
+        GB_LAUNCH(dense_memo_sim_kernel, (int)(un < 148 * 8 ? un : 148 * 8), 256, 0, s, P);
+        GB_LAUNCH(dense_memo_walk_kernel, T * D, 32, 0, s, P, stats);
+        return;
+    }
     // memo rows: every group may be risky on a short chain; long inputs get a 64 MB budget (groups beyond it run sequentially)
     size_t rcap = per;
     if (rcap > ((size_t)64 << 20) / (2 * DW_K * sizeof(float))) rcap = ((size_t)64 << 20) / (2 * DW_K * sizeof(float));
