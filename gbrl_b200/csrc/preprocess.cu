@@ -607,9 +607,8 @@ __global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long l
     float acc = 0.0f;
     int n_fast = 0, n_slow = 0, n_seq = 0;
     // segment of group gp around deviation `dev` (absolute, = running sum - prediction of the group the walk is at)
-    auto prefetch = [&](int gp, float dev) {
+    auto prefetch = [&](int gp, float dev, float pr) {       // pr = prediction of group gp (from the register windows: no load here)
         if (gp < c.ng) {
-            const float pr = P.pred[base + gp];
             float step, inv_step;
             int k0 = -MW_K;
             if (mw_grid(pr, step, inv_step)) {
@@ -624,12 +623,17 @@ __global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long l
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // predictions of the current and of the next window of 32 groups (lane = group), loaded a window ahead of their first use
+    float prw = lane < c.ng ? P.pred[base + lane] : 0.0f;
+    float prn = 32 + lane < c.ng ? P.pred[base + 32 + lane] : 0.0f;
 #pragma unroll 1
-    for (int gp = 0; gp < MW_PF; ++gp) prefetch(gp, 0.0f);
-    float prw = 0.0f;                                        // predictions of the current window of 32 groups (lane = group)
+    for (int gp = 0; gp < MW_PF; ++gp) prefetch(gp, 0.0f, __shfl_sync(full, prw, gp));
 #pragma unroll 1
     for (int g = 0; g < c.ng; ++g) {
-        if ((g & 31) == 0) prw = (g + lane < c.ng) ? P.pred[base + g + lane] : 0.0f;
+        if ((g & 31) == 0 && g > 0) {
+            prw = prn;
+            prn = g + 32 + lane < c.ng ? P.pred[base + g + 32 + lane] : 0.0f;
+        }
         const float pr = __shfl_sync(full, prw, g & 31);
         asm volatile("cp.async.wait_group %0;" ::"n"(MW_PF - 1) : "memory");
         __syncwarp();
@@ -656,7 +660,12 @@ __global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long l
             ++n_slow;
         }
         __syncwarp();
-        prefetch(g + MW_PF, dev);           // the deviation drifts by a few ulps per group: centre the segment of g + MW_PF on it
+        {
+            // the deviation drifts by a few ulps per group: centre the segment of group g + MW_PF on it
+            const int gp = g + MW_PF;
+            const float pa = __shfl_sync(full, prw, gp & 31), pb = __shfl_sync(full, prn, gp & 31);
+            prefetch(gp, dev, (gp >> 5) == (g >> 5) ? pa : pb);
+        }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) {
@@ -689,7 +698,8 @@ static void launch_ref_chain(Model *m, float *mat, const float *mean, float *par
     const long long longest = (ne - (long long)(T - 1) * ept + D - 1) / D + 1;      // the last thread takes the remainder
     P.gmax = (int)((longest + 255) / 256) + 1;
     const size_t per = (size_t)T * D * P.gmax;
-    if (mode == 0 && per * 2 * MW_K * sizeof(float) <= ((size_t)1 << 30)) {
+    // (chains beyond ~130 000 elements keep the table walk below: it takes 32 clean groups per step, and long chains are mostly clean)
+    if (mode == 0 && P.gmax <= 513 && per * 2 * MW_K * sizeof(float) <= ((size_t)1 << 30)) {
         // mean chains: memoised sequential evaluation of every group + a walk that only looks up (dense_memo_*_kernel)
         scratch.ensure(per * (sizeof(double) + sizeof(float) + 2 * MW_K * sizeof(float)) + 64);
         char *q = scratch.as<char>();
