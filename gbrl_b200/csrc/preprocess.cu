@@ -535,11 +535,11 @@ __global__ void __launch_bounds__(32) wide_dense_walk_kernel(DenseWide P, long l
 // slow random walk of rounding errors (~0.3 ulp per add: a few ulps per group, tens of ulps per chain).  So EVERY group is
 // evaluated sequentially for 2 * MW_K candidate starts around its predicted incoming sum -- one lane per candidate, all groups of all
 // chains at once: ~1 G independent adds, tens of microseconds for the whole GPU -- and the chain warp only looks its running sum
-// up: one group per ~250 cycles instead of 256 dependent adds.  The segment of the table around the current deviation is fetched
-// MW_PF groups ahead with cp.async, so that the lookup is a shared-memory read.  A start that is not in the table (or not on the
+// up: one group per ~200 cycles instead of 256 dependent adds.  The segment of the table around the current deviation is fetched
+// MW_PF groups ahead into registers, so that the lookup is one shuffle.  A start that is not in the table (or not on the
 // candidate grid) falls back to the sequential chain, which is right by definition; a candidate is accepted only when it EQUALS the
 // running sum bit for bit, so the result is the reference's sequential sum whatever the prediction was.
-constexpr int MW_K = 512;             // candidates on each side of the prediction
+constexpr int MW_K = 256;             // candidates on each side of the prediction (the deviation is ~0.3 ulp x sqrt(adds): sigma 72 after 62 500)
 constexpr int MW_SEG = 64;            // candidates per prefetched segment
 constexpr int MW_PF = 6;              // groups of lookahead
 
@@ -591,83 +591,73 @@ __global__ void __launch_bounds__(256) dense_memo_sim_kernel(DenseWide P) {
     }
 }
 
-__device__ __forceinline__ void mw_cp_async_4(unsigned int dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-
-// one warp per chain
+// one warp per chain.  Everything that does not depend on the running sum is prepared ahead: the per-group grid (prediction, candidate
+// spacing) sits in shared memory, the table segments of the next MW_PF groups in a register ring (the loop is unrolled by MW_PF so
+// that the ring is statically indexed).  What is left on the dependent path of a group is ~10 instructions and one shuffle.
+constexpr int MW_GMAX = 513;          // longest chain the memo walk takes (groups)
 __global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long long *stats) {
     __shared__ __align__(16) float s_wbuf[256];
-    __shared__ float s_seg[MW_PF][MW_SEG];
-    __shared__ int s_k0[MW_PF];
+    __shared__ float4 s_g[MW_GMAX + MW_PF + 1];             // (prediction, step, 1 / step, has a grid) per group
     const unsigned int full = 0xffffffffu;
     const int chain = blockIdx.x, lane = threadIdx.x;
     const DenseChain c = dense_chain_of(P, chain);
     const size_t base = (size_t)chain * P.gmax;
+    for (int g = lane; g < c.ng + MW_PF + 1 && g < MW_GMAX + MW_PF + 1; g += 32) {
+        float4 G = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (g < c.ng) {
+            G.x = P.pred[base + g];
+            G.w = mw_grid(G.x, G.y, G.z) ? 1.0f : 0.0f;
+        }
+        s_g[g] = G;
+    }
+    __syncwarp();
     float acc = 0.0f;
     int n_fast = 0, n_slow = 0, n_seq = 0;
-    // segment of group gp around deviation `dev` (absolute, = running sum - prediction of the group the walk is at)
-    auto prefetch = [&](int gp, float dev, float pr) {       // pr = prediction of group gp (from the register windows: no load here)
-        if (gp < c.ng) {
-            float step, inv_step;
-            int k0 = -MW_K;
-            if (mw_grid(pr, step, inv_step)) {
-                const float kc = rintf(dev * inv_step);
-                k0 = (int)fminf(fmaxf(kc - (float)(MW_SEG / 2), (float)-MW_K), (float)(MW_K - MW_SEG));
-            }
+    float sa[MW_PF], sb[MW_PF];
+    int sk0[MW_PF];
+    // table segment of group gp around deviation `dev` (running sum - prediction, MW_PF groups earlier) -> ring slot j
+    auto prefetch = [&](float &ra, float &rb, int &rk0, int gp, float dev) {
+        const float4 G = s_g[gp];
+        int k0 = -MW_K;
+        if (G.w != 0.0f) {
+            const float kc = rintf(dev * G.z);
+            k0 = (int)fminf(fmaxf(kc - (float)(MW_SEG / 2), (float)-MW_K), (float)(MW_K - MW_SEG));
             const float *src = P.cand + (base + gp) * 2 * MW_K + (k0 + MW_K);
-            const unsigned int dst = (unsigned int)__cvta_generic_to_shared(&s_seg[gp % MW_PF][0]);
-            mw_cp_async_4(dst + lane * 4, src + lane);
-            mw_cp_async_4(dst + (lane + 32) * 4, src + lane + 32);
-            if (lane == 0) s_k0[gp % MW_PF] = k0;
+            ra = __ldcg(src + lane); rb = __ldcg(src + 32 + lane);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        rk0 = k0;
     };
-    // predictions of the current and of the next window of 32 groups (lane = group), loaded a window ahead of their first use
-    float prw = lane < c.ng ? P.pred[base + lane] : 0.0f;
-    float prn = 32 + lane < c.ng ? P.pred[base + 32 + lane] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < MW_PF; ++j) { sa[j] = 0.0f; sb[j] = 0.0f; prefetch(sa[j], sb[j], sk0[j], j, 0.0f); }
 #pragma unroll 1
-    for (int gp = 0; gp < MW_PF; ++gp) prefetch(gp, 0.0f, __shfl_sync(full, prw, gp));
-#pragma unroll 1
-    for (int g = 0; g < c.ng; ++g) {
-        if ((g & 31) == 0 && g > 0) {
-            prw = prn;
-            prn = g + 32 + lane < c.ng ? P.pred[base + g + 32 + lane] : 0.0f;
-        }
-        const float pr = __shfl_sync(full, prw, g & 31);
-        asm volatile("cp.async.wait_group %0;" ::"n"(MW_PF - 1) : "memory");
-        __syncwarp();
-        float step, inv_step;
-        bool done = false;
-        const float dev = acc - pr;                          // how far the running sum is from the exact-arithmetic prediction
-        if (mw_grid(pr, step, inv_step)) {
-            const float kf = rintf(dev * inv_step);
-            if (fabsf(kf) < (float)MW_K) {
-                const int k = (int)kf;
-                if (mw_candidate(pr, step, k) == acc) {
-                    const int idx = k - s_k0[g % MW_PF];
-                    if (idx >= 0 && idx < MW_SEG) acc = s_seg[g % MW_PF][idx];
-                    else acc = __ldcg(P.cand + (base + g) * 2 * MW_K + (k + MW_K));
+    for (int g0 = 0; g0 < c.ng; g0 += MW_PF) {
+#pragma unroll
+        for (int j = 0; j < MW_PF; ++j) {
+            const int g = g0 + j;
+            if (g >= c.ng) break;
+            const float4 G = s_g[g];
+            const float dev = acc - G.x;                     // how far the running sum is from the exact-arithmetic prediction
+            bool done = false;
+            if (G.w != 0.0f) {
+                const float kf = rintf(dev * G.z);
+                if (fabsf(kf) < (float)MW_K && G.x + kf * G.y == acc) {      // the candidate IS the running sum, bit for bit
+                    const int idx = (int)kf - sk0[j];
+                    if ((unsigned int)idx < (unsigned int)MW_SEG) acc = __shfl_sync(full, idx < 32 ? sa[j] : sb[j], idx & 31);
+                    else acc = __ldcg(P.cand + (base + g) * 2 * MW_K + ((int)kf + MW_K));
                     done = true;
                     ++n_fast;
                 }
             }
-        }
-        if (!done) {
-            float x[8];
-            dense_group(P, c, g, x);
-            acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
-            ++n_slow;
-        }
-        __syncwarp();
-        {
-            // the deviation drifts by a few ulps per group: centre the segment of group g + MW_PF on it
-            const int gp = g + MW_PF;
-            const float pa = __shfl_sync(full, prw, gp & 31), pb = __shfl_sync(full, prn, gp & 31);
-            prefetch(gp, dev, (gp >> 5) == (g >> 5) ? pa : pb);
+            if (!done) {
+                float x[8];
+                dense_group(P, c, g, x);
+                acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
+                ++n_slow;
+            }
+            // the deviation drifts by a few ulps per group: centre the segment of group g + MW_PF on today's
+            prefetch(sa[j], sb[j], sk0[j], g + MW_PF, dev);
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) {
         P.partial[chain] = acc;
         if (stats) {
@@ -699,7 +689,7 @@ static void launch_ref_chain(Model *m, float *mat, const float *mean, float *par
     P.gmax = (int)((longest + 255) / 256) + 1;
     const size_t per = (size_t)T * D * P.gmax;
     // (chains beyond ~130 000 elements keep the table walk below: it takes 32 clean groups per step, and long chains are mostly clean)
-    if (mode == 0 && P.gmax <= 513 && per * 2 * MW_K * sizeof(float) <= ((size_t)1 << 30)) {
+    if (mode == 0 && P.gmax <= MW_GMAX && per * 2 * MW_K * sizeof(float) <= ((size_t)1 << 30)) {
         // mean chains: memoised sequential evaluation of every group + a walk that only looks up (dense_memo_*_kernel)
         scratch.ensure(per * (sizeof(double) + sizeof(float) + 2 * MW_K * sizeof(float)) + 64);
         char *q = scratch.as<char>();
