@@ -592,17 +592,22 @@ __global__ void __launch_bounds__(256) dense_memo_sim_kernel(DenseWide P) {
 }
 
 // one warp per chain.  Everything that does not depend on the running sum is prepared ahead: the per-group grid (prediction, candidate
-// spacing) sits in shared memory, the table segments of the next MW_PF groups in a register ring (the loop is unrolled by MW_PF so
-// that the ring is statically indexed).  What is left on the dependent path of a group is ~10 instructions and one shuffle.
+// spacing) sits in shared memory, the table segments of the next MW_PF groups arrive through cp.async (a register ring was measured
+// slower: 12 loads in flight share 6 scoreboards, so every lookup waited for the newest load).  What is left on the dependent path
+// of a group is ~12 instructions and one shared-memory read.
+__device__ __forceinline__ void mw_cp_async_4(unsigned int dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 constexpr int MW_GMAX = 513;          // longest chain the memo walk takes (groups)
 __global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long long *stats) {
     __shared__ __align__(16) float s_wbuf[256];
-    __shared__ float4 s_g[MW_GMAX + MW_PF + 1];             // (prediction, step, 1 / step, has a grid) per group
+    __shared__ float4 s_g[MW_GMAX + 2 * MW_PF + 1];         // (prediction, step, 1 / step, has a grid) per group; zero beyond the chain
+    __shared__ float s_seg[MW_PF][MW_SEG];
     const unsigned int full = 0xffffffffu;
     const int chain = blockIdx.x, lane = threadIdx.x;
     const DenseChain c = dense_chain_of(P, chain);
     const size_t base = (size_t)chain * P.gmax;
-    for (int g = lane; g < c.ng + MW_PF + 1 && g < MW_GMAX + MW_PF + 1; g += 32) {
+    for (int g = lane; g < MW_GMAX + 2 * MW_PF + 1; g += 32) {
         float4 G = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (g < c.ng) {
             G.x = P.pred[base + g];
@@ -613,51 +618,55 @@ __global__ void __launch_bounds__(32) dense_memo_walk_kernel(DenseWide P, long l
     __syncwarp();
     float acc = 0.0f;
     int n_fast = 0, n_slow = 0, n_seq = 0;
-    float sa[MW_PF], sb[MW_PF];
     int sk0[MW_PF];
+    const unsigned int seg_base = (unsigned int)__cvta_generic_to_shared(&s_seg[0][0]) + lane * 4;
     // table segment of group gp around deviation `dev` (running sum - prediction, MW_PF groups earlier) -> ring slot j
-    auto prefetch = [&](float &ra, float &rb, int &rk0, int gp, float dev) {
+    // (the copies are unconditional: a group without a grid reads the head of its own row, beyond the chain the head of the last row)
+    const int g_last = c.ng > 0 ? c.ng - 1 : 0;
+    auto prefetch = [&](int j, int &rk0, int gp, float dev) {
         const float4 G = s_g[gp];
-        int k0 = -MW_K;
-        if (G.w != 0.0f) {
-            const float kc = rintf(dev * G.z);
-            k0 = (int)fminf(fmaxf(kc - (float)(MW_SEG / 2), (float)-MW_K), (float)(MW_K - MW_SEG));
-            const float *src = P.cand + (base + gp) * 2 * MW_K + (k0 + MW_K);
-            ra = __ldcg(src + lane); rb = __ldcg(src + 32 + lane);
-        }
+        const float kc = rintf(dev * G.z);                   // G.z == 0 where there is no grid
+        const int k0 = (int)fminf(fmaxf(kc - (float)(MW_SEG / 2), (float)-MW_K), (float)(MW_K - MW_SEG));
+        const float *src = P.cand + (base + min(gp, g_last)) * 2 * MW_K + (k0 + MW_K) + lane;
+        mw_cp_async_4(seg_base + j * (MW_SEG * 4), src);
+        mw_cp_async_4(seg_base + j * (MW_SEG * 4) + 128, src + 32);
+        asm volatile("cp.async.commit_group;" ::: "memory");
         rk0 = k0;
     };
 #pragma unroll
-    for (int j = 0; j < MW_PF; ++j) { sa[j] = 0.0f; sb[j] = 0.0f; prefetch(sa[j], sb[j], sk0[j], j, 0.0f); }
+    for (int j = 0; j < MW_PF; ++j) prefetch(j, sk0[j], j, 0.0f);
 #pragma unroll 1
     for (int g0 = 0; g0 < c.ng; g0 += MW_PF) {
 #pragma unroll
         for (int j = 0; j < MW_PF; ++j) {
             const int g = g0 + j;
-            if (g >= c.ng) break;
-            const float4 G = s_g[g];
+            const float4 G = s_g[g];                         // beyond the chain: no grid, nothing to do
+            asm volatile("cp.async.wait_group %0;" ::"n"(MW_PF - 1) : "memory");
+            __syncwarp();
             const float dev = acc - G.x;                     // how far the running sum is from the exact-arithmetic prediction
             bool done = false;
             if (G.w != 0.0f) {
                 const float kf = rintf(dev * G.z);
                 if (fabsf(kf) < (float)MW_K && G.x + kf * G.y == acc) {      // the candidate IS the running sum, bit for bit
                     const int idx = (int)kf - sk0[j];
-                    if ((unsigned int)idx < (unsigned int)MW_SEG) acc = __shfl_sync(full, idx < 32 ? sa[j] : sb[j], idx & 31);
+                    if ((unsigned int)idx < (unsigned int)MW_SEG) acc = s_seg[j][idx];
                     else acc = __ldcg(P.cand + (base + g) * 2 * MW_K + ((int)kf + MW_K));
                     done = true;
                     ++n_fast;
                 }
             }
-            if (!done) {
+            if (!done && g < c.ng) {
                 float x[8];
                 dense_group(P, c, g, x);
                 acc = seq::warp_seq_block<8>(acc, x, s_wbuf, n_seq);
                 ++n_slow;
             }
             // the deviation drifts by a few ulps per group: centre the segment of group g + MW_PF on today's
-            prefetch(sa[j], sb[j], sk0[j], g + MW_PF, dev);
+            __syncwarp();
+            prefetch(j, sk0[j], g + MW_PF, dev);
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) {
         P.partial[chain] = acc;
         if (stats) {
