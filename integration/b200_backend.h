@@ -27,7 +27,7 @@ class GBRL_B200 {
         c.verbose = verbose; c.device_ordinal = 0;
         c.ref_threads = omp_get_max_threads();                 // reproduce this host's reduction partition
         c.tie_replay = 1; c.band_kappa = 0.f; c.use_subtraction = 1;   // engine defaults (near-tie replay on, band = 6 noise units)
-        c.hist_variant = 0; c.replay_variant = 0;                      // streaming histogram kernel, GPU-wide replay chains
+        c.hist_variant = 0; c.replay_variant = 0;                      // streaming histogram kernel; GPU-wide replay chains on side streams (speculative levels)
         ck(gbrl_b200_create(&c, &h_));
     }
     ~GBRL_B200() { gbrl_b200_destroy(h_); }
