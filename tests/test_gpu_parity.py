@@ -266,6 +266,19 @@ def test_targets_with_huge_dynamic_range():
         assert np.all(np.abs(vo - vg) <= TOL * np.maximum(1.0, np.abs(vo))), np.abs(vo - vg).max()
 
 
+@pytest.mark.parametrize("d,score,grow", [(20, "cosine", "greedy"), (48, "L2", "greedy"), (48, "cosine", "oblivious"), (64, "L2", "oblivious")])
+def test_wide_outputs(d, score, grow):
+    """output_dim beyond 16: the split scan is instantiated for 32 and 64 output dimensions (split.cu launch_scan), the histogram takes
+    two dimensions per pass, the replay runs one lane per output dimension."""
+    n, f = 2500, 7
+    X, y = synth(n, f, d, seed=d)
+    kw = dict(input_dim=f, output_dim=d, max_depth=3, n_bins=48, par_th=10, split_score_func=score, generator_type="quantile",
+              batch_size=n, grow_policy=grow)
+    o, g = _pair(ref_threads=2, lrs=[(0.1, 0, d)], **kw)
+    boosting_loop([o, g], X, y, 2)
+    assert g.m.get_stats()["replay_overflow"] == 0
+
+
 @pytest.mark.parametrize("n", [1, 2, 37, 300])
 def test_tiny_inputs(n):
     """n_samples below n_bins+1 (quantile ranks collapse), single-sample nodes, empty children."""
