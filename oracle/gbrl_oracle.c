@@ -5,7 +5,7 @@
  * checker for the CUDA engine: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference leg may load it.  The product path (gbrl_b200/) never links, imports or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks this file bit-for-bit against the
+ * Parity status: PINNED.  tests/test_oracle.py checks this file bit-for-bit against the
  * reference itself (oracle/_ref, compiled from /root/reference by oracle/Makefile) and against the
  * committed golden vectors under tests/golden/ that were generated from the reference.
  *
