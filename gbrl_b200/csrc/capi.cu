@@ -194,7 +194,14 @@ static void sync_ctl(Model &m, cudaStream_t s) {
     m.ens.n_leaves_ub = h.n_leaves;
     GB_CHECK(h.n_trees == m.ens.n_trees, "internal error: device/host tree count mismatch");
     m.replay_items = h.stat_replay_items; m.replay_nodes = h.stat_replay_nodes;
-    m.nodes_evaluated = h.stat_nodes_evaluated; m.replay_overflow = h.replay_overflow;
+    m.nodes_evaluated = h.stat_nodes_evaluated;
+    if (h.replay_overflow > m.replay_overflow && m.replay_overflow == 0) {
+        // not silent: a node (or level) whose near-tie list did not fit was decided on the exact tier alone, which can differ from
+        // the reference where the reference's own rounding noise decides (two tiers)
+        fprintf(stderr, "gbrl_b200: warning: the near-tie replay list overflowed (%d node(s)); those decisions use exact-arithmetic "
+                        "scores only. See get_stats()['replay_overflow'].\n", h.replay_overflow);
+    }
+    m.replay_overflow = h.replay_overflow;
     m.hist_rows = h.stat_hist_rows;
     m.chain_fast = h.stat_chain_fast; m.chain_slow = h.stat_chain_slow; m.chain_seq = h.stat_chain_seq; m.replay_flips = h.stat_replay_flips;
     m.max_noise = __builtin_bit_cast(float, h.stat_max_noise);
