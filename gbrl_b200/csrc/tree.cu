@@ -11,6 +11,7 @@
 //                          a depth-0 leaf never matches (passed=false, :559-564) and keeps value 0
 #include "engine.cuh"
 #include <utility>
+#include <cstddef>
 
 namespace gb {
 
@@ -280,8 +281,8 @@ void launch_finalize_tree(Model &m, const float *raw_grads, int N, int cur, cuda
 // (replay items, planes, summaries; the level's row order and histograms are kept too).  A verification kernel behind each
 // replay compares the decision in the reference's arithmetic with the one taken and records the lowest level that differs.
 // At the end of the tree the host reads that one word: none -> the tree IS the reference's tree; level L -> node states and
-// row -> node ids are returned to level L (rollback_kernel; order and histograms of L are still there), L is decided again
-// with its replay on the critical path, and the levels below L are grown speculatively again.  L strictly increases, so
+// row -> node ids are returned to level L (rollback_kernel; order, histograms, scan results and replayed scores of L are still
+// there), L is decided again -- this time from the replayed scores -- and the levels below L are grown speculatively again.  L strictly increases, so
 // a tree costs at most max_depth returns; the result never depends on speculation.
 namespace {
 struct SlotBind {            // swaps a slot's replay buffers into the workspace for the launches of one level
@@ -314,23 +315,20 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
     { ProfScope ps(m, P_PRE, s); raw_grad_scale(m, raw_grads, N, s); launch_init_tree(m, N, s); }
     const size_t slot_bytes = (size_t)ws.nT * NB * FT * (1 + ws.D) * sizeof(long long);
     if (md > 0) { ProfScope ps(m, P_DECIDE, s); launch_plan_level(m, 0, s); }
-    int start = 0, sync_level = -1;      // sync_level: the level that is decided with its replay on the critical path (after a return)
+    int start = 0;
     for (;;) {
         for (int level = start; level < md; ++level) {
             if (spec) {
                 ws.hist_p[level & 1] = ws.hist_lv[level].as<long long>();
                 ws.order_p[0] = ws.order_lv[level].as<int>(); ws.order_p[1] = ws.order_lv[level + 1].as<int>();
             }
-            if (level != sync_level) {         // the histograms of a level that is returned to are still in place
-                { ProfScope ps(m, P_DECIDE, s); GB_CUDA(cudaMemsetAsync(ws.hist_p[level & 1], 0, slot_bytes << level, s)); }
-                { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
-                if (m.world > 1) { ProfScope ps(m, P_ALLREDUCE, s);
-                    dist_allreduce_hist(m, ws.hist_p[level & 1], (slot_bytes << level) / sizeof(long long), s); }
-            }
+            { ProfScope ps(m, P_DECIDE, s); GB_CUDA(cudaMemsetAsync(ws.hist_p[level & 1], 0, slot_bytes << level, s)); }
+            { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
+            if (m.world > 1) { ProfScope ps(m, P_ALLREDUCE, s);
+                dist_allreduce_hist(m, ws.hist_p[level & 1], (slot_bytes << level) / sizeof(long long), s); }
             { ProfScope ps(m, P_SCAN, s); launch_scan(m, level, s); }
-            ReplaySlot *slot = (spec && level != sync_level) ? &ws.slots[level] : nullptr;
+            ReplaySlot *slot = spec ? &ws.slots[level] : nullptr;
             SlotBind bind(ws, slot);
-            ws.count_stats = level != sync_level;
             { ProfScope ps(m, P_SELECT, s); launch_select_and_replay(m, X, level, s, slot); }
             { ProfScope ps(m, P_DECIDE, s);      // (the node states of the level were snapshotted by the selection kernel)
               launch_decide(m, level, s, slot == nullptr);
@@ -346,11 +344,27 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
         GB_CUDA(cudaStreamSynchronize(s));
         flip = *ws.h_spec_flag;
         if (flip >= (unsigned int)md) break;
-        // the replay changed the decision of level `flip`: return to it
+        // The replay changed the decision of level L: return to it.  Its scan results (best candidate, replay list: per-node arrays)
+        // and its replayed scores (the level's slot) are all still in place, so the level is simply DECIDED again, this time with
+        // the replay, then partitioned; the levels below are grown speculatively again.
+        const int L = (int)flip;
         m.spec_rollbacks += 1;
-        { ProfScope ps(m, P_SPEC, s); launch_rollback(m, (int)flip, s); }
-        start = sync_level = (int)flip;
-        if (start > 0) ws.hist_p[(start + 1) & 1] = ws.hist_lv[start - 1].as<long long>();      // the parent level of the derived nodes
+        { ProfScope ps(m, P_SPEC, s); launch_rollback(m, L, s); }
+        ws.hist_p[L & 1] = ws.hist_lv[L].as<long long>();
+        ws.order_p[0] = ws.order_lv[L].as<int>(); ws.order_p[1] = ws.order_lv[L + 1].as<int>();
+        {
+            ReplaySlot &sl = ws.slots[L];
+            SlotBind bind(ws, &sl);
+            ProfScope ps(m, P_DECIDE, s);
+            // the oblivious decision reads the level's exact-tier winner and candidate count from the control block: the snapshot's
+            constexpr size_t o0 = offsetof(Ctl, obl_best_idx), o1 = offsetof(Ctl, obl_band) + sizeof(float);
+            GB_CUDA(cudaMemcpyAsync(ws.ctl.as<char>() + o0, sl.ctl_snap.as<char>() + o0, o1 - o0, cudaMemcpyDeviceToDevice, s));
+            ws.count_stats = false;          // verify_kernel counted this level already
+            launch_decide(m, L, s, true);
+            ws.count_stats = true;
+        }
+        { ProfScope ps(m, P_PART, s); launch_partition(m, X, L, 0, s); }
+        start = L + 1;
     }
     ws.count_stats = true;
     { ProfScope ps(m, P_FIN, s); launch_finalize_tree(m, raw_grads, N, 0, s); }
