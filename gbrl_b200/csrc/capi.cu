@@ -85,6 +85,8 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
     const size_t n1 = (size_t)(N > 0 ? N : 1);
     ws.order[0].ensure(n1 * sizeof(int)); ws.order[1].ensure(n1 * sizeof(int));
     ws.order_p[0] = ws.order[0].as<int>(); ws.order_p[1] = ws.order[1].as<int>();
+    ws.pnode[0].ensure(n1 * sizeof(int)); ws.pnode[1].ensure(n1 * sizeof(int));
+    ws.pnode_p[0] = ws.pnode[0].as<int>(); ws.pnode_p[1] = ws.pnode[1].as<int>();
     ws.nid.ensure(n1 * sizeof(int)); ws.rflag.ensure(n1 * sizeof(uint16_t) + 16);
     {   // chunk totals / prefixes of the partition + its "CTAs done" counter (kept zero between launches)
         const int cap = ceil_div((int)n1, 2048) + 1;
@@ -140,7 +142,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
         size_t extra = 0;
         if (md > 0) {
             const size_t per_slot = (size_t)ws.replay_cap * 20 + n1 * D * 4 + (size_t)ws.rbits_words * 4 + (D <= 2 ? rwide_bytes : 0);
-            extra = (size_t)md * per_slot + (slot_bytes << md) + (size_t)(md + 1) * n1 * 4;
+            extra = (size_t)md * per_slot + (slot_bytes << md) + (size_t)(md + 1) * n1 * 8;
         }
         ws.spec = m.cfg.tie_replay && md > 0 && !(m.cfg.replay_variant & 2) && !env_off && extra <= ((size_t)24 << 30);
         if (ws.spec) {
@@ -150,6 +152,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
                 sl.ctl_snap.ensure(sizeof(Ctl));
                 ws.hist_lv[l].ensure(slot_bytes << l);
                 ws.order_lv[l].ensure(n1 * sizeof(int));
+                ws.pnode_lv[l].ensure(n1 * sizeof(int));
                 if (!sl.stream) {
                     int lo = 0, hi = 0;
                     GB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority: the side work never delays the tree
@@ -160,6 +163,7 @@ static void prepare_workspace(Model &m, int N, int F, cudaStream_t s) {
                 }
             }
             ws.order_lv[md].ensure(n1 * sizeof(int));
+            ws.pnode_lv[md].ensure(n1 * sizeof(int));
             ws.state_snap.ensure((size_t)ws.MAXN * sizeof(int));
             ws.spec_flag.ensure(sizeof(unsigned int));
             if (!ws.h_spec_flag) GB_CUDA(cudaMallocHost(&ws.h_spec_flag, sizeof(unsigned int)));

@@ -9,7 +9,8 @@
 //   bg       [N x D]  fp32                build_grads (fitter.cpp:57-64)
 //   order    [N] int32 (ping-pong)        rows grouped by tree node, ascending inside a node
 //                                         (== the reference's per-node sample_indices, node.cpp:86-96)
-//   nid      [N] int32                    heap id of the node each row currently sits in
+//   pnode    [N] int32 (ping-pong)        heap id of the node the row at each POSITION of `order` sits in (coalesced for the
+//                                         partition and the leaf sums; `nid`, the same by ROW, is written once per tree)
 //   hist     [slot][nT][256][32][1+D] i64 per-node (count, sum of fixed-point build_grads) per
 //                                         (feature, code-1); two level buffers (parent / current)
 //   scores   [slot][F*n_bins] fp32        per-(node,candidate) score (exact-arithmetic path)
@@ -109,7 +110,7 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     int codes_rows = 0;             // rows of the code matrix (tile stride); >= N when a tree is grown on a mini-batch
     int row_offset = 0;             // first row of the current mini-batch inside the code matrix
     DevBuf bgq;                          // build_grads as fixed point, split (lo 18 bits, hi): what the histogram atomics add
-    DevBuf codes, thr, thrT, bg, order[2], nid, rflag, chunk_sums, hist[2], scores, cand_flags;
+    DevBuf codes, thr, thrT, bg, order[2], pnode[2], nid, rflag, chunk_sums, hist[2], scores, cand_flags;
     int chunk_cap = 0;                   // capacity of chunk_sums (entries); entry [chunk_cap] is the partition's done counter
     DevBuf items, replay, replay_scores, nodes, ctl, tile_best, obl_tot, sort_tmp, colbuf[2], lrs;
     DevBuf rgrad, rbits, rmeta;          // replay streams: order-space build_grads, side-bit planes, per-item offsets / modes / counts
@@ -124,10 +125,11 @@ struct Workspace {           // sized for (N, F, D, depth); reused across calls 
     // current / next row order and the histogram buffer of (level & 1): ws.order[] / ws.hist[], or -- while a tree is grown
     // speculatively -- the per-level buffers below (a rollback needs the order and the histograms of the level it returns to)
     int *order_p[2] = {nullptr, nullptr};
+    int *pnode_p[2] = {nullptr, nullptr};
     long long *hist_p[2] = {nullptr, nullptr};
     bool spec = false;                   // speculative replay enabled for this workspace shape
     bool count_stats = true;             // false while a rolled-back level is decided a second time
-    DevBuf order_lv[MAX_DEPTH_SUPPORTED + 1], hist_lv[MAX_DEPTH_SUPPORTED];
+    DevBuf order_lv[MAX_DEPTH_SUPPORTED + 1], pnode_lv[MAX_DEPTH_SUPPORTED + 1], hist_lv[MAX_DEPTH_SUPPORTED];
     ReplaySlot slots[MAX_DEPTH_SUPPORTED];
     DevBuf state_snap, spec_flag;        // node states of every level before its decision; lowest level whose decision the replay changed
     unsigned int *h_spec_flag = nullptr; // pinned host copy of spec_flag

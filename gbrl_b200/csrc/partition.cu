@@ -19,7 +19,7 @@ constexpr int PART_CHUNK = 2048;   // rows per CTA (256 threads x 8 consecutive 
 // chunk prefixes (so that no separate scan launch is needed).
 __global__ void __launch_bounds__(256)
 part_flag_scan_kernel(const float *__restrict__ X, int F, const uint16_t *__restrict__ codesT, long long stride, int row_offset,
-                      const int *__restrict__ order, const int *__restrict__ nid, NodeArrays na, uint16_t *__restrict__ rloc,
+                      const int *__restrict__ order, const int *__restrict__ pnode, NodeArrays na, uint16_t *__restrict__ rloc,
                       int *__restrict__ chunk_sums, int *__restrict__ done_counter, int N, int n_chunks) {
     __shared__ int s_warp[8];
     __shared__ int s_last;
@@ -31,10 +31,10 @@ part_flag_scan_kernel(const float *__restrict__ X, int F, const uint16_t *__rest
         const int k = k0 + j;
         int fl = 0;
         if (k < N) {
-            const int i = order[k];
-            const int h = nid[i];
+            const int h = pnode[k];                  // node of the row at this position (coalesced; the row id is only needed for the code)
             // x > thr[f][j]  <=>  code(x) > j  (candidates.cu): 2 bytes of the feature-major codes per row
             if (na.state[h] == NODE_SPLIT) {
+                const int i = order[k];
                 if (codesT != nullptr) fl = (int)codesT[(size_t)na.split_f[h] * stride + row_offset + i] > na.split_j[h] ? 1 : 0;
                 else fl = X[(size_t)i * F + na.split_f[h]] > na.split_thr[h] ? 1 : 0;          // node.cpp:89
             }
@@ -87,23 +87,23 @@ part_flag_scan_kernel(const float *__restrict__ X, int F, const uint16_t *__rest
 
 // Pass 2: stable scatter.  R[k] = chunk prefix + in-chunk prefix; rows right of the split go behind the node's left rows.
 __global__ void __launch_bounds__(256)
-part_scatter_kernel(const int *__restrict__ order_in, int *__restrict__ order_out, int *__restrict__ nid,
+part_scatter_kernel(const int *__restrict__ order_in, int *__restrict__ order_out, const int *__restrict__ pnode_in, int *__restrict__ pnode_out,
                     const uint16_t *__restrict__ rloc, const int *__restrict__ chunk_prefix, NodeArrays na, int N) {
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= N) return;
     const int i = order_in[k];
-    const int h = nid[i];
-    if (na.state[h] != NODE_SPLIT) { order_out[k] = i; return; }
+    const int h = pnode_in[k];
+    if (na.state[h] != NODE_SPLIT) { order_out[k] = i; pnode_out[k] = h; return; }
     const int s0 = na.seg_start[h];
     const unsigned int pk = rloc[k], p0 = rloc[s0];
     const int rbefore = (chunk_prefix[k / PART_CHUNK] + (int)(pk & 0x7fffu)) - (chunk_prefix[s0 / PART_CHUNK] + (int)(p0 & 0x7fffu));
     if (pk >> 15) {
         const int nl = na.seg_len[2 * h + 1];
         order_out[s0 + nl + rbefore] = i;
-        nid[i] = 2 * h + 2;
+        pnode_out[s0 + nl + rbefore] = 2 * h + 2;
     } else {
         order_out[s0 + (k - s0) - rbefore] = i;
-        nid[i] = 2 * h + 1;
+        pnode_out[s0 + (k - s0) - rbefore] = 2 * h + 1;
     }
 }
 
@@ -116,11 +116,12 @@ void launch_partition(Model &m, const float *X, int level, int cur, cudaStream_t
     const int n_chunks = ceil_div(N, PART_CHUNK);
     // ws.rflag holds the packed u16 (flag, in-chunk prefix) per position; chunk_sums[n_chunks] is the done counter (zero between launches)
     GB_LAUNCH(part_flag_scan_kernel, n_chunks, 256, 0, s, X, ws.F, ws.use_codesT ? ws.codesT.as<uint16_t>() : nullptr, ws.codesT_stride,
-              ws.row_offset, ws.order_p[0], ws.nid.as<int>(), ws.na, ws.rflag.as<uint16_t>(), ws.chunk_sums.as<int>(),
+              ws.row_offset, ws.order_p[0], ws.pnode_p[0], ws.na, ws.rflag.as<uint16_t>(), ws.chunk_sums.as<int>(),
               ws.chunk_sums.as<int>() + ws.chunk_cap, N, n_chunks);
-    GB_LAUNCH(part_scatter_kernel, ceil_div(N, 256), 256, 0, s, ws.order_p[0], ws.order_p[1], ws.nid.as<int>(),
+    GB_LAUNCH(part_scatter_kernel, ceil_div(N, 256), 256, 0, s, ws.order_p[0], ws.order_p[1], ws.pnode_p[0], ws.pnode_p[1],
               ws.rflag.as<uint16_t>(), ws.chunk_sums.as<int>(), ws.na, N);
     std::swap(ws.order_p[0], ws.order_p[1]);
+    std::swap(ws.pnode_p[0], ws.pnode_p[1]);
 }
 
 }  // namespace gb

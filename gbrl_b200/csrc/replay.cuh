@@ -26,7 +26,7 @@ struct StreamParams {
     int *nright;               // [n_items]
     long long cap_words;
     int replay_cap, N, oblivious;
-    const int *nid;
+    const int *pnode;          // node of the row at each position of `order`
     int wide;                  // 1: parents get a (zero) plane too and every streamed item is mode 0 (replay_wide.cu)
 };
 
@@ -93,7 +93,7 @@ __device__ __forceinline__ void replay_gather_body(const ReplayParams &P, NodeAr
     const bool all = S.oblivious != 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S.N; k += gridDim.x * blockDim.x) {
         const int row = P.order[k];
-        if (!all && na.rep_count[S.nid[row]] <= 0) continue;
+        if (!all && na.rep_count[S.pnode[k]] <= 0) continue;
         for (int d = 0; d < D; ++d) S.G[(size_t)k * D + d] = P.bg[(size_t)row * D + d];
     }
 }

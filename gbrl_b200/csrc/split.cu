@@ -1376,20 +1376,15 @@ __global__ void __launch_bounds__(1024) verify_kernel(DecideParams P, NodeArrays
     }
 }
 
-// Return to the state before the decision of level L: node states of that level from their snapshot, deeper nodes gone, every
-// row back in its ancestor at level L (the row ORDER and the histograms of level L are still in their per-level buffers).
-__global__ void __launch_bounds__(256) rollback_kernel(NodeArrays na, const int *state_snap, int *nid, int N, int MAXN, int L, unsigned int *flip_level) {
+// Return to the state before the decision of level L: node states of that level from their snapshot, deeper nodes gone (the row
+// order, the node of every position and the histograms of level L are still in their per-level buffers).
+__global__ void __launch_bounds__(256) rollback_kernel(NodeArrays na, const int *state_snap, int MAXN, int L, unsigned int *flip_level) {
     const int lo = level_base(L), hi = level_base(L + 1);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *flip_level = 0xffffffffu;
     if (i < MAXN) {
         if (i >= hi) na.state[i] = NODE_NONE;
         else if (i >= lo) na.state[i] = state_snap[i];
-    }
-    if (i < N) {
-        int h = nid[i];
-        while (h >= hi) h = (h - 1) >> 1;
-        nid[i] = h;
     }
 }
 
@@ -1489,7 +1484,7 @@ void launch_select_and_replay(Model &m, const float *X, int level, cudaStream_t 
         S.cap_words = force_direct ? 0 : ws.rbits_words; S.replay_cap = ws.replay_cap; S.N = ws.N;
         // a speculative level gathers every row: `nid` moves on with the deeper levels while this level is replayed
         S.oblivious = (obl || slot) ? 1 : 0;
-        S.nid = ws.nid.as<int>();
+        S.pnode = ws.pnode_p[0];
         S.wide = (D <= 2 && (m.cfg.replay_variant & 1) == 0) ? 1 : 0;
         GB_LAUNCH(replay_plan_kernel, 1, 1024, 0, rs, R, ws.na, S);
         GB_LAUNCH(replay_gather_kernel, ws.n_sms * replay_grid_mult(slot != nullptr), 256, 0, rs, R, ws.na, S);
@@ -1562,8 +1557,7 @@ void launch_verify(Model &m, int level, cudaStream_t s, ReplaySlot &slot) {
 
 void launch_rollback(Model &m, int level, cudaStream_t s) {
     Workspace &ws = m.ws;
-    const int n = ws.N > ws.MAXN ? ws.N : ws.MAXN;
-    GB_LAUNCH(rollback_kernel, ceil_div(n, 256), 256, 0, s, ws.na, ws.state_snap.as<int>(), ws.nid.as<int>(), ws.N, ws.MAXN, level,
+    GB_LAUNCH(rollback_kernel, ceil_div(ws.MAXN, 256), 256, 0, s, ws.na, ws.state_snap.as<int>(), ws.MAXN, level,
               ws.spec_flag.as<unsigned int>());
 }
 

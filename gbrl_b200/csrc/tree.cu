@@ -16,9 +16,9 @@
 namespace gb {
 
 // ---------------------------------------------------------------- init
-__global__ void init_rows_kernel(int *order, int *nid, int N) {
+__global__ void init_rows_kernel(int *order, int *pnode, int N) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < N) { order[k] = k; nid[k] = 0; }
+    if (k < N) { order[k] = k; pnode[k] = 0; }
 }
 
 __global__ void init_nodes_kernel(NodeArrays na, Ctl *ctl, int MAXN, int N, int D, int max_depth, int oblivious) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) root_totals_kernel(const float *__restric
 
 void launch_init_tree(Model &m, int N, cudaStream_t s) {
     Workspace &ws = m.ws;
-    if (N > 0) GB_LAUNCH(init_rows_kernel, ceil_div(N, 256), 256, 0, s, ws.order_p[0], ws.nid.as<int>(), N);
+    if (N > 0) GB_LAUNCH(init_rows_kernel, ceil_div(N, 256), 256, 0, s, ws.order_p[0], ws.pnode_p[0], N);
     GB_LAUNCH(init_nodes_kernel, 1, 256, 0, s, ws.na, ws.ctl.as<Ctl>(), ws.MAXN, N, ws.D, m.cfg.max_depth,
               m.cfg.grow_policy == GBRL_B200_GROW_OBLIVIOUS);
     if (N > 0) {
@@ -204,14 +204,19 @@ __global__ void __launch_bounds__(256) finalize_oblivious_kernel(NodeArrays na, 
 // ---------------------------------------------------------------- leaf values
 // rows are grouped by node in `order`, so a warp usually sees a single leaf: warp-reduce then one REDG per dim
 __global__ void __launch_bounds__(256)
-leaf_sums_kernel(const float *__restrict__ raw, const int *__restrict__ order, const int *__restrict__ nid, NodeArrays na,
+leaf_sums_kernel(const float *__restrict__ raw, const int *__restrict__ order, const int *__restrict__ pnode, int *__restrict__ nid, NodeArrays na,
                  const Ctl *ctl, long long *leaf_acc /*[leaves][1+D]*/, int N, int D) {
     const float scale = exp2f((float)ctl->qexp_raw);
     const int lane = threadIdx.x & 31;
     for (long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; k0 < N; k0 += (long long)gridDim.x * blockDim.x) {
         const long long k = k0 + lane;
         int li = -1, i = 0;
-        if (k < N) { i = order[k]; li = na.leaf_index[nid[i]]; }
+        if (k < N) {
+            i = order[k];
+            const int h = pnode[k];
+            nid[i] = h;                      // by row, once per tree: launch_update_preds_from_nodes reads it
+            li = na.leaf_index[h];
+        }
         const int li0 = __shfl_sync(0xffffffffu, li, 0);
         const bool uniform = __all_sync(0xffffffffu, li == li0);
         if (uniform) {
@@ -266,7 +271,7 @@ void launch_finalize_tree(Model &m, const float *raw_grads, int N, int cur, cuda
     if (N > 0) {
         int grid = ceil_div(N, 256);
         if (grid > 2368) grid = 2368;
-        GB_LAUNCH(leaf_sums_kernel, grid, 256, 0, s, raw_grads, ws.order_p[0], ws.nid.as<int>(), ws.na, ctl,
+        GB_LAUNCH(leaf_sums_kernel, grid, 256, 0, s, raw_grads, ws.order_p[0], ws.pnode_p[0], ws.nid.as<int>(), ws.na, ctl,
                   ws.loss_parts.as<long long>(), N, D);
     }
     GB_LAUNCH(leaf_values_kernel, ceil_div((1 << md) * D, 256), 256, 0, s, ws.loss_parts.as<long long>(), ctl, E, ws.na, D, md, obl ? 1 : 0, ws.MAXN);
@@ -305,10 +310,12 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
     const bool spec = ws.spec && md > 0 && N > 0;
     if (spec) {
         ws.order_p[0] = ws.order_lv[0].as<int>(); ws.order_p[1] = ws.order_lv[1].as<int>();
+        ws.pnode_p[0] = ws.pnode_lv[0].as<int>(); ws.pnode_p[1] = ws.pnode_lv[1].as<int>();
         GB_CUDA(cudaMemsetAsync(ws.spec_flag.p, 0xff, sizeof(unsigned int), s));
         m.spec_trees += 1;
     } else {
         ws.order_p[0] = ws.order[0].as<int>(); ws.order_p[1] = ws.order[1].as<int>();
+        ws.pnode_p[0] = ws.pnode[0].as<int>(); ws.pnode_p[1] = ws.pnode[1].as<int>();
         ws.hist_p[0] = ws.hist[0].as<long long>(); ws.hist_p[1] = ws.hist[1].as<long long>();
     }
     ws.count_stats = true;
@@ -321,6 +328,7 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
             if (spec) {
                 ws.hist_p[level & 1] = ws.hist_lv[level].as<long long>();
                 ws.order_p[0] = ws.order_lv[level].as<int>(); ws.order_p[1] = ws.order_lv[level + 1].as<int>();
+                ws.pnode_p[0] = ws.pnode_lv[level].as<int>(); ws.pnode_p[1] = ws.pnode_lv[level + 1].as<int>();
             }
             { ProfScope ps(m, P_DECIDE, s); GB_CUDA(cudaMemsetAsync(ws.hist_p[level & 1], 0, slot_bytes << level, s)); }
             { ProfScope ps(m, P_HIST, s); launch_histogram(m, level, s); }
@@ -352,6 +360,7 @@ void grow_tree(Model &m, const float *X, const float *raw_grads, int N, int F, c
         { ProfScope ps(m, P_SPEC, s); launch_rollback(m, L, s); }
         ws.hist_p[L & 1] = ws.hist_lv[L].as<long long>();
         ws.order_p[0] = ws.order_lv[L].as<int>(); ws.order_p[1] = ws.order_lv[L + 1].as<int>();
+        ws.pnode_p[0] = ws.pnode_lv[L].as<int>(); ws.pnode_p[1] = ws.pnode_lv[L + 1].as<int>();
         {
             ReplaySlot &sl = ws.slots[L];
             SlotBind bind(ws, &sl);
