@@ -67,11 +67,18 @@ def _replay_steps(m, X, y, exp, bias, lrs, iters, oblivious):
         m.step(X, None, (p - y).astype(np.float32))
 
 
+# fixtures whose generation from the reference (hours of CPU time) ended after the round's last GPU call; see the skip message
+UNVALIDATED = ("c5", "c2s")
+
+
 @pytest.mark.parametrize("name", ["c1", "c1_l2", "s_greedy", "s_obl", "c2", "c2s", "j3", "c3", "c5"])
 def test_full_size_golden_from_reference(name):
     path = os.path.join(GOLDEN_DIR, "full_%s.npz" % name)
     if not os.path.exists(path):
         pytest.skip("tests/golden/full_%s.npz not generated (tests/golden/make_golden_full.py %s)" % (name, name))
+    if name in UNVALIDATED and os.environ.get("GBRL_B200_UNVALIDATED_GOLDENS", "") != "1":
+        pytest.skip("full_%s.npz was generated after this round's GPU budget was spent: the engine has not been run against it yet "
+                    "(GBRL_B200_UNVALIDATED_GOLDENS=1 runs it)" % name)
     z = np.load(path, allow_pickle=False)
     n, f, d, depth, bins, iters, batch, seed, T = [int(v) for v in z["cfg"]]
     lrs = [(float(a), int(b), int(c)) for a, b, c in z["lrs"]]
